@@ -1,0 +1,172 @@
+"""
+Golden-vector generator  --  runs ONLY in the build container, where the
+reference is mounted at /root/reference.  TEST INFRASTRUCTURE.
+
+It imports the *unmodified* reference modules (`lib.setup_model.setup_model /
+setup_predictor`), loads the seeded synthetic weights of `tests/synth.py` into
+them, runs the seed+rollout path of `src/05_evaluate_PlaySlot.py:112-139`
+(`savi(videos, decode=False)` -> `forward_multiple_samples(use_posterior=True)`
+-> `savi.decode`) on seeded synthetic video and stores the outputs as small
+fixtures under tests/golden/.  The fixtures carry the config dicts and the
+state_dict manifests (key -> shape) so that nothing has to be read from
+/root/reference at test time.
+
+Usage:  python oracle/make_golden.py            (writes tests/golden/*.pt)
+"""
+import copy
+import json
+import os
+import sys
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("PLAYSLOT_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.dont_write_bytecode = True
+
+from synth import synth_state_dict, synth_video, synth_noise  # noqa: E402
+
+
+def _import_reference():
+    os.chdir(REF)                                   # CONFIG.py:11 resolves paths from cwd
+    sys.path.insert(0, os.path.join(REF, "src"))
+    from lib.setup_model import setup_model, setup_predictor
+    return setup_model, setup_predictor
+
+
+CASES = {
+    # name: (experiment, B, num_seed, num_preds, weight seed, sharpen, overrides)
+    "blockpush":        ("BlockPush",       2, 6, 5, 11, 1.0, {}),
+    "blockpush_sharp":  ("BlockPush",       1, 6, 3, 12, 6.0, {}),
+    "buttonpress":      ("ButtonPress",     2, 4, 3, 13, 1.0, {}),
+    "gridshapes5":      ("GridShapes5Objs", 2, 6, 4, 14, 1.0, {}),
+    "sketchy_sharp":    ("Sketchy",         1, 6, 6, 15, 4.0, {}),
+}
+DECODE_LAST = 2       # decode only the last 2 predicted frames of every video (fixture size)
+
+
+def manifest_of(module):
+    return {k: list(v.shape) for k, v in module.state_dict().items()}
+
+
+def run_case(name, setup_model, setup_predictor):
+    exp, B, ns, npred, wseed, sharpen, _ = CASES[name]
+    j = json.load(open(os.path.join(REF, "experiments", exp, "predictors", "PlaySlot", "experiment_params.json")))
+    scfg = copy.deepcopy(j["model"]["model_params"])
+    pcfg = copy.deepcopy(j["predictor"]["predictor_params"])
+    savi = setup_model(copy.deepcopy(j["model"])).eval()
+    pred = setup_predictor(copy.deepcopy(j)).eval()
+    sman, pman = manifest_of(savi), manifest_of(pred)
+
+    ssd = synth_state_dict(sman, wseed, sharpen)
+    psd = synth_state_dict(pman, wseed + 100)
+    psd["dynamics_model.pos_emb.pe"] = pred.state_dict()["dynamics_model.pos_emb.pe"].clone()
+    savi.load_state_dict(ssd, strict=True)
+    pred.load_state_dict(psd, strict=True)
+
+    T = ns + npred
+    H, W = scfg["encoder"]["encoder_params"]["resolution"]
+    S, D, A = scfg["num_slots"], scfg["slot_dim"], pcfg["action_dim"]
+    video = synth_video(B, T, H, W, wseed)
+    per_slot = pcfg["LatentAction"]["model_name"] == "VQSimpleMLPSlotLatentAction"
+    noise_shape = (B, T - 1, S, A) if per_slot else (B, T - 1, A)
+    noise = synth_noise(noise_shape, wseed)
+    init_noise = synth_noise((B, S, D), wseed + 1) if scfg["initializer"] == "LearnedRandom" else None
+
+    with torch.no_grad():
+        if init_noise is not None:
+            # LearnedRandom draws torch.randn on the module's device (initializers.py:123): inject
+            real_randn = torch.randn
+            torch.randn = lambda *a, **k: init_noise.clone()
+            try:
+                out = savi(video, num_imgs=T, decode=False)
+            finally:
+                torch.randn = real_randn
+        else:
+            out = savi(video, num_imgs=T, decode=False)
+        sh = out["slot_history"]
+        sa_masks = savi.slot_attention.get_attention_masks().clone()
+
+        # InvDyn.sample draws torch.randn(mean.size()) on the CPU generator (LatentAction.py:73): inject
+        real_randn = torch.randn
+        torch.randn = lambda *a, **k: noise.clone()
+        try:
+            act = pred.latent_action.compute_actions(sh)
+        finally:
+            torch.randn = real_randn
+        torch.randn = lambda *a, **k: noise.clone()
+        try:
+            pred_slots, _ = pred.forward_multiple_samples(sh, 1, ns, npred, use_posterior=True)
+        finally:
+            torch.randn = real_randn
+        pred_slots = pred_slots[:, 0]
+        dec_in = pred_slots[:, -DECODE_LAST:].reshape(B * DECODE_LAST, S, D)
+        recon, (recons, masks) = savi.decode(dec_in)
+
+        # margins of the VQ argmin (for the exact index comparison)
+        cb = pred.latent_action.quantizer.get_codewords()
+        z = act["sampled_latent_action"].reshape(-1, A)
+        dist = (z.pow(2).sum(1, keepdim=True) - 2 * z @ cb.t() + cb.t().pow(2).sum(0, keepdim=True))
+        top2 = dist.topk(2, dim=1, largest=False).values
+        margin = (top2[:, 1] - top2[:, 0]).min().item()
+
+    fx = {
+        "case": name, "experiment": exp, "B": B, "num_seed": ns, "num_preds": npred,
+        "weight_seed": wseed, "sharpen": sharpen, "decode_last": DECODE_LAST,
+        "savi_cfg": scfg, "predictor_cfg": pcfg,
+        "predictor_name": j["predictor"]["predictor_name"],
+        "savi_manifest": sman, "predictor_manifest": pman,
+        "video_checksum": [float(video.double().sum()), float(video[0, 0, 0, 0, :4].double().sum())],
+        "noise_checksum": float(noise.double().sum()),
+        "slot_history": sh.clone(), "sa_masks_last": sa_masks,
+        "action_proto": act["action_proto"].clone(), "action_variability": act["action_variability"].clone(),
+        "action_idxs": act["action_idxs"].clone(), "action_dist": act["action_dist"].clone(),
+        "sampled_latent_action": act["sampled_latent_action"].clone(),
+        "vq_margin_min": margin,
+        "pred_slots": pred_slots.clone(),
+        "recon": recon.clone(), "masks": masks.clone(), "recons_m0": recons[0].clone(),
+    }
+    return fx
+
+
+def run_slot_attention_cases(setup_model):
+    """ Stand-alone SlotAttention (config-2 shapes, reduced batch): 3 iterations, S in {4, 8}. """
+    sys.path.insert(0, os.path.join(REF, "src"))
+    from models.BlocksUtils.attention import SlotAttention
+    res = {}
+    for S, sharpen in ((8, 1.0), (4, 6.0)):
+        sa = SlotAttention(dim_feats=128, dim_slots=128, num_slots=S, num_iters_first=3, num_iters=1, mlp_hidden=256).eval()
+        man = {"slot_attention." + k: list(v.shape) for k, v in sa.state_dict().items()}
+        sd = synth_state_dict(man, 21 + S, sharpen)
+        sa.load_state_dict({k[len("slot_attention."):]: v for k, v in sd.items()}, strict=True)
+        g = torch.Generator().manual_seed(100 + S)
+        feats = torch.randn(2, 4096, 128, generator=g)
+        slots = torch.randn(2, S, 128, generator=g)
+        with torch.no_grad():
+            o3 = sa(feats, slots, step=0); m3 = sa.get_attention_masks().clone()
+            o1 = sa(feats, slots, step=1); m1 = sa.get_attention_masks().clone()
+        res[f"S{S}"] = {"manifest": man, "weight_seed": 21 + S, "sharpen": sharpen, "input_seed": 100 + S,
+                        "feats_checksum": float(feats.double().sum()),
+                        "slots_step0": o3.clone(), "masks_step0": m3, "slots_step1": o1.clone(), "masks_step1": m1}
+    return res
+
+
+def main():
+    setup_model, setup_predictor = _import_reference()
+    outdir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+    for name in CASES:
+        fx = run_case(name, setup_model, setup_predictor)
+        path = os.path.join(outdir, f"{name}.pt")
+        torch.save(fx, path)
+        print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB), vq margin {fx['vq_margin_min']:.3e}, "
+              f"mask max {float(fx['masks'].max()):.3f}, sa mask max {float(fx['sa_masks_last'].max()):.3f}")
+    sa = run_slot_attention_cases(setup_model)
+    path = os.path.join(outdir, "slot_attention.pt")
+    torch.save(sa, path)
+    print(f"slot_attention: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
+if __name__ == "__main__":
+    main()
