@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""
+bench.py -- PlaySlot seed + rollout throughput (frames/s) on N B200s, with the roofline of the dominant
+kernel, the SlotAttention roofline (BASELINE.json metric) and the CPU baseline beside it.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun launches N>1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle port of the reference)
+
+A "step" = one pass of the seed+rollout path of src/05_evaluate_PlaySlot.py:112-139 over one batch of
+synthetic video per GPU: savi(videos, decode=False) -> forward_multiple_samples(posterior) -> savi.decode.
+Workload (BASELINE.json configs[2]): GridShapes5Objs config, 64 videos per GPU, 6 seed + 15 predicted
+frames, 64x64 RGB, random-init weights, fp32.  Videos shard over the GPUs (weak scaling, no collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+EXPERIMENT = "GridShapes5Objs"
+NUM_SEED, NUM_PREDS = 6, 15
+METRIC, UNIT = "seed_rollout_frames_per_sec", "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_burst": j["bf16_tflops"], "bf16_sustained": j["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """ samples SM clocks and throttle reasons with nvidia-smi while the timed region runs """
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # median of the upper half = clock under load (idle samples before/after the region drag the median down)
+        under_load = sm[len(sm) // 2:] if sm else []
+        med = under_load[len(under_load) // 2] if under_load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+
+def oracle_models(cfg, seed=0):
+    """ random-init weights of the architecture (our module mirror's initialiser), as CPU state dicts """
+    from playslot_b200 import configs
+    torch.manual_seed(seed)
+    savi, pred = configs.build_models(cfg, "cpu")
+    return ({k: v.detach() for k, v in savi.state_dict().items()}, {k: v.detach() for k, v in pred.state_dict().items()})
+
+
+def oracle_step(cfg, ssd, psd, B, seed):
+    from oracle import playslot_oracle as O
+    scfg, pcfg = cfg["model"]["model_params"], cfg["predictor"]["predictor_params"]
+    g = torch.Generator().manual_seed(seed)
+    T = NUM_SEED + NUM_PREDS
+    H, W = scfg["encoder"]["encoder_params"]["resolution"]
+    S, D, A = scfg["num_slots"], scfg["slot_dim"], pcfg["action_dim"]
+    video = torch.rand(B, T, 3, H, W, generator=g)
+    per_slot = pcfg["LatentAction"]["model_name"] == "VQSimpleMLPSlotLatentAction"
+    noise = torch.randn((B, T - 1, S, A) if per_slot else (B, T - 1, A), generator=g)
+    init_noise = torch.randn(B, S, D, generator=g) if scfg["initializer"] == "LearnedRandom" else None
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.seed_rollout_pipeline(ssd, scfg, psd, pcfg, video, NUM_SEED, NUM_PREDS, noise, init_noise)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from playslot_b200 import configs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = configs.experiment(EXPERIMENT)
+    ssd, psd = oracle_models(cfg)
+    B = args.ref_batch
+    for i in range(args.warmup):
+        oracle_step(cfg, ssd, psd, 1, 100 + i)
+    times = [oracle_step(cfg, ssd, psd, B, 200 + i) for i in range(args.steps)]
+    tot = sum(times)
+    frames = B * (NUM_SEED + NUM_PREDS) * args.steps
+    val = frames / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.batch, args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{B} videos x {NUM_SEED + NUM_PREDS} frames per step, {args.steps} steps, torch CPU fp32, "
+                                   f"{cores} threads (oracle port of the reference; the PyTorch reference itself cannot travel to the GPU box)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(batch_per_gpu, n_gpus):
+    return {"workload": f"{EXPERIMENT} seed+rollout: {batch_per_gpu} videos/GPU x {n_gpus} GPU, {NUM_SEED} seed + {NUM_PREDS} pred frames, "
+                        "64x64 RGB, 6 slots, encode(decode=False) -> InvDyn posterior + cOCVP rollout -> decode",
+            "batch_per_gpu": batch_per_gpu, "num_seed": NUM_SEED, "num_preds": NUM_PREDS,
+            "l2_policy": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no flush needed",
+            "parallelism": f"videos sharded over {n_gpus} GPU(s), no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+
+def conv_flops(meta):
+    n, cin, cout, H, W, k = meta
+    return 2.0 * n * H * W * cin * cout * k * k
+
+
+def sa_main_bytes(meta):
+    B, N, S, D, masks = meta
+    return B * N * D * 4 + (B * S * N * 4 if masks else 0) + 2 * B * S * (D + 2) * 4
+
+
+def slot_attention_config2(pk):
+    """ BASELINE.json configs[1]: SlotAttention forward, B=64, N=4096, D=128, 3 iterations, S in {8, 4} """
+    from playslot_b200.models.BlocksUtils.attention import SlotAttention
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for S in (8, 4):
+        torch.manual_seed(S)
+        m = SlotAttention(128, 128, S, 3, 1, 256).eval().cuda()
+        feats = torch.randn(64, 4096, 128, device="cuda")
+        slots = torch.randn(64, S, 128, device="cuda")
+        with torch.no_grad():
+            for _ in range(3):
+                m(feats, slots, step=0)
+            ts = []
+            for _ in range(10):
+                flush.zero_()                                   # flush L2 between timed iterations
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                m(feats, slots, step=0)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+        byts = 64 * 4096 * 128 * 4 + 2 * 64 * S * 128 * 4 + 64 * S * 4096 * 4 + 720e3
+        out[f"S{S}"] = {"ms": ms, "algorithmic_MB": byts / 1e6, "achieved_GBs": byts / ms / 1e6,
+                        "frac": byts / ms / 1e6 / pk["hbm_gbs"], "frames_per_s": 64 / ms * 1e3}
+    return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from playslot_b200 import configs, ops
+    from playslot_b200.pipeline import seed_rollout, seed_rollout_host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pk = peaks()
+    cfg = configs.experiment(EXPERIMENT)
+    torch.manual_seed(0)                                           # same random-init weights on every rank
+    savi, pred = configs.build_models(cfg, "cuda")
+    B, T = args.batch, NUM_SEED + NUM_PREDS
+    g = torch.Generator().manual_seed(1234 + rank)                 # a different synthetic shard per rank
+    video_host = torch.rand(B, T, 3, 64, 64, generator=g).pin_memory()
+    video = video_host.cuda()
+    out_host = torch.empty(B, NUM_PREDS, 3, 64, 64, pin_memory=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        seed_rollout(savi, pred, video, NUM_SEED, NUM_PREDS)
+    barrier()
+
+    # ---- device-resident timing -------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ops.reset_launch_count()
+    ops.profile_start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        seed_rollout(savi, pred, video, NUM_SEED, NUM_PREDS)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launch_count()
+    prof = ops.profile_stop()
+
+    # ---- end-to-end timing: pinned host video in, predicted frames back to the host, every step ------------
+    for _ in range(2):
+        seed_rollout_host(savi, pred, video_host, NUM_SEED, NUM_PREDS, out_host)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e2.record()
+    for _ in range(args.steps):
+        seed_rollout_host(savi, pred, video_host, NUM_SEED, NUM_PREDS, out_host)
+    e3.record()
+    barrier()
+    wall_e2e = time.perf_counter() - t_host0
+    ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), 1e3 * wall_e2e))
+    clocks = sampler.stop() if rank == 0 else None
+
+    frames_per_step = B * T * world
+    value = frames_per_step * args.steps / (ms_total * 1e-3)
+    e2e_value = frames_per_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (by summed device time over the timed region) ------------------------
+    total_prof = sum(v["ms"] for v in prof.values()) or 1.0
+    shares = {k: round(v["ms"] / total_prof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    roofline = None
+    if dom[0].startswith("conv2d"):
+        fl = sum(conv_flops(m) for m in dom[1]["meta"])
+        ach = fl / (dom[1]["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": dom[0], "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_sustained"], "traffic": None,
+                    "note": "fp32 CUDA-core direct convolution measured against the " + pk["source"] + " sustained bf16 tensor peak; "
+                            "FLOPs = 2*n*H*W*Cin*Cout*k*k of the launches in the timed region", "share_of_step": shares[dom[0]]}
+    sa = prof.get("sa_main")
+    roofline_sa = None
+    if sa:
+        by = sum(sa_main_bytes(m) for m in sa["meta"])
+        ach = by / (sa["ms"] * 1e-3) / 1e9
+        roofline_sa = {"kernel": "sa_main", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                       "frac": ach / pk["hbm_gbs"], "traffic": None, "launches": sa["calls"],
+                       "avg_launch_us": 1e3 * sa["ms"] / sa["calls"], "share_of_step": shares.get("sa_main")}
+        if roofline is None:
+            roofline = roofline_sa
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": video_host.numel() * 4 * world,
+                "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_slot_attention": roofline_sa,
+        "kernel_time_shares": shares, "peaks": pk,
+    }
+    if world == 1 and not args.skip_extras:
+        line["slot_attention_config2"] = slot_attention_config2(pk)
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ssd, psd = oracle_models(cfg)
+        oracle_step(cfg, ssd, psd, 1, 7)                                # warm-up
+        bs = args.ref_batch
+        dt = oracle_step(cfg, ssd, psd, bs, 8)
+        line["cpu_baseline"] = {"value": bs * T / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{bs} videos x {T} frames of the same workload, one pass after a 1-video warm-up "
+                                          f"({dt:.1f} s), torch CPU fp32 oracle port, {cores} threads"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="videos per GPU")
+    ap.add_argument("--ref-batch", type=int, default=4, help="videos per step of the CPU arm (bounded sample)")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the config-2 SlotAttention sweep and the CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+/*
+ * playslot_b200 -- C ABI of the B200 (sm_100a) kernels behind PlaySlot's per-frame slot pipeline.
+ *
+ * The reference (chrono-motz/PlaySlot) is pure PyTorch and has no FFI of its own; the drop-in boundary is
+ * its `src/models` nn.Module surface.  The functions below are what the Python
+ * mirror of that surface (playslot_b200/models) binds through ctypes: one entry point per fused device
+ * op, each replacing the chain of ATen calls cited next to it (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to contiguous fp32 (`float`) data unless stated otherwise;
+ *     tensors are row-major with the last listed axis contiguous;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call is
+ *     stream-ordered, asynchronous, allocates nothing and keeps no pointer after it returns;
+ *   - return value: 0 = ok, negative = invalid argument / unsupported shape, positive = cudaError_t;
+ *     `ps_last_error()` returns a thread-local human readable message; nothing throws;
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef PLAYSLOT_B200_H
+#define PLAYSLOT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLAYSLOT_B200_VERSION 100   /* 0.1.0 */
+
+/* ---- plumbing ---------------------------------------------------------------------------------------- */
+int ps_version(void);
+const char* ps_last_error(void);
+unsigned long long ps_launch_count(void);      /* kernels launched through this library by this process */
+void ps_reset_launch_count(void);
+int ps_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- dense building blocks ---------------------------------------------------------------------------- */
+
+/* Y[M,N] = act( LN_eps(X)[M,K] * W[N,K]^T + bias ) + res[(m / res_div) % res_mod, :]
+ * Replaces nn.LayerNorm + nn.Linear + activation + residual chains, e.g. the encoder MLP
+ * (src/models/SAVi.py:111-116,214-216), transformer-block MLPs and q/k/v/out projections
+ * (src/models/BlocksUtils/attention.py:296,462-475,539-563; model_blocks.py:293-309), the cOCVP token /
+ * action / variability embedding with its sinusoidal time encoding (Predictors/DynamicsModels.py:119-148,
+ * 487-497) and regression head (:85-88,510).
+ * ln_gamma/ln_beta may be NULL (no LayerNorm); bias, res may be NULL.
+ * act: 0 none, 1 ReLU, 2 GELU (exact erf), 3 |x|.  K, ldx multiples of 4; X, W 16-byte aligned. */
+int ps_linear(const float* X, int ldx, const float* W, const float* bias,
+              const float* ln_gamma, const float* ln_beta, float ln_eps,
+              const float* res, int ldres, int res_div, int res_mod,
+              float* Y, int ldy, int M, int N, int K, int act, void* stream);
+
+/* Multi-head self attention over n_seq independent sequences of L tokens.
+ * qkv: [n_seq*L, ld] rows holding q | k | v (each n_heads*head_dim wide, head-major); out: [n_seq*L, ldo].
+ * slots_per_frame > 0 applies the block-causal (time x slot staircase) mask: token j is visible to token i
+ * iff j / slots_per_frame <= i / slots_per_frame; masked logits are set to -1e9 as the reference does.
+ * Replaces MetaAttention.attention / split_into_heads / merge_heads
+ * (src/models/BlocksUtils/attention.py:204-263,288-316) and build_slot_causal_mask
+ * (BlocksUtils/model_utils.py:115-124). */
+int ps_mha(const float* qkv, int ld, const float* res /* optional residual, laid out like out */, float* out,
+           int ldo, int n_seq, int L, int n_heads, int head_dim, int slots_per_frame, void* stream);
+
+/* KxK stride-1 zero-padded ("same") convolution + bias (+ReLU).  x: [n,Cin,H,W]; w_packed: [Cin][K*K][Cout]
+ * (a repack of nn.Conv2d's [Cout,Cin,K,K]); y: [n,Cout,H,W], or with out_nhwc [n,H,W,Cout] (+ addend_nhwc
+ * [H*W,Cout], used to add the soft position embedding).  ksize in {3,5}, Cout in {32,64}, H,W % 16 == 0.
+ * Replaces ConvBlock / SimpleConvEncoder / Decoder convolutions (src/models/BlocksUtils/model_blocks.py:48-79,
+ * EncodersDecoders/encoders.py:77-104, decoders.py:78-113) and the NHWC permute + SoftPositionEmbed add
+ * (SAVi.py:210-212, model_blocks.py:110-119). */
+int ps_conv2d(const float* x, const float* w_packed, const float* bias, const float* addend_nhwc, float* y,
+              int n_img, int Cin, int Cout, int H, int W, int ksize, int relu, int out_nhwc, void* stream);
+
+/* ---- SlotAttention (src/models/BlocksUtils/attention.py:76-119) ---------------------------------------- */
+
+/* floats per (frame, chunk) of the partial buffer used between ps_sa_main and ps_sa_update */
+int ps_sa_partial_floats(int num_slots);
+
+/* One streaming pass over the feature tokens of every frame: LayerNorm statistics of the inputs
+ * (norm_input, :92), logits against the folded queries A/a0/a1 (= scale * to_q(norm_slot(slots)) . to_k(.),
+ * :100-106), softmax over the SLOT axis + eps (:107), optional store of that tensor as the attention masks
+ * [B,S,N] (:108), and the un-normalised weighted sums needed for `updates` (:109-110), written as
+ * per-chunk partials [B][n_chunks][ps_sa_partial_floats(S)]. */
+int ps_sa_main(const float* x, const float* A, const float* a0, const float* a1, float* partial,
+               float* masks /* may be NULL */, int B, int N, int S, int dim, int n_chunks, float ln_eps,
+               float attn_eps, void* stream);
+
+/* Per-slot update: reduce the partials, renormalise over locations (:109), to_v (:94), nn.GRUCell (:112-115),
+ * residual MLP (:117), then (do_prep) the folded queries of the next iteration.  With do_update = 0 it only
+ * prepares A/a0/a1 from slots_in.  Weight matrices suffixed T are transposed to [in][out]. */
+int ps_sa_update(const float* partial, int n_chunks, const float* slots_in, float* slots_out,
+                 const float* ln_in_g, const float* ln_in_b, const float* WvT,
+                 const float* WihT, const float* WhhT, const float* b_ih, const float* b_hh,
+                 const float* ln_mlp_g, const float* ln_mlp_b,
+                 const float* W1T, const float* b1, const float* W2T, const float* b2,
+                 const float* ln_slot_g, const float* ln_slot_b, const float* WqT, const float* Wk,
+                 float* A, float* a0, float* a1,
+                 int B, int S, int dim, int mlp_hidden, float scale, float ln_eps,
+                 int do_update, int do_prep, void* stream);
+
+/* ---- spatial-broadcast decoder (src/models/SAVi.py:220-248, EncodersDecoders/decoders.py:89-113) -------- */
+
+/* h1[img,co,y,x] = relu(G[img, cls(y), cls(x), co] + P[co,y,x]): the first decoder convolution applied to
+ * broadcast(slot) + position embedding, collapsed into (2*pad+1)^2 border classes (exact re-association). */
+int ps_dec_expand(const float* G, const float* P, float* out, int n_img, int C, int H, int W, int ksize,
+                  void* stream);
+
+/* Final 3x3 conv (Cin -> RGB + alpha), softmax of alpha over the slot axis, recon = sum_s rgb_s * mask_s.
+ * h: [M*S,Cin,H,W]; w_packed: [Cin][9][4]; recon [M,3,H,W]; recons [M,S,3,H,W] (un-masked); masks [M,S,1,H,W]. */
+int ps_dec_composite(const float* h, const float* w_packed, const float* bias, float* recon, float* recons,
+                     float* masks, int M, int S, int Cin, int H, int W, void* stream);
+
+/* ---- InvDyn tail (src/models/Predictors/LatentAction.py:72-87,228-249,340-359; quantization.py:256-372) -- */
+
+/* mv: [B,T,R,2A] = mean_fc | variance_fc outputs (R = 1 for InvDynS, num_slots for InvDynM); noise [B,T-1,R,A]
+ * is drawn by the host exactly as the reference draws it.  Outputs: action_dist [B,T-1,2,R,A], sampled latent
+ * z, prototype z + (z_q - z), variability, int64 code indices, per-vector mean_A (z_q - z)^2. */
+int ps_invdyn_tail(const float* mv, const float* noise, const float* codebook, float* dist_out, float* z_out,
+                   float* proto_out, float* var_out, long long* idx_out, float* loss_out,
+                   int B, int T, int R, int A, int K, int per_slot, float eps, void* stream);
+
+/* Stand-alone nearest-codeword lookup (VectorQuantizer.forward, quantization.py:294-322): z [n,A] ->
+ * proto = z + (z_q - z), exact codewords z_q, int64 indices, per-vector mean_A (z_q - z)^2. */
+int ps_vq_lookup(const float* z, const float* codebook, float* proto_out, float* zq_out, long long* idx_out,
+                 float* loss_out, int n, int A, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAYSLOT_B200_H */

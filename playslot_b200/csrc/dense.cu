@@ -1,0 +1,406 @@
+// fp32 CUDA-core building blocks shared by the encoder MLP, the transition block, InvDyn and cOCVP:
+//   ps_linear  : Y = act(LN?(X) W^T + b) (+ residual), tiled SGEMM with fused LayerNorm prologue
+//   ps_mha     : multi-head self attention over short token sequences (<= a few hundred tokens),
+//                optional block-causal (time x slot staircase) mask
+//   ps_conv2d  : direct KxK stride-1 "same" convolution, NCHW, fused bias/ReLU, optional NHWC(+addend) output
+// These are the exact-fp32 reference kernels of the library; the tcgen05 kernels are checked against them.
+#include "common.cuh"
+#include "../../include/playslot_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// linear
+// ------------------------------------------------------------------------------------------------
+struct LinearParams {
+    const float* X; int ldx;
+    const float* W;
+    const float* bias;
+    const float* ln_g; const float* ln_b; float ln_eps;
+    const float* res; int ldres; int res_div; int res_mod;
+    float* Y; int ldy;
+    int M, N, K;
+    int act;
+    int vec_store;
+};
+
+#define LBM 64
+#define LBN 64
+#define LBK 16
+
+template <bool LN>
+__global__ __launch_bounds__(256) void linear_kernel(LinearParams p) {
+    __shared__ __align__(16) float As[LBK][LBM + 4];
+    __shared__ __align__(16) float Bs[LBK][LBN + 4];
+    __shared__ float s_mean[LBM], s_rstd[LBM];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * LBN;
+    const int lr = tid >> 2;          // tile row handled by this thread when loading (0..63)
+    const int lk = (tid & 3) * 4;     // k offset inside the k-tile (0,4,8,12)
+
+    float mean = 0.f, rstd = 1.f;
+    if (LN) {
+        const int m = m0 + lr;
+        float s = 0.f;
+        if (m < p.M)
+            for (int k = lk; k < p.K; k += 16) {
+                float4 v = *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k);
+                s += (v.x + v.y) + (v.z + v.w);
+            }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        mean = s / (float)p.K;
+        float ss = 0.f;
+        if (m < p.M)
+            for (int k = lk; k < p.K; k += 16) {
+                float4 v = *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k);
+                float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+                ss += (a * a + b * b) + (c * c + d * d);
+            }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        rstd = 1.0f / sqrtf(ss / (float)p.K + p.ln_eps);
+        if ((tid & 3) == 0) { s_mean[lr] = mean; s_rstd[lr] = rstd; }
+    }
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int tx = tid & 15, ty = tid >> 4;
+    for (int k0 = 0; k0 < p.K; k0 += LBK) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+        const int k = k0 + lk;
+        if (m0 + lr < p.M && k < p.K) {
+            av = *reinterpret_cast<const float4*>(p.X + (size_t)(m0 + lr) * p.ldx + k);
+            if (LN) {
+                float4 g = *reinterpret_cast<const float4*>(p.ln_g + k);
+                float4 b = *reinterpret_cast<const float4*>(p.ln_b + k);
+                av.x = (av.x - mean) * rstd * g.x + b.x;
+                av.y = (av.y - mean) * rstd * g.y + b.y;
+                av.z = (av.z - mean) * rstd * g.z + b.z;
+                av.w = (av.w - mean) * rstd * g.w + b.w;
+            }
+        }
+        if (n0 + lr < p.N && k < p.K)
+            bv = *reinterpret_cast<const float4*>(p.W + (size_t)(n0 + lr) * p.K + k);
+        As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
+        Bs[lk + 0][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < LBK; ++kk) {
+            float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+        const int n = n0 + tx * 4;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = acc[i][j];
+            if (n + j < p.N) {
+                if (p.bias) v += p.bias[n + j];
+                if (p.act == 1) v = fmaxf(v, 0.f);
+                else if (p.act == 2) v = gelu_erf(v);
+                else if (p.act == 3) v = fabsf(v);
+                if (p.res) {
+                    const int rr = (m / p.res_div) % p.res_mod;
+                    v += p.res[(size_t)rr * p.ldres + n + j];
+                }
+            }
+            o[j] = v;
+        }
+        float* dst = p.Y + (size_t)m * p.ldy + n;
+        if (p.vec_store && n + 3 < p.N) {
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) dst[j] = o[j];
+        }
+    }
+}
+
+extern "C" int ps_linear(const float* X, int ldx, const float* W, const float* bias,
+                         const float* ln_gamma, const float* ln_beta, float ln_eps,
+                         const float* res, int ldres, int res_div, int res_mod,
+                         float* Y, int ldy, int M, int N, int K, int act, void* stream) {
+    PS_REQUIRE(X && W && Y, "ps_linear: null pointer");
+    PS_REQUIRE(M >= 0 && N > 0 && K > 0, "ps_linear: bad shape M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return PS_OK;
+    PS_REQUIRE(K % 4 == 0 && ldx % 4 == 0, "ps_linear: K (%d) and ldx (%d) must be multiples of 4", K, ldx);
+    PS_REQUIRE(ps_aligned16(X) && ps_aligned16(W), "ps_linear: X and W must be 16-byte aligned");
+    PS_REQUIRE((ln_gamma == nullptr) == (ln_beta == nullptr), "ps_linear: LayerNorm needs both gamma and beta");
+    PS_REQUIRE(!ln_gamma || (ps_aligned16(ln_gamma) && ps_aligned16(ln_beta)), "ps_linear: LN params must be 16-byte aligned");
+    PS_REQUIRE(act >= 0 && act <= 3, "ps_linear: unknown activation %d", act);
+    LinearParams p;
+    p.X = X; p.ldx = ldx; p.W = W; p.bias = bias; p.ln_g = ln_gamma; p.ln_b = ln_beta; p.ln_eps = ln_eps;
+    p.res = res; p.ldres = ldres; p.res_div = res_div > 0 ? res_div : 1; p.res_mod = res_mod > 0 ? res_mod : M;
+    p.Y = Y; p.ldy = ldy; p.M = M; p.N = N; p.K = K; p.act = act;
+    p.vec_store = (ldy % 4 == 0 && ps_aligned16(Y)) ? 1 : 0;
+    dim3 grid((M + LBM - 1) / LBM, (N + LBN - 1) / LBN);
+    PS_REQUIRE(grid.y <= 65535, "ps_linear: N=%d too large for one launch", N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ln_gamma) linear_kernel<true><<<grid, 256, 0, st>>>(p);
+    else linear_kernel<false><<<grid, 256, 0, st>>>(p);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-head self attention for short sequences
+// ------------------------------------------------------------------------------------------------
+struct MhaParams {
+    const float* qkv; int ld;
+    const float* res;      // optional residual added to the output, same layout as out
+    float* out; int ldo;
+    int n_seq, L, H, dh, spf;
+    float scale;
+};
+
+__global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int seq = blockIdx.x, h = blockIdx.y;
+    const int L = p.L, dh = p.dh, inner = p.H * dh;
+    float* Ks = sm;                      // [L][dh+1]
+    float* Vs = Ks + L * (dh + 1);       // [L][dh]
+    float* Ps = Vs + L * dh;             // [4][L]
+    float* Qs = Ps + 4 * L;              // [4][dh]
+    const float* base = p.qkv + (size_t)seq * L * p.ld;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int idx = tid; idx < L * dh; idx += 128) {
+        const int j = idx / dh, d = idx - j * dh;
+        Ks[j * (dh + 1) + d] = base[(size_t)j * p.ld + inner + h * dh + d];
+        Vs[j * dh + d] = base[(size_t)j * p.ld + 2 * inner + h * dh + d];
+    }
+    __syncthreads();
+    for (int i = w; i < L; i += 4) {
+        for (int d = lane; d < dh; d += 32) Qs[w * dh + d] = base[(size_t)i * p.ld + h * dh + d];
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < L; j += 32) {
+            float dot = 0.f;
+            const float* kr = Ks + j * (dh + 1);
+            const float* qr = Qs + w * dh;
+#pragma unroll 8
+            for (int d = 0; d < dh; ++d) dot = fmaf(qr[d], kr[d], dot);
+            dot *= p.scale;
+            if (p.spf > 0 && (j / p.spf) > (i / p.spf)) dot = -1e9f;   // masked_fill(mask == 0, -1e9)
+            Ps[w * L + j] = dot;
+            mx = fmaxf(mx, dot);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < L; j += 32) {
+            const float e = expf(Ps[w * L + j] - mx);
+            Ps[w * L + j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        const float inv = 1.0f / sum;
+        for (int d = lane; d < dh; d += 32) {
+            float acc = 0.f;
+            for (int j = 0; j < L; ++j) acc = fmaf(Ps[w * L + j] * inv, Vs[j * dh + d], acc);
+            const size_t oi = ((size_t)seq * L + i) * p.ldo + h * dh + d;
+            p.out[oi] = p.res ? acc + p.res[oi] : acc;
+        }
+        __syncwarp();
+    }
+}
+
+extern "C" int ps_mha(const float* qkv, int ld, const float* res, float* out, int ldo, int n_seq, int L, int n_heads,
+                      int head_dim, int slots_per_frame, void* stream) {
+    PS_REQUIRE(qkv && out, "ps_mha: null pointer");
+    PS_REQUIRE(n_seq >= 0 && L > 0 && n_heads > 0 && head_dim > 0, "ps_mha: bad shape");
+    if (n_seq == 0) return PS_OK;
+    PS_REQUIRE(ld >= 3 * n_heads * head_dim && ldo >= n_heads * head_dim, "ps_mha: leading dimensions too small");
+    MhaParams p;
+    p.qkv = qkv; p.ld = ld; p.res = res; p.out = out; p.ldo = ldo; p.n_seq = n_seq; p.L = L; p.H = n_heads; p.dh = head_dim;
+    p.spf = slots_per_frame; p.scale = 1.0f / sqrtf((float)head_dim);
+    size_t smem = (size_t)(L * (head_dim + 1) + L * head_dim + 4 * L + 4 * head_dim) * sizeof(float);
+    PS_REQUIRE(smem <= 200 * 1024, "ps_mha: sequence of %d tokens x head_dim %d does not fit in shared memory", L, head_dim);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        PS_CUDA(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    PS_REQUIRE(n_heads <= 65535, "ps_mha: too many heads");
+    mha_kernel<<<dim3(n_seq, n_heads), 128, smem, (cudaStream_t)stream>>>(p);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// direct convolution (stride 1, zero "same" padding), fp32
+// ------------------------------------------------------------------------------------------------
+struct ConvParams {
+    const float* x;        // [n][Cin][H][W]
+    const float* wp;       // packed [Cin][KS*KS][Cout]
+    const float* bias;     // [Cout] or null
+    const float* addend;   // NHWC addend [H*W][Cout] (only with out_nhwc) or null
+    float* y;              // [n][Cout][H][W] or [n][H][W][Cout]
+    int n, Cin, Cout, H, W;
+    int relu, out_nhwc;
+};
+
+#define CV_T 16        // output tile is CV_T x CV_T pixels
+#define CV_CI 8        // input channels staged per step
+#define CV_HS 20       // shared-memory row stride of the halo tile (floats)
+
+template <int KS, int COUT_T>
+__global__ __launch_bounds__(256) void conv2d_kernel(ConvParams p) {
+    constexpr int PAD = KS / 2;
+    constexpr int HH = CV_T + KS - 1;
+    constexpr int KK = KS * KS;
+    constexpr int COUT = 8 * COUT_T;
+    extern __shared__ __align__(16) float sm[];
+    float* s_in = sm;                               // [CV_CI][HH][CV_HS]
+    float* s_w = sm + CV_CI * HH * CV_HS;           // [CV_CI][KK][COUT]
+    const int tid = threadIdx.x, lane = tid & 31, cg = tid >> 5;
+    const int tiles_x = p.W / CV_T;
+    const int ty0 = (blockIdx.x / tiles_x) * CV_T, tx0 = (blockIdx.x % tiles_x) * CV_T;
+    const int img = blockIdx.y;
+    const int py = lane >> 1, px0 = (lane & 1) * 8;
+    const float* xin = p.x + (size_t)img * p.Cin * p.H * p.W;
+
+    float acc[8][COUT_T];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < COUT_T; ++j) acc[i][j] = 0.f;
+
+    for (int c0 = 0; c0 < p.Cin; c0 += CV_CI) {
+        const int cc = min(CV_CI, p.Cin - c0);
+        // stage the input halo tile (zero padded)
+        for (int idx = tid; idx < cc * HH * CV_HS; idx += 256) {
+            const int ci = idx / (HH * CV_HS);
+            const int r = idx - ci * (HH * CV_HS);
+            const int hy = r / CV_HS, hx = r - hy * CV_HS;
+            const int gy = ty0 + hy - PAD, gx = tx0 + hx - PAD;
+            float v = 0.f;
+            if (hx < HH && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+                v = xin[((size_t)(c0 + ci) * p.H + gy) * p.W + gx];
+            s_in[idx] = v;
+        }
+        // stage the weights of these channels: contiguous in the packed layout
+        {
+            const float4* src = reinterpret_cast<const float4*>(p.wp + (size_t)c0 * KK * COUT);
+            float4* dst = reinterpret_cast<float4*>(s_w);
+            for (int idx = tid; idx < cc * KK * COUT / 4; idx += 256) dst[idx] = src[idx];
+        }
+        __syncthreads();
+        for (int ci = 0; ci < cc; ++ci) {
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky) {
+                const float* row = s_in + (ci * HH + py + ky) * CV_HS + px0;
+                float in[12];
+                *reinterpret_cast<float4*>(&in[0]) = *reinterpret_cast<const float4*>(row);
+                *reinterpret_cast<float4*>(&in[4]) = *reinterpret_cast<const float4*>(row + 4);
+                *reinterpret_cast<float4*>(&in[8]) = *reinterpret_cast<const float4*>(row + 8);
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
+                    const float* wr = s_w + (ci * KK + ky * KS + kx) * COUT + cg * COUT_T;
+                    float wv[COUT_T];
+#pragma unroll
+                    for (int j = 0; j < COUT_T; j += 4)
+                        *reinterpret_cast<float4*>(&wv[j]) = *reinterpret_cast<const float4*>(wr + j);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < COUT_T; ++j) acc[i][j] = fmaf(in[i + kx], wv[j], acc[i][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    const int oy = ty0 + py, ox = tx0 + px0;
+#pragma unroll
+    for (int j = 0; j < COUT_T; ++j) {
+        const int co = cg * COUT_T + j;
+        const float b = p.bias ? p.bias[co] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = acc[i][j] + b;
+            if (p.relu) v = fmaxf(v, 0.f);
+            acc[i][j] = v;
+        }
+    }
+    if (!p.out_nhwc) {
+#pragma unroll
+        for (int j = 0; j < COUT_T; ++j) {
+            const int co = cg * COUT_T + j;
+            float* dst = p.y + (((size_t)img * COUT + co) * p.H + oy) * p.W + ox;
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const size_t pix = (size_t)oy * p.W + ox + i;
+            float* dst = p.y + ((size_t)img * p.H * p.W + pix) * COUT + cg * COUT_T;
+            const float* ad = p.addend ? p.addend + pix * COUT + cg * COUT_T : nullptr;
+#pragma unroll
+            for (int j = 0; j < COUT_T; j += 4) {
+                float4 v = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+                if (ad) {
+                    float4 a = *reinterpret_cast<const float4*>(ad + j);
+                    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                }
+                *reinterpret_cast<float4*>(dst + j) = v;
+            }
+        }
+    }
+}
+
+template <int KS, int COUT_T>
+static int launch_conv(const ConvParams& p, cudaStream_t st) {
+    constexpr int HH = CV_T + KS - 1;
+    const size_t smem = (size_t)(CV_CI * HH * CV_HS + CV_CI * KS * KS * 8 * COUT_T) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        PS_CUDA(cudaFuncSetAttribute(conv2d_kernel<KS, COUT_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((p.H / CV_T) * (p.W / CV_T), p.n);
+    conv2d_kernel<KS, COUT_T><<<grid, 256, smem, st>>>(p);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
+
+extern "C" int ps_conv2d(const float* x, const float* w_packed, const float* bias, const float* addend_nhwc,
+                         float* y, int n_img, int Cin, int Cout, int H, int W, int ksize, int relu,
+                         int out_nhwc, void* stream) {
+    PS_REQUIRE(x && w_packed && y, "ps_conv2d: null pointer");
+    PS_REQUIRE(n_img >= 0 && Cin > 0, "ps_conv2d: bad shape");
+    if (n_img == 0) return PS_OK;
+    PS_REQUIRE(H % CV_T == 0 && W % CV_T == 0, "ps_conv2d: H and W must be multiples of %d (got %dx%d)", CV_T, H, W);
+    PS_REQUIRE(n_img <= 65535, "ps_conv2d: at most 65535 images per launch (got %d)", n_img);
+    PS_REQUIRE(ps_aligned16(x) && ps_aligned16(w_packed) && ps_aligned16(y), "ps_conv2d: pointers must be 16-byte aligned");
+    PS_REQUIRE(!addend_nhwc || out_nhwc, "ps_conv2d: the addend is only supported with NHWC output");
+    ConvParams p;
+    p.x = x; p.wp = w_packed; p.bias = bias; p.addend = addend_nhwc; p.y = y;
+    p.n = n_img; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu; p.out_nhwc = out_nhwc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ksize == 5 && Cout == 64) return launch_conv<5, 8>(p, st);
+    if (ksize == 5 && Cout == 32) return launch_conv<5, 4>(p, st);
+    if (ksize == 3 && Cout == 64) return launch_conv<3, 8>(p, st);
+    if (ksize == 3 && Cout == 32) return launch_conv<3, 4>(p, st);
+    ps_set_error("ps_conv2d: unsupported ksize=%d Cout=%d (supported: ksize 3|5, Cout 32|64)", ksize, Cout);
+    return PS_EUNSUPPORTED;
+}

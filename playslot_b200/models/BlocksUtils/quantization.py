@@ -1,0 +1,164 @@
+"""
+Vector quantisation of latent actions -- mirror of src/models/BlocksUtils/quantization.py
+(VectorQuantizer, EmaVectorQuantizer, EmaCodebookMeter; same state_dict: `embeddings.0.weight`,
+`ema_count`, `ema_weight`).  The nearest-codeword search runs in csrc/invdyn.cu (fp32, first-index ties).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from .._common import print_, require_cuda, no_grad_only, f32c
+
+
+def L2_efficient(x, y):
+    """ pairwise squared distances |x|^2 - 2 x y + |y|^2 (quantization.py:18-20); kept for API parity """
+    return (x.pow(2).sum(1, keepdim=True) - 2 * x @ y + y.pow(2).sum(0, keepdim=True))
+
+
+class EmaCodebookMeter:
+    """ EMA estimate of codeword usage (quantization.py:24-83); python-side statistics, not in the state_dict """
+
+    def __init__(self, codebook_size, ema_alpha=0.05):
+        if ema_alpha < 0 or ema_alpha > 1.0:
+            raise ValueError(f"{ema_alpha = } must be in [0, 1]...")
+        self.codebook_size = codebook_size
+        self.ema_alpha = ema_alpha
+        self.reset()
+
+    def reset(self):
+        self.bins = nn.Parameter(torch.ones(self.codebook_size) / self.codebook_size, requires_grad=False)
+        self.iters = 0
+
+    def bincount(self, val, weights=None):
+        norm = val.shape[0]
+        weights = weights.reshape(-1) if weights is not None else None
+        count = torch.bincount(val.reshape(-1), minlength=self.codebook_size, weights=weights).detach()
+        self.iters += 1
+        return count / norm
+
+    def load(self, bins):
+        self.bins = torch.load(bins)
+
+    def update(self, val, weights=None):
+        count = self.bincount(val, weights=weights)
+        alpha = max(self.ema_alpha, 1 / (self.iters + 1))
+        self.bins = (1. - alpha) * self.bins + alpha * count.to(self.bins.device)
+
+    def get_hist(self):
+        return self.bins
+
+
+class VectorQuantizer(nn.Module):
+    """ Nearest-codeword quantiser with straight-through value (quantization.py:177-372); nbooks == 1 only """
+
+    def __init__(self, num_embs, emb_dim, nbooks=1, balance=False):
+        if nbooks != 1:
+            raise NotImplementedError("So far we only support 'nbooks' = 1")
+        if balance is not False:
+            raise NotImplementedError("So far we only support 'balance' = False")
+        super().__init__()
+        print_("Instanciating VectorQuantizer")
+        self.num_embs = num_embs
+        self.emb_dim = emb_dim
+        self.nbooks = nbooks
+        self.balance = balance
+        self.num_embs_i = num_embs // nbooks
+        self.chunk_dims = [emb_dim]
+        self.embeddings = torch.nn.ModuleDict({"0": nn.Embedding(self.num_embs_i, emb_dim)})
+        self.embeddings["0"].weight.data.uniform_(-1.0 / self.num_embs_i, 1.0 / self.num_embs_i)
+        self.trackers = {0: EmaCodebookMeter(self.num_embs_i)}
+
+    def get_codewords(self, i='0'):
+        return self.embeddings[i].weight
+
+    def get_hist(self, i='0'):
+        return self.trackers[int(i)].get_hist()
+
+    def get_state(self):
+        return {i: self.get_hist(i).cpu().data.numpy() for i in self.trackers.keys()}
+
+    def load_state(self, bins):
+        for i, b in bins.items():
+            self.trackers[i].load(b)
+
+    def track_assigment(self, emb_ind, i):
+        self.trackers[i].update(emb_ind)
+
+    def lookup(self, z):
+        """ kernel path: (proto = z + (z_q - z), exact z_q, idx (..., 1), per-vector loss) """
+        require_cuda(z, "VectorQuantizer")
+        no_grad_only("VectorQuantizer", z)
+        out = ops.vq_lookup(f32c(z), f32c(self.embeddings["0"].weight.detach()))
+        if self.training:
+            self.track_assigment(out[2].reshape(-1, 1).detach(), 0)
+        return out
+
+    def forward_one(self, z, i, weights=None):
+        _, zq, idx, _ = self.lookup(z)
+        return zq, idx
+
+    def forward(self, z, **kwargs):
+        assert z.size(-1) == self.emb_dim, f"{z.shape = } must have {self.emb_dim = }"
+        proto, _, idx, loss = self.lookup(z)
+        return proto, {"quant_loss": loss, "commit_loss": loss.clone()}, idx
+
+    def get_codebook_entry(self, indices):
+        return self.embeddings["0"](indices.squeeze(-1))
+
+    def get_variability(self, z, action_embs=None, action_idxs=None):
+        """ variability = z - codeword (re-looked-up unless both action_embs and action_idxs are given) """
+        shape, A = z.shape[:-1], z.shape[-1]
+        if action_embs is None or action_idxs is None:
+            action_embs, action_idxs = self.forward_one(z, i=0, weights=None)
+        v = (z.reshape(-1, A) - action_embs.reshape(-1, A)).reshape(*shape, A)
+        scores = F.one_hot(action_idxs, num_classes=self.num_embs)
+        return v, scores
+
+
+class EmaVectorQuantizer(nn.Module):
+    """ VectorQuantizer whose codebook follows an exponential moving average in train mode
+    (quantization.py:87-173); buffers `ema_count` (K,), `ema_weight` (K, A). """
+
+    def __init__(self, num_embs, emb_dim, nbooks=1, balance=False, ema_alpha=0.05):
+        assert 0 <= ema_alpha <= 1.0, f"{ema_alpha = } must be in [0, 1]"
+        if nbooks != 1:
+            raise NotImplementedError(f"Only nbooks=1 is implemented, but {nbooks = }")
+        super().__init__()
+        self.num_embs = num_embs
+        self.emb_dim = emb_dim
+        self.ema_alpha = ema_alpha
+        self.epsilon = 1e-6
+        self.update = True
+        self.vq = VectorQuantizer(num_embs=num_embs, emb_dim=emb_dim, nbooks=nbooks, balance=balance).requires_grad_(False)
+        self.register_buffer('ema_count', torch.zeros(self.num_embs))
+        self.register_buffer('ema_weight', torch.empty((self.num_embs, self.emb_dim)).uniform_(-1 / num_embs, 1 / num_embs))
+
+    @torch.no_grad()
+    def ema_update(self, z, idx):
+        """ quantization.py:137-150: counts and sums of the assigned vectors, Laplace-smoothed counts """
+        B = z.shape[0]
+        zf = z.flatten(0, -2)
+        enc = F.one_hot(idx.reshape(-1), num_classes=self.num_embs).to(zf.dtype)
+        cnt = self.ema_alpha * self.ema_count + (1 - self.ema_alpha) * enc.sum(0)
+        self.ema_count = (cnt + self.epsilon) / (B + self.num_embs * self.epsilon) * B
+        self.ema_weight = self.ema_alpha * self.ema_weight + (1 - self.ema_alpha) * (enc.t() @ zf)
+        self.vq.embeddings['0'].weight.data = self.ema_weight / (self.ema_count.unsqueeze(1) + 1e-8)
+
+    def forward(self, z):
+        z_q, losses, idx = self.vq(z)
+        if self.training and self.update:
+            self.ema_update(z, idx)
+        return z_q, losses, idx
+
+    def get_codebook_entry(self, indices):
+        return self.vq.get_codebook_entry(indices)
+
+    def get_hist(self):
+        return self.ema_count.cpu().detach()
+
+    def get_codewords(self, i='0'):
+        return self.vq.get_codewords(i=i)
+
+    def get_variability(self, z, action_embs=None, action_idxs=None):
+        return self.vq.get_variability(z=z, action_embs=action_embs, action_idxs=action_idxs)

@@ -1,0 +1,244 @@
+"""
+SAVi object-centric video decomposition -- mirror of src/models/SAVi.py (same constructor kwargs = the JSON
+`model_params`, same attributes, forward / encode / decode / broadcast signatures and state_dict layout).
+
+Kernel mapping (csrc/):
+  encode : 4x ps_conv2d (the last one writes NHWC tokens and adds the weight-only position embedding in its
+           epilogue) -> ps_linear (LayerNorm fused) + ReLU -> ps_linear                 [SAVi.py:207-217]
+  slots  : SlotAttention (ps_sa_main / ps_sa_update), transition block (ps_linear / ps_mha)  [:172-195]
+  decode : first conv collapsed on the broadcast input (ps_linear + ps_dec_expand), 3x ps_conv2d,
+           ps_dec_composite (last conv + slot softmax + compositing)                       [:220-248]
+The image encoder has no temporal dependency, so `forward` encodes all frames of the clip in one batched
+pass (time-major) before running the recurrent slot loop.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ._common import DerivedWeights, require_cuda, no_grad_only, f32c
+from .BlocksUtils.attention import SlotAttention
+from .BlocksUtils.initializers import get_initializer
+from .BlocksUtils.model_blocks import SoftPositionEmbed
+from .BlocksUtils.model_utils import init_xavier_
+from .BlocksUtils.transition_models import get_transition_module
+from .EncodersDecoders.encoders import get_encoder
+from .EncodersDecoders.decoders import get_decoder
+
+
+class SAVi(nn.Module):
+    """
+    Args mirror the reference (SAVi.py:29-56): num_slots, slot_dim, num_iterations, num_iterations_first,
+    in_channels, mlp_hidden, mlp_encoder_dim, initializer (str), encoder / decoder (dicts),
+    transition_module_params (dict).
+    """
+
+    ENCODE_CHUNK_BYTES = 6 << 30      # feature tokens kept per batched encode pass
+    DECODE_CHUNK_IMAGES = 4096        # slot-images decoded per pass (1 MiB of fp32 activations each at 64x64x64)
+
+    def __init__(self, num_slots, slot_dim, num_iterations=3, num_iterations_first=None,
+                 in_channels=3, mlp_hidden=128, mlp_encoder_dim=128,
+                 initializer=None, encoder=None, decoder=None, transition_module_params=None):
+        super().__init__()
+        self.num_slots = num_slots
+        self.slot_dim = slot_dim
+        self.num_iterations_first = num_iterations_first
+        self.num_iterations = num_iterations
+        self.in_channels = in_channels
+        self.mlp_hidden = mlp_hidden
+        self.mlp_encoder_dim = mlp_encoder_dim
+
+        self.initializer = get_initializer(mode=initializer, slot_dim=slot_dim, num_slots=num_slots)
+        self.transition_module = get_transition_module(slot_dim=slot_dim, num_slots=num_slots, **transition_module_params)
+        self.build_encoder(encoder_params=encoder)
+        self.build_decoder(decoder_params=decoder)
+        self.slot_attention = SlotAttention(
+                dim_feats=self.mlp_encoder_dim,
+                dim_slots=self.slot_dim,
+                num_slots=self.num_slots,
+                num_iters_first=self.num_iterations_first,
+                num_iters=self.num_iterations,
+                mlp_hidden=self.mlp_hidden,
+            )
+        self._dec_cache = DerivedWeights()
+        self._init_model()
+
+    def build_encoder(self, encoder_params):
+        self.encoder = get_encoder(in_channels=self.in_channels, encoder=encoder_params)
+        out_feats = self.encoder.out_features
+        self.encoder_pos_embedding = SoftPositionEmbed(
+                hidden_size=out_feats,
+                resolution=encoder_params["encoder_params"].get("resolution")
+            )
+        self.encoder_mlp = nn.Sequential(
+                nn.LayerNorm(out_feats),
+                nn.Linear(out_feats, self.mlp_encoder_dim),
+                nn.ReLU(),
+                nn.Linear(self.mlp_encoder_dim, self.mlp_encoder_dim),
+            )
+
+    def build_decoder(self, decoder_params):
+        self.decoder_resolution = decoder_params["decoder_params"].get("resolution")
+        self.decoder_pos_embedding = SoftPositionEmbed(hidden_size=self.slot_dim, resolution=self.decoder_resolution)
+        self.decoder = get_decoder(in_channels=self.slot_dim, decoder=decoder_params)
+
+    # --------------------------------------------------------------------------------------------- forward
+    def forward(self, x, num_imgs=10, decode=True, **kwargs):
+        """
+        x (B, T, C, H, W) -> dict(recons_imgs (B,num_imgs,C,H,W), recons_objs (B,num_imgs,S,C,H,W),
+        masks (B,num_imgs,S,1,H,W), slot_history (B,num_imgs,S,D)); with decode=False the first three are
+        stacks of empty tensors, as in the reference (SAVi.py:135-204).
+        """
+        require_cuda(x, "SAVi.forward")
+        no_grad_only("SAVi.forward", x, self.slot_attention.to_q.weight)
+        B = x.shape[0]
+        predicted = self.initializer(batch_size=B, **kwargs)
+        predicted = f32c(predicted.detach())
+
+        slot_history, recons_h, objs_h, masks_h = [], [], [], []
+        feats_all = self._encode_clip(x, num_imgs)            # list of (t0, (t1-t0, B, N, D)) chunks
+        for t in range(num_imgs):
+            feats = self._feats_at(feats_all, t)
+            slots = self.slot_attention(inputs=feats, slots=predicted, step=t)
+            if decode:
+                recon, (recons, masks) = self.decode(slots)
+            else:
+                recon, recons, masks = torch.tensor([]), torch.tensor([]), torch.tensor([])
+            predicted = self.transition_module(slots)
+            slot_history.append(slots)
+            recons_h.append(recon)
+            objs_h.append(recons)
+            masks_h.append(masks)
+        return {
+            "recons_imgs": torch.stack(recons_h, dim=1),
+            "recons_objs": torch.stack(objs_h, dim=1),
+            "masks": torch.stack(masks_h, dim=1),
+            "slot_history": torch.stack(slot_history, dim=1),
+        }
+
+    def _encode_clip(self, x, num_imgs):
+        """ batched, time-major encode of frames [0, num_imgs) in chunks bounded by ENCODE_CHUNK_BYTES """
+        B, _, C, H, W = x.shape
+        N = H * W
+        per_frame = B * N * self.mlp_encoder_dim * 4
+        step = max(1, min(num_imgs, self.ENCODE_CHUNK_BYTES // max(per_frame, 1)))
+        chunks = []
+        for t0 in range(0, num_imgs, step):
+            t1 = min(num_imgs, t0 + step)
+            frames = x[:, t0:t1].transpose(0, 1).reshape((t1 - t0) * B, C, H, W)
+            feats = self.encode(frames).view(t1 - t0, B, N, self.mlp_encoder_dim)
+            chunks.append((t0, feats))
+        return chunks
+
+    @staticmethod
+    def _feats_at(chunks, t):
+        for t0, feats in chunks:
+            if t0 <= t < t0 + feats.shape[0]:
+                return feats[t - t0]
+        raise IndexError(t)
+
+    # --------------------------------------------------------------------------------------------- encode
+    def encode(self, x):
+        """ images (M, C, H, W) -> feature tokens (M, H*W, mlp_encoder_dim)   (SAVi.py:207-217) """
+        require_cuda(x, "SAVi.encode")
+        no_grad_only("SAVi.encode", x, self.encoder_mlp[1].weight)
+        x = f32c(x)
+        M, _, H, W = x.shape
+        tokens = self.encoder.run(x, last_nhwc_addend=self.encoder_pos_embedding.table(channels_last=True))
+        tokens = tokens.view(M, H * W, -1)
+        ln, fc1, fc2 = self.encoder_mlp[0], self.encoder_mlp[1], self.encoder_mlp[3]
+        h = ops.linear(tokens, fc1.weight, fc1.bias, ln=(ln.weight, ln.bias, ln.eps), act=ops.ACT_RELU)
+        return ops.linear(h, fc2.weight, fc2.bias)
+
+    # --------------------------------------------------------------------------------------------- decode
+    def _decoder_constants(self):
+        """
+        Weight-only tensors of the collapsed first decoder convolution (cached per weight version):
+          Wsum (ncls*ncls*C1, D): tap-sums of conv1's weights for the (2p+1)^2 border classes,
+          P (C1, H, W): conv1(position embedding) + bias.
+        """
+        blocks = self.decoder.conv_blocks()
+        conv1 = blocks[0].conv
+        pe = self.decoder_pos_embedding
+        srcs = [conv1.weight, conv1.bias, pe.projection.weight, pe.projection.bias]
+
+        def build():
+            w = conv1.weight.detach()                      # (C1, D, k, k)
+            k = w.shape[-1]
+            p = k // 2
+
+            def taps(c):                                   # valid kernel taps along one axis for border class c
+                if c < p:
+                    return slice(p - c, k)
+                if c > p:
+                    return slice(0, k - (c - p))
+                return slice(0, k)
+            rows = []
+            for cy in range(2 * p + 1):
+                for cx in range(2 * p + 1):
+                    rows.append(w[:, :, taps(cy), taps(cx)].sum(dim=(2, 3)))     # (C1, D)
+            wsum = torch.stack(rows, dim=0).reshape(-1, w.shape[1]).contiguous()  # (ncls^2 * C1, D)
+            pos = pe.table(channels_last=False)[None].contiguous()               # (1, D, H, W)
+            P = ops.conv2d(pos, blocks[0].packed_weight(), conv1.bias, k, relu=False)   # conv1(posemb) + bias
+            return wsum, P[0].contiguous(), k
+        return self._dec_cache.get(srcs, build)
+
+    def decode(self, slots):
+        """
+        slots (M, S, D) -> recon_combined (M, C, H, W), (recons (M, S, C, H, W) un-masked, masks (M, S, 1, H, W))
+        (SAVi.py:220-234).
+        """
+        require_cuda(slots, "SAVi.decode")
+        no_grad_only("SAVi.decode", slots, self.decoder.final_conv().weight)
+        slots = f32c(slots)
+        M, S, D = slots.shape
+        H, W = self.decoder_resolution
+        dec = self.decoder
+        if dec.upsample not in (None, 1) or self.in_channels != 3:
+            raise NotImplementedError("SAVi.decode kernels cover upsample in (None, 1) and RGB outputs "
+                                      "(every shipped config); got upsample=%r in_channels=%r" % (dec.upsample, self.in_channels))
+        blocks = dec.conv_blocks()
+        wsum, P, k = self._decoder_constants()
+        C1 = blocks[0].conv.out_channels
+        final = dec.final_conv()
+        wfin = self._final_packed(final)
+        recon_l, recons_l, masks_l = [], [], []
+        step = max(1, self.DECODE_CHUNK_IMAGES // S)
+        for m0 in range(0, M, step):
+            m1 = min(M, m0 + step)
+            sl = slots[m0:m1].reshape((m1 - m0) * S, D)
+            G = ops.linear(sl, wsum)                                           # (n_img, ncls^2 * C1)
+            h = ops.dec_expand(G, P, (m1 - m0) * S, C1, H, W, k)
+            for blk in blocks[1:]:
+                h = blk.run(h)
+            r, rs, ms = ops.dec_composite(h, wfin, final.bias, m1 - m0, S)
+            recon_l.append(r); recons_l.append(rs); masks_l.append(ms)
+        if len(recon_l) == 1:
+            return recon_l[0], (recons_l[0], masks_l[0])
+        return torch.cat(recon_l), (torch.cat(recons_l), torch.cat(masks_l))
+
+    def _final_packed(self, conv):
+        if not hasattr(self, "_fin_cache"):
+            self._fin_cache = DerivedWeights()
+        return self._fin_cache.get([conv.weight], lambda: ops.pack_conv_weight(conv.weight))
+
+    def broadcast(self, slots):
+        """ (B, S, D) -> (B*S, D, H, W): slot broadcast + position embedding (SAVi.py:237-248).  The decode
+        kernels never materialise this tensor; the method exists for API parity (plain tensor ops). """
+        D = slots.shape[-1]
+        H, W = self.decoder_resolution
+        grid = slots.reshape(-1, D, 1, 1).expand(-1, D, H, W)
+        return grid + self.decoder_pos_embedding.table(channels_last=False)[None]
+
+    @torch.no_grad()
+    def _init_model(self):
+        """ Xavier weights / zero biases, zero GRU biases, orthogonal recurrent GRU weights (SAVi.py:251-267) """
+        init_xavier_(self)
+        torch.nn.init.zeros_(self.slot_attention.gru.bias_ih)
+        torch.nn.init.zeros_(self.slot_attention.gru.bias_hh)
+        torch.nn.init.orthogonal_(self.slot_attention.gru.weight_hh)
+        if hasattr(self.slot_attention, "slots_mu"):
+            limit = math.sqrt(6.0 / (1 + self.slot_attention.dim_slots))
+            torch.nn.init.uniform_(self.slot_attention.slots_mu, -limit, limit)
+            torch.nn.init.uniform_(self.slot_attention.slots_sigma, -limit, limit)

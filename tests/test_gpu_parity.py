@@ -1,0 +1,282 @@
+"""
+GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI (playslot_b200.ops / models),
+against (a) the CPU oracle on the same seeded inputs and (b) the golden vectors produced by the real
+reference.  Tolerance (fp32): rel-L2 <= 1e-4 and max|diff|/max|ref| <= 1e-4 (BASELINE.json north_star);
+integer outputs (VQ indices) bit-exact; slot order compared index-wise.
+"""
+import copy
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from golden_util import GOLDEN_DIR, PIPELINE_CASES, load_case
+from build_util import make_savi, make_predictor, to_dev, FixedRandn
+from synth import synth_state_dict, rel_l2, max_rel
+from oracle import playslot_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda"
+
+
+def check(name, got, ref, tol=TOL):
+    got, ref = got.detach().cpu(), ref.detach().cpu()
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(got).all(), f"{name}: non-finite values"
+    r, m = rel_l2(got, ref), max_rel(got, ref)
+    assert r <= tol and m <= tol, f"{name}: rel_l2={r:.3e} max_rel={m:.3e} (tol {tol:.0e})"
+
+
+def g(*shape, seed=0, scale=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=gen) * scale
+
+
+# ----------------------------------------------------------------------------------------------- primitives
+
+@pytest.mark.parametrize("M,N,K", [(1, 8, 16), (64, 64, 16), (130, 72, 36), (515, 384, 128), (4096, 1024, 256), (300, 128, 1024)])
+@pytest.mark.parametrize("mode", ["plain", "ln_gelu_res", "relu_bcast"])
+def test_linear(M, N, K, mode):
+    from playslot_b200 import ops
+    x, w, b = g(M, K, seed=1), g(N, K, seed=2, scale=K ** -0.5), g(N, seed=3, scale=0.1)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    if mode == "plain":
+        y = ops.linear(xd, wd, bd)
+        ref = F.linear(x.double(), w.double(), b.double())
+    elif mode == "ln_gelu_res":
+        gam, bet, res = 1 + 0.1 * g(K, seed=4), 0.1 * g(K, seed=5), g(M, N, seed=6)
+        y = ops.linear(xd, wd, bd, ln=(gam.to(DEV), bet.to(DEV), 1e-6), act=ops.ACT_GELU, res=res.to(DEV))
+        h = F.layer_norm(x.double(), (K,), gam.double(), bet.double(), 1e-6)
+        ref = F.gelu(F.linear(h, w.double(), b.double())) + res.double()
+    else:
+        R = 5
+        div = 3
+        table = g(R, N, seed=7)
+        y = ops.linear(xd, wd, None, act=ops.ACT_RELU, res=table.to(DEV), res_div=div, res_mod=R)
+        rows = (torch.arange(M) // div) % R
+        ref = F.relu(F.linear(x.double(), w.double())) + table.double()[rows]
+    check(f"linear[{mode}]", y, ref.float())
+
+
+@pytest.mark.parametrize("n_seq,L,H,dh,spf", [(3, 9, 4, 64, 0), (2, 64, 8, 64, 8), (5, 8, 4, 32, 0), (2, 160, 8, 64, 16), (4, 30, 8, 64, 6)])
+def test_mha(n_seq, L, H, dh, spf):
+    from playslot_b200 import ops
+    inner = H * dh
+    qkv = g(n_seq * L, 3 * inner, seed=L)
+    res = g(n_seq * L, inner, seed=L + 1)
+    out = ops.mha(qkv.to(DEV), n_seq, L, H, dh, spf, res=res.to(DEV))
+    q, k, v = [t.double().view(n_seq, L, H, dh).transpose(1, 2) for t in qkv.split(inner, dim=1)]
+    dots = q @ k.transpose(-1, -2) * dh ** -0.5
+    if spf:
+        mask = O.block_causal_mask(L // spf, spf)
+        dots = dots.masked_fill(mask[None, None] == 0, -1e9)
+    ref = (torch.softmax(dots, -1) @ v).transpose(1, 2).reshape(n_seq * L, inner) + res.double()
+    check("mha", out, ref.float())
+
+
+@pytest.mark.parametrize("n,Cin,Cout,H,W,k,relu", [(3, 3, 32, 64, 64, 5, 1), (2, 32, 32, 64, 64, 5, 0), (2, 64, 64, 64, 64, 5, 1),
+                                                    (1, 128, 64, 64, 64, 5, 0), (2, 64, 64, 32, 48, 3, 1), (1, 3, 64, 128, 128, 5, 1)])
+def test_conv2d(n, Cin, Cout, H, W, k, relu):
+    from playslot_b200 import ops
+    x, w, b = g(n, Cin, H, W, seed=1), g(Cout, Cin, k, k, seed=2, scale=(Cin * k * k) ** -0.5), g(Cout, seed=3, scale=0.1)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2)
+    ref = F.relu(ref) if relu else ref
+    wp = ops.pack_conv_weight(w.to(DEV))
+    y = ops.conv2d(x.to(DEV), wp, b.to(DEV), k, relu)
+    check("conv2d nchw", y, ref.float())
+    add = g(H * W, Cout, seed=4)
+    y2 = ops.conv2d(x.to(DEV), wp, b.to(DEV), k, relu, out_nhwc=True, addend=add.to(DEV))
+    check("conv2d nhwc+addend", y2, (ref.permute(0, 2, 3, 1) + add.double().view(1, H, W, Cout)).float())
+
+
+# ----------------------------------------------------------------------------------------------- SlotAttention
+
+def _sa_module(S, sd, mlp_hidden=256, it_first=3, it=1):
+    from playslot_b200.models.BlocksUtils.attention import SlotAttention
+    m = SlotAttention(dim_feats=128, dim_slots=128, num_slots=S, num_iters_first=it_first, num_iters=it, mlp_hidden=mlp_hidden).eval()
+    m.load_state_dict({k[len("slot_attention."):]: v for k, v in sd.items()}, strict=True)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("key", ["S8", "S4"])
+def test_slot_attention_golden(key):
+    """ against the real reference's SlotAttention (fixture made by oracle/make_golden.py) """
+    fx = torch.load(os.path.join(GOLDEN_DIR, "slot_attention.pt"), weights_only=False)[key]
+    S = int(key[1:])
+    sd = synth_state_dict(fx["manifest"], fx["weight_seed"], fx["sharpen"])
+    gen = torch.Generator().manual_seed(fx["input_seed"])
+    feats = torch.randn(2, 4096, 128, generator=gen)
+    slots = torch.randn(2, S, 128, generator=gen)
+    m = _sa_module(S, sd)
+    with torch.no_grad():
+        o3 = m(feats.to(DEV), slots.to(DEV), step=0)
+        m3 = m.get_attention_masks().clone()
+        o1 = m(feats.to(DEV), slots.to(DEV), step=1)
+        m1 = m.get_attention_masks().clone()
+    check("slots step0", o3, fx["slots_step0"])
+    check("masks step0", m3, fx["masks_step0"])
+    check("slots step1", o1, fx["slots_step1"])
+    check("masks step1", m1, fx["masks_step1"])
+
+
+@pytest.mark.parametrize("B,N,S,hidden,iters,sharpen", [(3, 1000, 6, 128, 2, 1.0), (1, 16384, 16, 256, 3, 4.0), (5, 4096, 3, 256, 1, 8.0),
+                                                         (2, 77, 8, 256, 3, 1.0), (2, 256, 1, 128, 2, 1.0)])
+def test_slot_attention_oracle(B, N, S, hidden, iters, sharpen):
+    """ ragged / large token counts, 1..16 slots, vs the CPU oracle """
+    from playslot_b200.models.BlocksUtils.attention import SlotAttention
+    ref_mod = SlotAttention(128, 128, S, iters, iters, hidden)
+    man = {"slot_attention." + k: list(v.shape) for k, v in ref_mod.state_dict().items()}
+    sd = synth_state_dict(man, 40 + S, sharpen)
+    feats, slots = g(B, N, 128, seed=N), g(B, S, 128, seed=N + 1)
+    feats = feats * (1.0 + 0.5 * g(B, N, 1, seed=3)) + 0.7 * g(B, N, 1, seed=4)     # per-token scale / offset
+    with torch.no_grad():
+        ro, rm = O.slot_attention(sd, feats, slots, iters)
+        m = _sa_module(S, sd, hidden, iters, iters)
+        o = m(feats.to(DEV), slots.to(DEV), step=0)
+        mk = m.get_attention_masks()
+    check("slots", o, ro)
+    check("masks", mk, rm)
+
+
+def test_slot_attention_full_size_properties():
+    """ config-2 size (B=64, N=4096, D=128, S=8, 3 iterations): size-independent properties """
+    from playslot_b200.models.BlocksUtils.attention import SlotAttention
+    S = 8
+    man = {"slot_attention." + k: list(v.shape) for k, v in SlotAttention(128, 128, S, 3, 1, 256).state_dict().items()}
+    sd = synth_state_dict(man, 77, 4.0)
+    m = _sa_module(S, sd)
+    feats, slots = g(64, 4096, 128, seed=5).to(DEV), g(64, S, 128, seed=6).to(DEV)
+    with torch.no_grad():
+        o = m(feats, slots, step=0)
+        mk = m.get_attention_masks().clone()
+        # (1) the masks are a softmax over slots plus eps
+        colsum = mk.sum(dim=1)
+        assert torch.allclose(colsum, torch.full_like(colsum, 1.0 + S * 1e-8), atol=2e-6)
+        assert float(mk.min()) >= 1e-8 * 0.999
+        # (2) frames are independent: any sub-batch gives the same rows
+        sub = [3, 17, 63]
+        o_sub = m(feats[sub].contiguous(), slots[sub].contiguous(), step=0)
+        check("batch independence", o_sub, o[sub], 2e-6)
+        # (3) permutation equivariance over slots: ordering of the outputs follows the ordering of the inputs
+        perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device=DEV)
+        o_p = m(feats, slots[:, perm].contiguous(), step=0)
+        check("slot-order equivariance", o_p, o[:, perm], 2e-5)
+        check("mask slot-order equivariance", m.get_attention_masks(), mk[:, perm], 2e-5)
+        # (4) spot check of 2 frames against the oracle
+        ro, rm = O.slot_attention(sd, feats[:2].cpu(), slots[:2].cpu(), 3)
+    check("slots vs oracle", o[:2], ro)
+    check("masks vs oracle", mk[:2], rm)
+
+
+# ----------------------------------------------------------------------------------------------- blocks / stages
+
+@pytest.mark.parametrize("E,H,dh,mlp,proj,spf,L", [(128, 4, 32, 512, False, 0, 8), (256, 4, 64, 1024, True, 0, 9), (256, 8, 64, 1024, True, 8, 64),
+                                                    (128, 8, 64, 512, True, 6, 48)])
+def test_transformer_block(E, H, dh, mlp, proj, spf, L):
+    from playslot_b200.models.BlocksUtils.attention import TransformerEncoderBlock
+    blk = TransformerEncoderBlock(embed_dim=E, head_dim=dh, num_heads=H, mlp_size=mlp, project_out=proj).eval()
+    man = {"b." + k: list(v.shape) for k, v in blk.state_dict().items()}
+    sd = synth_state_dict(man, 5)
+    blk.load_state_dict({k[2:]: v for k, v in sd.items()})
+    x = g(3, L, E, seed=9)
+    mask = O.block_causal_mask(L // spf, spf) if spf else None
+    with torch.no_grad():
+        ref = O.transformer_block(sd, "b", x, H, dh, mask)
+        out = blk.to(DEV)(x.to(DEV), mask=mask.to(DEV) if mask is not None else None)
+    check("transformer block", out, ref)
+
+
+@pytest.mark.parametrize("case", ["blockpush", "gridshapes5"])
+def test_encode_and_decode_vs_oracle(case):
+    fx, ssd, psd, video, noise, init_noise = load_case(case)
+    scfg = fx["savi_cfg"]
+    savi = make_savi(scfg, ssd, DEV)
+    frames = video[:, :2].reshape(-1, *video.shape[2:])
+    S, D = scfg["num_slots"], scfg["slot_dim"]
+    slots = g(3, S, D, seed=2)
+    with torch.no_grad():
+        check("encode", savi.encode(frames.to(DEV)), O.encode(ssd, frames))
+        recon, (recons, masks) = savi.decode(slots.to(DEV))
+        r_recon, r_recons, r_masks = O.decode(ssd, scfg, slots)
+    check("recon", recon, r_recon)
+    check("recons", recons, r_recons)
+    check("masks", masks, r_masks)
+    ms = masks.sum(dim=1)
+    assert torch.allclose(ms, torch.ones_like(ms), atol=1e-5)
+    check("recon == sum(rgb*mask)", recon, (recons * masks).sum(dim=1), 1e-5)
+
+
+# ----------------------------------------------------------------------------------------------- whole pipeline
+
+@pytest.mark.parametrize("case", PIPELINE_CASES)
+def test_pipeline_matches_reference_golden(case):
+    """ seed + rollout pipeline of 05_evaluate_PlaySlot.py:112-139 against vectors produced by the real reference """
+    fx, ssd, psd, video, noise, init_noise = load_case(case)
+    scfg, pcfg = fx["savi_cfg"], fx["predictor_cfg"]
+    B, ns, npred = fx["B"], fx["num_seed"], fx["num_preds"]
+    savi = make_savi(scfg, ssd, DEV)
+    pred = make_predictor(fx["predictor_name"], pcfg, psd, DEV)
+    S, D = scfg["num_slots"], scfg["slot_dim"]
+    with torch.no_grad():
+        if init_noise is not None:
+            with FixedRandn(init_noise):
+                out = savi(video.to(DEV), num_imgs=ns + npred, decode=False)
+        else:
+            out = savi(video.to(DEV), num_imgs=ns + npred, decode=False)
+        sh = out["slot_history"]
+        check("slot_history", sh, fx["slot_history"])
+        check("sa masks (last frame)", savi.slot_attention.get_attention_masks(), fx["sa_masks_last"])
+        # feed the reference's slots to the predictor so that stage errors do not compound in this check
+        sh_ref = fx["slot_history"].to(DEV)
+        with FixedRandn(noise):
+            act = pred.latent_action.compute_actions(sh_ref)
+        assert torch.equal(act["action_idxs"].cpu().reshape(-1), fx["action_idxs"].reshape(-1)), "VQ indices differ"
+        check("action_proto", act["action_proto"], fx["action_proto"])
+        check("action_variability", act["action_variability"], fx["action_variability"])
+        check("action_dist", act["action_dist"], fx["action_dist"])
+        check("sampled_latent_action", act["sampled_latent_action"], fx["sampled_latent_action"])
+        with FixedRandn(noise):
+            ps, _ = pred.forward_multiple_samples(sh_ref, 1, ns, npred, use_posterior=True)
+        assert ps.shape == (B, 1, npred, S, D)
+        check("pred_slots", ps[:, 0], fx["pred_slots"])
+        k = fx["decode_last"]
+        recon, (recons, masks) = savi.decode(fx["pred_slots"][:, -k:].reshape(B * k, S, D).to(DEV))
+        check("recon", recon, fx["recon"])
+        check("masks", masks, fx["masks"])
+        check("recons_m0", recons[0], fx["recons_m0"])
+        # end-to-end chained run (our slots -> our predictor -> our decoder): looser, errors compound over 11 frames
+        with FixedRandn(noise):
+            ps2, _ = pred.forward_multiple_samples(sh, 1, ns, npred, use_posterior=True)
+        check("pred_slots (chained)", ps2[:, 0], fx["pred_slots"], 5e-4)
+
+
+def test_decode_true_shapes_and_empty_stacks():
+    fx, ssd, psd, video, noise, init_noise = load_case("buttonpress")
+    savi = make_savi(fx["savi_cfg"], ssd, DEV)
+    with torch.no_grad():
+        out = savi(video[:1, :2].to(DEV), num_imgs=2, decode=True)
+        assert out["recons_imgs"].shape == (1, 2, 3, 64, 64)
+        assert out["recons_objs"].shape == (1, 2, 4, 3, 64, 64)
+        assert out["masks"].shape == (1, 2, 4, 1, 64, 64)
+        assert out["slot_history"].shape == (1, 2, 4, 128)
+        out = savi(video[:1, :2].to(DEV), num_imgs=2, decode=False)
+        assert out["recons_imgs"].shape == (1, 2, 0)
+        r0, _, _ = O.decode(ssd, fx["savi_cfg"], out["slot_history"][:, 0].cpu())
+        out2 = savi(video[:1, :2].to(DEV), num_imgs=2, decode=True)
+    check("decode=True recon", out2["recons_imgs"][:, 0], r0)
+
+
+def test_prior_rollout_runs_and_is_seeded():
+    """ prior samples (random codebook actions): shapes and determinism under a fixed seed """
+    fx, ssd, psd, video, noise, init_noise = load_case("blockpush")
+    pred = make_predictor(fx["predictor_name"], fx["predictor_cfg"], psd, DEV)
+    sh = fx["slot_history"].to(DEV)
+    with torch.no_grad():
+        torch.manual_seed(3); torch.cuda.manual_seed(3)
+        a, ia = pred.forward_multiple_samples(sh, 2, 6, 3, use_posterior=False)
+        torch.manual_seed(3); torch.cuda.manual_seed(3)
+        b, ib = pred.forward_multiple_samples(sh, 2, 6, 3, use_posterior=False)
+    assert a.shape == (2, 2, 3, 8, 128) and torch.equal(a, b) and torch.equal(ia, ib)
+    assert torch.isfinite(a).all()
