@@ -161,7 +161,7 @@ def conv_flops(meta):
 
 def sa_main_bytes(meta):
     B, N, S, D, masks = meta
-    return B * N * D * 4 + (B * S * N * 4 if masks else 0) + 2 * B * S * (D + 2) * 4
+    return B * N * D * 4 + (B * S * N * 4 if masks else 0) + 2 * B * S * (D + 1) * 4
 
 
 def slot_attention_config2(pk):

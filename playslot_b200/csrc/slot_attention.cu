@@ -1,9 +1,10 @@
 // SlotAttention iteration (reference: src/models/BlocksUtils/attention.py:92-119), fp32, re-associated so
 // that k and v are never materialised:
-//     dots[s,j]   = scale * q_s . (W_k xhat_j)      = rstd_j * (A_s . x_j - mu_j * a1_s) + a0_s
-//     updates[s]  = W_v * sum_j attn_n[s,j] xhat_j  = W_v * (gamma o (U_s - um_s) + beta * rs_s) / rs_s
-// with xhat = LayerNorm(x), A_s = scale * (q_s W_k) o gamma, a1_s = sum_c A_s[c], a0_s = scale * (q_s W_k) . beta,
-// w[s,j] = attn[s,j] * rstd_j, U_s = sum_j w[s,j] x_j, um_s = sum_j w[s,j] mu_j, rs_s = sum_j attn[s,j].
+//     dots[s,j]   = scale * q_s . (W_k xhat_j)      = rstd_j * (A_s . (x_j - mu_j)) + a0_s
+//     updates[s]  = W_v * sum_j attn_n[s,j] xhat_j  = W_v * (gamma o U_s + beta * rs_s) / rs_s
+// with xhat = LayerNorm(x), A_s = scale * (q_s W_k) o gamma, a0_s = scale * (q_s W_k) . beta,
+// w[s,j] = attn[s,j] * rstd_j, U_s = sum_j w[s,j] (x_j - mu_j), rs_s = sum_j attn[s,j].
+// Tokens are centred (x - mu) before both contractions so that no large terms have to cancel afterwards.
 // One iteration = ps_sa_main (streams the feature tokens once: logits, softmax over slots, +eps, masks,
 // weighted sums as per-chunk partials) followed by ps_sa_update (reduces the partials, renormalises,
 // v-projection, GRUCell, residual MLP, and the q / A preparation of the next iteration).
@@ -31,8 +32,9 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
     float* xs = sm;                                   // [2][SA_TT][SA_XS]
     float* As = xs + 2 * SA_TT * SA_XS;               // [SMAX][128]
     float* ws = As + SMAX * SA_D;                     // [SA_TT][SMAX]
-    float* red = ws + SA_TT * SMAX;                   // [8][2*SMAX]
-    __shared__ float s_a0[SMAX], s_a1[SMAX];
+    float* mus = ws + SA_TT * SMAX;                   // [SA_TT] token means
+    float* red = mus + SA_TT;                         // [8][SMAX]
+    __shared__ float s_a0[SMAX];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, chunk = blockIdx.x;
@@ -47,10 +49,7 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
         const int s = idx / SA_D;
         As[idx] = (s < S) ? p.A[((size_t)b * S + s) * SA_D + (idx - s * SA_D)] : 0.f;
     }
-    if (tid < SMAX) {
-        s_a0[tid] = (tid < S) ? p.a0[b * S + tid] : 0.f;
-        s_a1[tid] = (tid < S) ? p.a1[b * S + tid] : 0.f;
-    }
+    if (tid < SMAX) s_a0[tid] = (tid < S) ? p.a0[b * S + tid] : 0.f;
 
     auto load_tile = [&](int t, int buf) {
         float* dst = xs + buf * SA_TT * SA_XS;
@@ -72,9 +71,9 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
     float U[SMAX][4];
 #pragma unroll
     for (int s = 0; s < SMAX; ++s) { U[s][0] = U[s][1] = U[s][2] = U[s][3] = 0.f; }
-    float rs_acc[SMAX], um_acc[SMAX];
+    float rs_acc[SMAX];
 #pragma unroll
-    for (int s = 0; s < SMAX; ++s) { rs_acc[s] = 0.f; um_acc[s] = 0.f; }
+    for (int s = 0; s < SMAX; ++s) rs_acc[s] = 0.f;
 
     load_tile(0, 0);
     for (int t = 0; t < ntiles; ++t) {
@@ -99,12 +98,6 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
                 const float4 v1 = *reinterpret_cast<const float4*>(r1 + c);
                 sum0 += (v0.x + v0.y) + (v0.z + v0.w);
                 sum1 += (v1.x + v1.y) + (v1.z + v1.w);
-#pragma unroll
-                for (int s = 0; s < SMAX; ++s) {
-                    const float4 a = *reinterpret_cast<const float4*>(As + s * SA_D + c);
-                    dot0[s] = fmaf(a.x, v0.x, fmaf(a.y, v0.y, fmaf(a.z, v0.z, fmaf(a.w, v0.w, dot0[s]))));
-                    dot1[s] = fmaf(a.x, v1.x, fmaf(a.y, v1.y, fmaf(a.z, v1.z, fmaf(a.w, v1.w, dot1[s]))));
-                }
             }
             sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
             sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
@@ -113,13 +106,18 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = (4 * i + q) * 4;
-                const float4 v0 = *reinterpret_cast<const float4*>(r0 + c);
-                const float4 v1 = *reinterpret_cast<const float4*>(r1 + c);
-                float d;
-                d = v0.x - mean0; sq0 = fmaf(d, d, sq0); d = v0.y - mean0; sq0 = fmaf(d, d, sq0);
-                d = v0.z - mean0; sq0 = fmaf(d, d, sq0); d = v0.w - mean0; sq0 = fmaf(d, d, sq0);
-                d = v1.x - mean1; sq1 = fmaf(d, d, sq1); d = v1.y - mean1; sq1 = fmaf(d, d, sq1);
-                d = v1.z - mean1; sq1 = fmaf(d, d, sq1); d = v1.w - mean1; sq1 = fmaf(d, d, sq1);
+                float4 v0 = *reinterpret_cast<const float4*>(r0 + c);
+                float4 v1 = *reinterpret_cast<const float4*>(r1 + c);
+                v0.x -= mean0; v0.y -= mean0; v0.z -= mean0; v0.w -= mean0;
+                v1.x -= mean1; v1.y -= mean1; v1.z -= mean1; v1.w -= mean1;
+                sq0 = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, sq0))));
+                sq1 = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, sq1))));
+#pragma unroll
+                for (int s = 0; s < SMAX; ++s) {
+                    const float4 a = *reinterpret_cast<const float4*>(As + s * SA_D + c);
+                    dot0[s] = fmaf(a.x, v0.x, fmaf(a.y, v0.y, fmaf(a.z, v0.z, fmaf(a.w, v0.w, dot0[s]))));
+                    dot1[s] = fmaf(a.x, v1.x, fmaf(a.y, v1.y, fmaf(a.z, v1.z, fmaf(a.w, v1.w, dot1[s]))));
+                }
             }
             sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
             sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2);
@@ -135,8 +133,8 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
 #pragma unroll
             for (int s = 0; s < SMAX; ++s) {
                 if (s < S) {
-                    dot0[s] = rstd0 * (dot0[s] - mean0 * s_a1[s]) + s_a0[s];
-                    dot1[s] = rstd1 * (dot1[s] - mean1 * s_a1[s]) + s_a0[s];
+                    dot0[s] = rstd0 * dot0[s] + s_a0[s];
+                    dot1[s] = rstd1 * dot1[s] + s_a0[s];
                     mx0 = fmaxf(mx0, dot0[s]); mx1 = fmaxf(mx1, dot1[s]);
                 }
             }
@@ -160,15 +158,14 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
             }
             if (q == 0) {
 #pragma unroll
-                for (int s = 0; s < SMAX; ++s) {
-                    rs_acc[s] += dot0[s] + dot1[s];
-                    um_acc[s] = fmaf(dot0[s] * rstd0, mean0, fmaf(dot1[s] * rstd1, mean1, um_acc[s]));
-                }
+                for (int s = 0; s < SMAX; ++s) rs_acc[s] += dot0[s] + dot1[s];
             }
             if (q == 0) {
+                mus[jp] = mean0;
 #pragma unroll
                 for (int s = 0; s < SMAX; ++s) ws[jp * SMAX + s] = dot0[s] * rstd0;
             } else if (q == 1) {
+                mus[jp + 64] = mean1;
 #pragma unroll
                 for (int s = 0; s < SMAX; ++s) ws[(jp + 64) * SMAX + s] = dot1[s] * rstd1;
             } else if (p.masks) {
@@ -187,7 +184,9 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
         {
 #pragma unroll 4
             for (int j = warp; j < SA_TT; j += 8) {
-                const float4 xv = *reinterpret_cast<const float4*>(xt + j * SA_XS + c4b * 4);
+                float4 xv = *reinterpret_cast<const float4*>(xt + j * SA_XS + c4b * 4);
+                const float mu = mus[j];
+                xv.x -= mu; xv.y -= mu; xv.z -= mu; xv.w -= mu;
                 const float* wr = ws + j * SMAX;
 #pragma unroll
                 for (int s4 = 0; s4 < SMAX; s4 += 4) {
@@ -215,11 +214,10 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
 #pragma unroll
     for (int s = 0; s < SMAX; ++s) {
         const float r = warp_sum(rs_acc[s]);             // lanes with q != 0 hold zeros
-        const float u = warp_sum(um_acc[s]);
-        if (lane == 0) { red[warp * 2 * SMAX + s] = r; red[warp * 2 * SMAX + SMAX + s] = u; }
+        if (lane == 0) red[warp * SMAX + s] = r;
     }
     __syncthreads();
-    const int pstride = S * SA_D + 2 * S;
+    const int pstride = S * SA_D + S;
     float* pout = p.partial + ((size_t)b * p.CH + chunk) * pstride;
     for (int idx = tid; idx < S * SA_D; idx += 256) {
         float v = 0.f;
@@ -227,18 +225,17 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
         for (int w = 0; w < 8; ++w) v += scratch[(w * SMAX) * SA_D + (idx / SA_D) * SA_D + (idx % SA_D)];
         pout[idx] = v;
     }
-    if (tid < 2 * S) {
-        const int s = tid % S, which = tid / S;
+    if (tid < S) {
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[w * 2 * SMAX + which * SMAX + s];
-        pout[S * SA_D + which * S + s] = v;
+        for (int w = 0; w < 8; ++w) v += red[w * SMAX + tid];
+        pout[S * SA_D + tid] = v;
     }
 }
 
 template <int SMAX>
 static int launch_sa_main(const SaMainParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)(2 * SA_TT * SA_XS + SMAX * SA_D + SA_TT * SMAX + 8 * 2 * SMAX) * sizeof(float);
+    const size_t smem = (size_t)(2 * SA_TT * SA_XS + SMAX * SA_D + SA_TT * SMAX + SA_TT + 8 * SMAX) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         PS_CUDA(cudaFuncSetAttribute(sa_main_kernel<SMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -250,7 +247,7 @@ static int launch_sa_main(const SaMainParams& p, cudaStream_t st) {
     return PS_OK;
 }
 
-extern "C" int ps_sa_partial_floats(int S) { return S * SA_D + 2 * S; }
+extern "C" int ps_sa_partial_floats(int S) { return S * SA_D + S; }
 
 extern "C" int ps_sa_main(const float* x, const float* A, const float* a0, const float* a1, float* partial,
                           float* masks, int B, int N, int S, int dim, int n_chunks, float ln_eps,
@@ -334,7 +331,7 @@ __global__ __launch_bounds__(SU_THREADS) void sa_update_kernel(SaUpdParams p) {
     __shared__ __align__(16) float s_gi[3 * SA_D * SU_RS];
     __shared__ __align__(16) float s_gh[3 * SA_D * SU_RS];
     __shared__ __align__(16) float s_hid[512 * SU_RS];
-    __shared__ float s_rs[SU_RS], s_um[SU_RS];
+    __shared__ float s_rs[SU_RS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, r0 = blockIdx.x * SU_RS;
     const int S = p.S;
@@ -347,14 +344,13 @@ __global__ __launch_bounds__(SU_THREADS) void sa_update_kernel(SaUpdParams p) {
     __syncthreads();
 
     if (p.do_update) {
-        const int pstride = S * SA_D + 2 * S;
+        const int pstride = S * SA_D + S;
         const float* pb = p.partial + (size_t)b * p.CH * pstride;
-        if (tid < 2 * SU_RS) {
-            const int r = tid % SU_RS, which = tid / SU_RS;
+        if (tid < SU_RS) {
             float v = 0.f;
-            if (r < nr)
-                for (int c = 0; c < p.CH; ++c) v += pb[(size_t)c * pstride + S * SA_D + which * S + r0 + r];
-            if (which == 0) s_rs[r] = v; else s_um[r] = v;
+            if (tid < nr)
+                for (int c = 0; c < p.CH; ++c) v += pb[(size_t)c * pstride + S * SA_D + r0 + tid];
+            s_rs[tid] = v;
         }
         __syncthreads();
         for (int idx = tid; idx < SA_D * SU_RS; idx += SU_THREADS) {
@@ -364,7 +360,7 @@ __global__ __launch_bounds__(SU_THREADS) void sa_update_kernel(SaUpdParams p) {
                 float u = 0.f;
                 for (int ch = 0; ch < p.CH; ++ch) u += pb[(size_t)ch * pstride + (r0 + r) * SA_D + c];
                 const float rs = s_rs[r];
-                v = (p.ln_in_g[c] * (u - s_um[r]) + p.ln_in_b[c] * rs) / rs;
+                v = (p.ln_in_g[c] * u + p.ln_in_b[c] * rs) / rs;
             }
             s_u[c * SU_RS + r] = v;
         }
@@ -458,7 +454,7 @@ __global__ __launch_bounds__(SU_THREADS) void sa_update_kernel(SaUpdParams p) {
                 s0 += s_gh[(lane + 32 * i) * SU_RS + warp];
             }
             s1 = warp_sum(s1); s0 = warp_sum(s0);
-            if (lane == 0) { p.a1[b * S + r0 + warp] = s1; p.a0[b * S + r0 + warp] = s0; }
+            if (lane == 0) { p.a1[b * S + r0 + warp] = s1; p.a0[b * S + r0 + warp] = s0; }   // a1 = sum_c A (diagnostic only)
         }
     }
 }

@@ -109,6 +109,13 @@ class BaseSlotDynamicsModel(nn.Module):
     def _check_inputs(self, slots, action_protos, action_vars):
         if action_protos is None:
             raise ValueError("'action_protos' were not provided")
+        S = slots.shape[2]
+        # the reference adds (B, F, 1, E) action embeddings to (B, F, S, E) tokens by broadcasting
+        # (prior samples of the single-action model, LatentActionPredictors.py:511-532): expand explicitly
+        if action_protos.dim() == 4 and action_protos.shape[2] == 1 and S > 1:
+            action_protos = action_protos.expand(-1, -1, S, -1)
+        if action_vars is not None and action_vars.dim() == 4 and action_vars.shape[2] == 1 and S > 1:
+            action_vars = action_vars.expand(-1, -1, S, -1)
         if slots.shape[:-1] != action_protos.shape[:-1]:
             raise ValueError(f"{slots.shape =} != {action_protos.shape = }")
         if self.use_variability and action_vars is None:

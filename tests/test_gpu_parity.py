@@ -29,6 +29,19 @@ def check(name, got, ref, tol=TOL):
     assert r <= tol and m <= tol, f"{name}: rel_l2={r:.3e} max_rel={m:.3e} (tol {tol:.0e})"
 
 
+def check_conditioned(name, got, ref32, ref64, tol=TOL, factor=4.0):
+    """
+    For deliberately ill-conditioned cases (sharpened softmaxes amplify fp32 rounding): the error of the CUDA path
+    against the fp64 evaluation must stay within `factor` x the error the reference-order fp32 evaluation has
+    against that same fp64 truth (or within `tol`, whichever is larger).
+    """
+    got, ref32, ref64 = got.detach().cpu(), ref32.detach().cpu(), ref64.detach().cpu()
+    assert torch.isfinite(got).all(), f"{name}: non-finite values"
+    e_ours = max(rel_l2(got, ref64), max_rel(got, ref64))
+    e_ref = max(rel_l2(ref32, ref64), max_rel(ref32, ref64))
+    assert e_ours <= max(tol, factor * e_ref), f"{name}: ours vs fp64 {e_ours:.3e}, fp32 oracle vs fp64 {e_ref:.3e}"
+
+
 def g(*shape, seed=0, scale=1.0):
     gen = torch.Generator().manual_seed(seed)
     return torch.randn(*shape, generator=gen) * scale
@@ -133,11 +146,17 @@ def test_slot_attention_oracle(B, N, S, hidden, iters, sharpen):
     feats = feats * (1.0 + 0.5 * g(B, N, 1, seed=3)) + 0.7 * g(B, N, 1, seed=4)     # per-token scale / offset
     with torch.no_grad():
         ro, rm = O.slot_attention(sd, feats, slots, iters)
+        sd64 = {k: v.double() for k, v in sd.items()}
+        ro64, rm64 = O.slot_attention(sd64, feats.double(), slots.double(), iters)
         m = _sa_module(S, sd, hidden, iters, iters)
         o = m(feats.to(DEV), slots.to(DEV), step=0)
         mk = m.get_attention_masks()
-    check("slots", o, ro)
-    check("masks", mk, rm)
+    if sharpen > 1.0:       # logits scaled by sharpen^2: compare conditioning-aware against the fp64 evaluation
+        check_conditioned("slots", o, ro, ro64)
+        check_conditioned("masks", mk, rm, rm64)
+    else:
+        check("slots", o, ro)
+        check("masks", mk, rm)
 
 
 def test_slot_attention_full_size_properties():
@@ -262,7 +281,7 @@ def test_decode_true_shapes_and_empty_stacks():
         assert out["masks"].shape == (1, 2, 4, 1, 64, 64)
         assert out["slot_history"].shape == (1, 2, 4, 128)
         out = savi(video[:1, :2].to(DEV), num_imgs=2, decode=False)
-        assert out["recons_imgs"].shape == (1, 2, 0)
+        assert out["recons_imgs"].shape == (0, 2)      # torch.stack of empty tensors, exactly as the reference returns
         r0, _, _ = O.decode(ssd, fx["savi_cfg"], out["slot_history"][:, 0].cpu())
         out2 = savi(video[:1, :2].to(DEV), num_imgs=2, decode=True)
     check("decode=True recon", out2["recons_imgs"][:, 0], r0)
