@@ -209,6 +209,7 @@ def run_ours(args):
     cfg = configs.experiment(EXPERIMENT)
     torch.manual_seed(0)                                           # same random-init weights on every rank
     savi, pred = configs.build_models(cfg, "cuda")
+    savi.conv_mode = args.conv_mode
     B, T = args.batch, NUM_SEED + NUM_PREDS
     g = torch.Generator().manual_seed(1234 + rank)                 # a different synthetic shard per rank
     video_host = torch.rand(B, T, 3, 64, 64, generator=g).pin_memory()
@@ -279,13 +280,16 @@ def run_ours(args):
     shares = {k: round(v["ms"] / total_prof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
     roofline = None
-    if dom[0].startswith("conv2d"):
+    if dom[0].startswith("conv"):
         fl = sum(conv_flops(m) for m in dom[1]["meta"])
         ach = fl / (dom[1]["ms"] * 1e-3) / 1e12
+        note = ("algorithmic FLOPs = 2*n*H*W*Cin*Cout*k*k of the launches in the timed region (the fp16x3 mode issues 3x that on "
+                "the tensor pipe, padded-grid junk columns add 6%); peak = " + pk["source"] + " sustained bf16")
         roofline = {"kernel": dom[0], "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_sustained"], "traffic": None,
-                    "note": "fp32 CUDA-core direct convolution measured against the " + pk["source"] + " sustained bf16 tensor peak; "
-                            "FLOPs = 2*n*H*W*Cin*Cout*k*k of the launches in the timed region", "share_of_step": shares[dom[0]]}
+                    "frac": ach / pk["bf16_sustained"], "traffic": None, "note": note, "share_of_step": shares[dom[0]],
+                    "launches": dom[1]["calls"], "avg_launch_ms": dom[1]["ms"] / dom[1]["calls"]}
+        if dom[0].startswith("conv5x5_tc_p3"):
+            roofline["issued_tensor_TFLOPs"] = 3 * ach * (68.0 / 64.0)
     sa = prof.get("sa_main")
     roofline_sa = None
     if sa:
@@ -300,7 +304,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+        "dtype": {"fp16x3": "f32 (64->64 convs: fp16x3 split tensor-core products, 22-bit mantissa, fp32 accumulate)",
+                  "fp16": "fp16 convs + f32", "bf16": "bf16 convs + f32", "fp32": "f32"}[args.conv_mode],
+        "data": "synthetic", "config": dict(workload_config(B, world), conv_mode=args.conv_mode),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": video_host.numel() * 4 * world,
                 "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps},
@@ -332,6 +338,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="videos per GPU")
     ap.add_argument("--ref-batch", type=int, default=4, help="videos per step of the CPU arm (bounded sample)")
+    ap.add_argument("--conv-mode", default=os.environ.get("PLAYSLOT_CONV_MODE", "fp16x3"), choices=["fp16x3", "fp16", "bf16", "fp32"],
+                    help="arithmetic of the 64->64 5x5 convolutions (fp16x3 = split fp16 tensor-core products, fp32-grade)")
     ap.add_argument("--skip-extras", action="store_true", help="skip the config-2 SlotAttention sweep and the CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -113,6 +113,33 @@ int ps_invdyn_tail(const float* mv, const float* noise, const float* codebook, f
                    float* proto_out, float* var_out, long long* idx_out, float* loss_out,
                    int B, int T, int R, int A, int K, int per_slot, float eps, void* stream);
 
+/* ---- tcgen05 (tensor-core) 5x5 convolution, 64 -> 64 channels ------------------------------------------- */
+
+/* Activations for the tensor-core convolutions are zero-bordered NHWC 16-bit planes [hi | lo]:
+ * plane[img][y+2][x+2][64] with (H+4) x (W+4) positions per image; ps_conv_tc_plane_elems gives the element count
+ * of ONE plane (a buffer holds two planes; only the first is used by the single-product modes).  Buffers must
+ * be zero-initialised once: the kernels keep the borders zero.
+ * precision 3 ("fp16x3"): hi = fp16(x), lo = fp16((x - hi) * 2048), three products, fp32-grade result;
+ * precision 2 ("fp16") / 1 ("bf16"): hi plane only, one product. */
+long long ps_conv_tc_plane_elems(int n_img, int H, int W);
+
+/* nn.Conv2d(64, 64, 5, padding=2) (+bias, +ReLU) as an implicit GEMM on tcgen05 / TMEM fed by TMA.
+ * w_tc: 16-bit [25 taps][2 (hi, lo)][64 cout][64 cin] in the format of `precision`, holding w * w_scale
+ * (w_scale: a power of two chosen by the packer so that the weights sit mid-range; undone in the epilogue).
+ * out_mode 0: padded NHWC split into act_out;  1: fp32 NCHW [n,64,H,W] into out_f32;
+ * 2: fp32 NHWC tokens [n,H*W,64] + addend [H*W,64] into out_f32 (encoder output + position embedding).
+ * Replaces the 64-channel ConvBlocks of EncodersDecoders/decoders.py:89-102 and encoders.py:86-96. */
+int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* bias, float w_scale, void* act_out,
+                  float* out_f32, const float* addend, int n_img, int H, int W, int relu, int out_mode, int precision,
+                  void* stream);
+
+/* ps_dec_expand writing the padded NHWC split format (P_hwc: [H*W][64] = conv1(position embedding) + bias). */
+int ps_dec_expand_split(const float* G, const float* P_hwc, void* act_out, int n_img, int H, int W, int ksize,
+                        int precision, void* stream);
+
+/* fp32 NCHW [n,64,H,W] -> padded NHWC split (feeds the first tensor-core layer after a CUDA-core layer). */
+int ps_nchw_to_split(const float* x, void* act_out, int n_img, int H, int W, int precision, void* stream);
+
 /* Stand-alone nearest-codeword lookup (VectorQuantizer.forward, quantization.py:294-322): z [n,A] ->
  * proto = z + (z_q - z), exact codewords z_q, int64 indices, per-vector mean_A (z_q - z)^2. */
 int ps_vq_lookup(const float* z, const float* codebook, float* proto_out, float* zq_out, long long* idx_out,

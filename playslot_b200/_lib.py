@@ -26,6 +26,10 @@ SIGNATURES = {
     "ps_dec_composite": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_invdyn_tail": (c_i, [c_f] * 9 + [c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "ps_vq_lookup": (c_i, [c_f] * 6 + [c_i, c_i, c_i, c_f]),
+    "ps_conv_tc_plane_elems": (ctypes.c_longlong, [c_i, c_i, c_i]),
+    "ps_conv5x5_tc": (c_i, [c_f, c_f, c_f, c_fl, c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
+    "ps_dec_expand_split": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_nchw_to_split": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
 }
 
 _lib = None

@@ -1,0 +1,395 @@
+// tcgen05 implicit-GEMM 5x5 convolution, 64 -> 64 channels (decoder conv2..4 of every config, encoder
+// conv2..4 of the 64-channel configs).  Reference op: nn.Conv2d(64, 64, 5, padding=2) (+ReLU) in
+// src/models/BlocksUtils/model_blocks.py:48-79 as stacked by EncodersDecoders/{encoders,decoders}.py.
+//
+// Layout.  Activations live in HBM as zero-bordered NHWC bf16 planes: position p = (y+2)*Wp + (x+2),
+// Wp = W+4, Hp = H+4, one 128-byte row of 64 channels per position; an activation tensor is two such planes
+// [hi | lo] with x ~= hi + lo (bf16 split of the fp32 value).  On this "padded-linear" grid a filter tap
+// (ky,kx) is a constant row shift (ky-2)*Wp + (kx-2), so for a tile of 128 consecutive positions the A operand
+// of every tap is a 128-row window of ONE shared-memory resident region (tile + halo), addressed purely by the
+// UMMA descriptor start address (128B swizzle is applied on absolute smem address bits, verified by
+// tools/tc_probe.cu).  Outputs computed at border columns are junk by construction and are written as zeros,
+// which maintains the zero border of the next layer's input.
+//
+// GEMM per tile: D[128 pos x 64 cout] += A_tap[128 x 64 cin] * W_tap[64 cout x 64 cin]^T over 25 taps, 16-bit
+// operands, fp32 accumulation in TMEM.  Precision modes:
+//   3 = "fp16x3": x = hi + lo/2048 with hi = fp16(x), lo = fp16((x - hi) * 2048)  (22 mantissa bits, the scaled
+//       low part never goes subnormal); D0 += A_hi*W_hi and D1 += A_hi*W_lo + A_lo*W_hi in a second TMEM
+//       accumulator, result = D0 + D1/2048.  The dropped lo*lo term is 2^-22 relative: fp32-grade.
+//   2 = "fp16" : A_hi*W_hi only with fp16 operands;   1 = "bf16": the same with bf16 operands.
+// (A bf16 hi/lo split was measured first and rejected: 16 mantissa bits put the decoder's slot-softmax masks
+//  at 1.6e-4..3.7e-4 max error, above the 1e-4 parity bar.)
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/playslot_b200.h"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int C = 64;              // channels in == channels out
+constexpr int ROWB = 128;          // bytes per position row (64 bf16)
+constexpr int TILE_M = 128;
+constexpr int MAX_STAGES = 4;
+constexpr int ABOX = 32;           // rows per TMA box of the activation region
+constexpr int WTAP_BYTES = 64 * ROWB;   // one [cout][cin] bf16 tile
+
+constexpr float LO_SCALE = 2048.0f;      // low parts are stored multiplied by 2^11
+
+// 8 consecutive channels -> 16 bytes of the hi plane (and of the lo plane when lo != nullptr).
+// bf16 == true: single bf16 plane (precision 1);  otherwise fp16 hi (+ scaled fp16 lo).
+__device__ __forceinline__ void split_store8(const float* v, uint16_t* hi, uint16_t* lo, bool bf16) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = v[2 * j], b = v[2 * j + 1];
+        if (bf16) {
+            hw[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+            lw[j] = 0;
+        } else {
+            const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+            const __half al = __float2half_rn((a - __half2float(ah)) * LO_SCALE);
+            const __half bl = __float2half_rn((b - __half2float(bh)) * LO_SCALE);
+            hw[j] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
+            lw[j] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+        }
+    }
+    *reinterpret_cast<uint4*>(hi) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+struct ConvTcParams {
+    const float* bias;
+    const float* addend;     // mode 2: [H*W][64]
+    uint16_t* out_hi;        // mode 0
+    uint16_t* out_lo;        // mode 0 (null in the single-product modes)
+    float* out_f32;          // mode 1 (NCHW) / mode 2 (NHWC)
+    int n_img, H, W, Wp, Hp;
+    int items_per_img;       // work items (NPOS positions each) per image
+    int halo, a_rows;        // halo rows on each side, staged A rows (multiple of ABOX)
+    int stages;              // weight ring depth (2..MAX_STAGES)
+    int relu, out_mode;
+    int bf16;                // operand format: 1 = bf16, 0 = fp16
+    float out_scale;         // 1 / (power-of-two scale folded into the packed weights)
+};
+
+template <int TILES, int NSPLIT>
+__global__ void __launch_bounds__(192, 1)
+conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                  const __grid_constant__ CUtensorMap mapW, const ConvTcParams p) {
+    constexpr int NPOS = TILE_M * TILES;
+    constexpr int NPROD = (NSPLIT == 2) ? 3 : 1;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = p.a_rows * ROWB;
+    uint8_t* sA[2] = {smem, smem + a_bytes};
+    uint8_t* sW = smem + NSPLIT * a_bytes;                 // stages x NSPLIT x 8 KB
+    __shared__ uint64_t bar_a, bar_wfull[MAX_STAGES], bar_wempty[MAX_STAGES], bar_acc;
+    const int STAGES = p.stages;
+    __shared__ uint32_t tmem_base;
+    __shared__ float s_bias[C];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int img = blockIdx.x / p.items_per_img;
+    const int item = blockIdx.x - img * p.items_per_img;
+    const int p0 = 2 * p.Wp + item * NPOS;                 // first output position (padded-linear, per image)
+    const long long img_base = (long long)img * p.Hp * p.Wp;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_a, 1);
+        tc::mbar_init(&bar_acc, 1);
+        for (int s = 0; s < MAX_STAGES; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
+        tc::fence_mbar_init();
+    }
+    if (tid < C) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
+    if (warp == 1) tc::tmem_alloc(&tmem_base, 64 * TILES * NSPLIT);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tm = tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (tc::elect_one()) {
+            tc::tma_prefetch_desc(&mapA_hi);
+            tc::tma_prefetch_desc(&mapW);
+            const int g0 = (int)(img_base + p0 - p.halo);
+            tc::mbar_expect_tx(&bar_a, (uint32_t)(NSPLIT * a_bytes));
+            for (int r = 0; r < p.a_rows; r += ABOX) {
+                tc::tma_load_2d(sA[0] + r * ROWB, &mapA_hi, &bar_a, 0, g0 + r);
+                if (NSPLIT == 2) tc::tma_load_2d(sA[1] + r * ROWB, &mapA_lo, &bar_a, 0, g0 + r);
+            }
+            for (int tap = 0; tap < 25; ++tap) {
+                const int s = tap % STAGES;
+                if (tap >= STAGES) tc::mbar_wait(&bar_wempty[s], ((tap / STAGES) - 1) & 1);
+                tc::mbar_expect_tx(&bar_wfull[s], NSPLIT * WTAP_BYTES);
+                tc::tma_load_2d(sW + s * NSPLIT * WTAP_BYTES, &mapW, &bar_wfull[s], 0, tap * 128);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (tc::elect_one()) {
+            const uint32_t idesc = p.bf16 ? tc::umma_idesc_bf16(TILE_M, C) : tc::umma_idesc_f16(TILE_M, C);
+            const uint32_t a_base[2] = {tc::smem_u32(sA[0]), tc::smem_u32(sA[1])};
+            const uint32_t w_base = tc::smem_u32(sW);
+            tc::mbar_wait(&bar_a, 0);
+            tc::tc_fence_after();
+            for (int tap = 0; tap < 25; ++tap) {
+                const int s = tap % STAGES;
+                tc::mbar_wait(&bar_wfull[s], (tap / STAGES) & 1);
+                tc::tc_fence_after();
+                const int ky = tap / 5, kx = tap - ky * 5;
+                const int off = (ky - 2) * p.Wp + (kx - 2);
+#pragma unroll
+                for (int tile = 0; tile < TILES; ++tile) {
+                    const uint32_t row0 = (uint32_t)(p.halo + tile * TILE_M + off);
+#pragma unroll
+                    for (int pr = 0; pr < NPROD; ++pr) {
+                        const int as = (pr == 2) ? 1 : 0;       // (A_hi,W_hi), (A_hi,W_lo), (A_lo,W_hi)
+                        const int ws = (pr == 1) ? 1 : 0;
+#pragma unroll
+                        for (int k = 0; k < C / 16; ++k) {
+                            const uint32_t a_addr = a_base[as] + row0 * ROWB + k * 32;
+                            const uint32_t b_addr = w_base + (s * NSPLIT + ws) * WTAP_BYTES + k * 32;
+                            // accumulator 0: hi*hi; accumulator 1 (scaled by 2^11): hi*lo + lo*hi
+                            const uint32_t acc = tm + (tile * NSPLIT + (pr ? 1 : 0)) * C;
+                            const uint32_t first = (pr <= 1) ? (uint32_t)(tap | k) : 1u;
+                            tc::umma_bf16(acc, tc::umma_desc_sw128(a_addr, 1024, 0),
+                                          tc::umma_desc_sw128(b_addr, 1024, 0), idesc, first != 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                tc::umma_commit(&bar_wempty[s]);           // frees the weight stage once these MMAs retire
+            }
+            tc::umma_commit(&bar_acc);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+        tc::mbar_wait(&bar_acc, 0);
+        tc::tc_fence_after();
+        const int HW = p.H * p.W;
+#pragma unroll 1
+        for (int tile = 0; tile < TILES; ++tile) {
+            const int r = quad * 32 + lane;
+            const int pp = p0 + tile * TILE_M + r;          // padded-linear position inside the image
+            const int yp = pp / p.Wp, xp = pp - yp * p.Wp;
+            const bool row_ok = yp < p.H + 2;               // rows >= 2 by construction
+            const bool interior = row_ok && xp >= 2 && xp < p.W + 2;
+            float v[64];
+            const uint32_t tbase = tm + ((uint32_t)(quad * 32) << 16) + tile * NSPLIT * C;
+            tc::tmem_ld_32x32(tbase, v);
+            tc::tmem_ld_32x32(tbase + 32, v + 32);
+            if (NSPLIT == 2) {
+                float u[32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tc::tmem_ld_32x32(tbase + C + h * 32, u);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[h * 32 + c] = fmaf(u[c], 1.0f / LO_SCALE, v[h * 32 + c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                float t = fmaf(v[c], p.out_scale, s_bias[c]);
+                if (p.relu) t = fmaxf(t, 0.f);
+                v[c] = interior ? t : 0.f;
+            }
+            if (p.out_mode == 0) {
+                if (row_ok) {
+                    const size_t o = ((size_t)img_base + pp) * C;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        split_store8(v + g * 8, p.out_hi + o + g * 8, p.out_lo ? p.out_lo + o + g * 8 : nullptr, p.bf16 != 0);
+                }
+            } else if (interior) {
+                const int y = yp - 2, x = xp - 2;
+                if (p.out_mode == 1) {
+                    float* dst = p.out_f32 + (size_t)img * C * HW + (size_t)y * p.W + x;
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) dst[(size_t)c * HW] = v[c];
+                } else {
+                    const size_t pix = (size_t)y * p.W + x;
+                    float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((size_t)img * HW + pix) * C);
+                    const float4* ad = p.addend ? reinterpret_cast<const float4*>(p.addend + pix * C) : nullptr;
+#pragma unroll
+                    for (int g = 0; g < 16; ++g) {
+                        float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        if (ad) { const float4 a = ad[g]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                        dst[g] = o;
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tm, 64 * TILES * NSPLIT);
+}
+
+template <int TILES, int NSPLIT>
+int launch_conv_tc(const CUtensorMap& mA_hi, const CUtensorMap& mA_lo, const CUtensorMap& mW, const ConvTcParams& p,
+                   cudaStream_t st) {
+    const size_t smem = (size_t)NSPLIT * p.a_rows * ROWB + (size_t)p.stages * NSPLIT * WTAP_BYTES + 1024;
+    PS_REQUIRE(smem <= 227 * 1024, "ps_conv5x5_tc: image width %d needs %zu bytes of shared memory", p.W, smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        PS_CUDA(cudaFuncSetAttribute(conv5x5_tc_kernel<TILES, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    conv5x5_tc_kernel<TILES, NSPLIT><<<p.n_img * p.items_per_img, 192, smem, st>>>(mA_hi, mA_lo, mW, p);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
+
+}  // namespace
+
+extern "C" long long ps_conv_tc_plane_elems(int n_img, int H, int W) {
+    return (long long)n_img * (H + 4) * (W + 4) * C;
+}
+
+extern "C" int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* bias, float w_scale, void* act_out,
+                             float* out_f32, const float* addend, int n_img, int H, int W, int relu, int out_mode,
+                             int precision, void* stream) {
+    PS_REQUIRE(act_in && w_tc, "ps_conv5x5_tc: null pointer");
+    PS_REQUIRE(precision >= 1 && precision <= 3, "ps_conv5x5_tc: precision must be 1 (bf16), 2 (fp16) or 3 (fp16x3)");
+    PS_REQUIRE(w_scale > 0.f, "ps_conv5x5_tc: w_scale must be positive");
+    PS_REQUIRE(out_mode >= 0 && out_mode <= 2, "ps_conv5x5_tc: out_mode must be 0, 1 or 2");
+    PS_REQUIRE(out_mode == 0 ? act_out != nullptr : out_f32 != nullptr, "ps_conv5x5_tc: missing output buffer");
+    PS_REQUIRE(H >= 8 && W >= 8 && W <= 252, "ps_conv5x5_tc: unsupported image size %dx%d", H, W);
+    if (n_img == 0) return PS_OK;
+    const int Wp = W + 4, Hp = H + 4;
+    const long long P = (long long)n_img * Hp * Wp;
+    PS_REQUIRE(P < (1ll << 31) - 4096, "ps_conv5x5_tc: too many positions for 32-bit TMA coordinates");
+    const int nsplit = precision == 3 ? 2 : 1;
+    const int halo = 2 * Wp + 2;
+    // two 128-position tiles per CTA when the staged region fits, else one
+    int tiles = 2;
+    auto a_rows_for = [&](int t) { return ((TILE_M * t + 2 * halo) + 63) / 64 * 64; };   // multiple of 64 rows = 8 KB: keeps every region 1024-byte aligned
+    auto stages_for = [&](int t) {
+        const long long room = 227ll * 1024 - 1024 - (long long)nsplit * a_rows_for(t) * ROWB;
+        long long st = room / ((long long)nsplit * WTAP_BYTES);
+        return (int)(st > MAX_STAGES ? MAX_STAGES : st);
+    };
+    if (stages_for(2) < 3) tiles = 1;
+    PS_REQUIRE(stages_for(tiles) >= 2, "ps_conv5x5_tc: image width %d does not fit the shared-memory staging", W);
+    ConvTcParams p;
+    p.bias = bias; p.addend = addend; p.out_f32 = out_f32;
+    p.out_hi = reinterpret_cast<uint16_t*>(act_out);
+    p.out_lo = (act_out && precision == 3) ? p.out_hi + P * C : nullptr;
+    p.bf16 = precision == 1 ? 1 : 0;
+    p.out_scale = 1.0f / w_scale;
+    p.n_img = n_img; p.H = H; p.W = W; p.Wp = Wp; p.Hp = Hp;
+    p.items_per_img = (H * Wp + TILE_M * tiles - 1) / (TILE_M * tiles);
+    p.halo = halo; p.a_rows = a_rows_for(tiles); p.stages = stages_for(tiles);
+    p.relu = relu; p.out_mode = out_mode;
+    const uint16_t* in_hi = reinterpret_cast<const uint16_t*>(act_in);
+    CUtensorMap mA_hi, mA_lo, mW;
+    int r = tc::make_tmap_2d_bf16_sw128(&mA_hi, in_hi, (uint64_t)P, C, ABOX, C);
+    PS_REQUIRE(r == 0, "ps_conv5x5_tc: cuTensorMapEncodeTiled(A_hi) failed (%d)", r);
+    r = tc::make_tmap_2d_bf16_sw128(&mA_lo, precision == 3 ? in_hi + P * C : in_hi, (uint64_t)P, C, ABOX, C);
+    PS_REQUIRE(r == 0, "ps_conv5x5_tc: cuTensorMapEncodeTiled(A_lo) failed (%d)", r);
+    // weights: [25 taps][2 (hi, lo)][64 cout][64 cin]; the single-product modes load the hi half of each tap only
+    r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 25ull * 2 * 64, C, 64 * nsplit, C);
+    PS_REQUIRE(r == 0, "ps_conv5x5_tc: cuTensorMapEncodeTiled(W) failed (%d)", r);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tiles == 2) return nsplit == 2 ? launch_conv_tc<2, 2>(mA_hi, mA_lo, mW, p, st) : launch_conv_tc<2, 1>(mA_hi, mA_lo, mW, p, st);
+    return nsplit == 2 ? launch_conv_tc<1, 2>(mA_hi, mA_lo, mW, p, st) : launch_conv_tc<1, 1>(mA_hi, mA_lo, mW, p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// producers of the zero-bordered NHWC bf16 [hi | lo] activation format
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+
+__device__ __forceinline__ int border_class_tc(int v, int n, int pad) {
+    if (v < pad) return v;
+    if (v > n - 1 - pad) return 2 * pad - (n - 1 - v);
+    return pad;
+}
+
+// h1[img, y, x, :] = relu(G[img, cls(y), cls(x), :] + P[y, x, :]) written as padded NHWC split;
+// one thread per (img, pixel, group of 8 channels)
+__global__ void dec_expand_split_kernel(const float* __restrict__ G, const float* __restrict__ Phwc,
+                                        uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
+                                        int n_img, int H, int W, int pad, long long total, int bf16) {
+    const int ncls = 2 * pad + 1;
+    const int Wp = W + 4, Hp = H + 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i & 7);
+        const long long pix = i >> 3;
+        const int x = (int)(pix % W);
+        const int y = (int)((pix / W) % H);
+        const int img = (int)(pix / ((long long)W * H));
+        const float* gp = G + (((size_t)img * ncls + border_class_tc(y, H, pad)) * ncls + border_class_tc(x, W, pad)) * C + g * 8;
+        const float* pp = Phwc + ((size_t)y * W + x) * C + g * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
+        const float4 q0 = *reinterpret_cast<const float4*>(pp), q1 = *reinterpret_cast<const float4*>(pp + 4);
+        float v[8] = {fmaxf(g0.x + q0.x, 0.f), fmaxf(g0.y + q0.y, 0.f), fmaxf(g0.z + q0.z, 0.f), fmaxf(g0.w + q0.w, 0.f),
+                      fmaxf(g1.x + q1.x, 0.f), fmaxf(g1.y + q1.y, 0.f), fmaxf(g1.z + q1.z, 0.f), fmaxf(g1.w + q1.w, 0.f)};
+        const size_t o = (((size_t)img * Hp + y + 2) * Wp + x + 2) * C + g * 8;
+        split_store8(v, out_hi + o, out_lo ? out_lo + o : nullptr, bf16 != 0);
+    }
+}
+
+// fp32 NCHW [n][64][H][W] -> padded NHWC split; one CTA per (img, row y), transpose through shared memory
+__global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ out_hi,
+                                                            uint16_t* __restrict__ out_lo, int H, int W, int bf16) {
+    extern __shared__ float s_t[];                    // [64][W+1]
+    const int y = blockIdx.x, img = blockIdx.y;
+    const int Wp = W + 4, Hp = H + 4;
+    const float* src = x + (size_t)img * C * H * W + (size_t)y * W;
+    for (int i = threadIdx.x; i < C * W; i += 256) {
+        const int c = i / W, xx = i - c * W;
+        s_t[c * (W + 1) + xx] = src[(size_t)c * H * W + xx];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < W * 8; i += 256) {
+        const int xx = i >> 3, g = i & 7;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = s_t[(g * 8 + j) * (W + 1) + xx];
+        const size_t o = (((size_t)img * Hp + y + 2) * Wp + xx + 2) * C + g * 8;
+        split_store8(v, out_hi + o, out_lo ? out_lo + o : nullptr, bf16 != 0);
+    }
+}
+
+}  // namespace
+
+extern "C" int ps_dec_expand_split(const float* G, const float* P_hwc, void* act_out, int n_img, int H, int W,
+                                   int ksize, int precision, void* stream) {
+    PS_REQUIRE(G && P_hwc && act_out, "ps_dec_expand_split: null pointer");
+    PS_REQUIRE(precision >= 1 && precision <= 3, "ps_dec_expand_split: precision must be 1, 2 or 3");
+    PS_REQUIRE(ksize % 2 == 1 && H > ksize && W > ksize, "ps_dec_expand_split: unsupported geometry");
+    if (n_img == 0) return PS_OK;
+    const long long P = (long long)n_img * (H + 4) * (W + 4);
+    uint16_t* hi = reinterpret_cast<uint16_t*>(act_out);
+    uint16_t* lo = precision == 3 ? hi + P * C : nullptr;
+    const long long total = (long long)n_img * H * W * 8;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    dec_expand_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(G, P_hwc, hi, lo, n_img, H, W, ksize / 2, total, precision == 1);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
+
+extern "C" int ps_nchw_to_split(const float* x, void* act_out, int n_img, int H, int W, int precision, void* stream) {
+    PS_REQUIRE(x && act_out, "ps_nchw_to_split: null pointer");
+    PS_REQUIRE(precision >= 1 && precision <= 3, "ps_nchw_to_split: precision must be 1, 2 or 3");
+    PS_REQUIRE(W <= 160 && H <= 65535, "ps_nchw_to_split: unsupported image size");
+    if (n_img == 0) return PS_OK;
+    PS_REQUIRE(n_img <= 65535, "ps_nchw_to_split: at most 65535 images per launch");
+    const long long P = (long long)n_img * (H + 4) * (W + 4);
+    uint16_t* hi = reinterpret_cast<uint16_t*>(act_out);
+    uint16_t* lo = precision == 3 ? hi + P * C : nullptr;
+    const size_t smem = (size_t)C * (W + 1) * sizeof(float);
+    nchw_to_split_kernel<<<dim3(H, n_img), 256, smem, (cudaStream_t)stream>>>(x, hi, lo, H, W, precision == 1);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}

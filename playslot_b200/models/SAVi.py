@@ -12,6 +12,7 @@ The image encoder has no temporal dependency, so `forward` encodes all frames of
 pass (time-major) before running the recurrent slot loop.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -36,6 +37,13 @@ class SAVi(nn.Module):
 
     ENCODE_CHUNK_BYTES = 6 << 30      # feature tokens kept per batched encode pass
     DECODE_CHUNK_IMAGES = 4096        # slot-images decoded per pass (1 MiB of fp32 activations each at 64x64x64)
+
+    # arithmetic of the 64 -> 64 channel 5x5 convolutions:
+    #   "fp16x3": tcgen05 tensor cores, fp16 hi + scaled fp16 lo operands, three products, fp32 accumulate
+    #             (22 mantissa bits: fp32-grade, passes the 1e-4 parity bar)
+    #   "fp16" / "bf16": tcgen05 tensor cores, single half-precision product (stated tolerances)
+    #   "fp32"  : exact fp32 FFMA kernel on the CUDA cores
+    CONV_MODES = ("fp16x3", "fp16", "bf16", "fp32")
 
     def __init__(self, num_slots, slot_dim, num_iterations=3, num_iterations_first=None,
                  in_channels=3, mlp_hidden=128, mlp_encoder_dim=128,
@@ -62,6 +70,11 @@ class SAVi(nn.Module):
                 mlp_hidden=self.mlp_hidden,
             )
         self._dec_cache = DerivedWeights()
+        self.conv_mode = os.environ.get("PLAYSLOT_CONV_MODE", "fp16x3")
+        if self.conv_mode not in self.CONV_MODES:
+            raise ValueError(f"PLAYSLOT_CONV_MODE={self.conv_mode!r}; expected one of {self.CONV_MODES}")
+        self._tc_ws = {}
+        self._tc_w = {}
         self._init_model()
 
     def build_encoder(self, encoder_params):
@@ -145,11 +158,59 @@ class SAVi(nn.Module):
         no_grad_only("SAVi.encode", x, self.encoder_mlp[1].weight)
         x = f32c(x)
         M, _, H, W = x.shape
-        tokens = self.encoder.run(x, last_nhwc_addend=self.encoder_pos_embedding.table(channels_last=True))
+        posemb = self.encoder_pos_embedding.table(channels_last=True)
+        if self._tc_applicable(self.encoder.encoder, skip_first=True):
+            tokens = self._encode_convs_tc(x, posemb)
+        else:
+            tokens = self.encoder.run(x, last_nhwc_addend=posemb)
         tokens = tokens.view(M, H * W, -1)
         ln, fc1, fc2 = self.encoder_mlp[0], self.encoder_mlp[1], self.encoder_mlp[3]
         h = ops.linear(tokens, fc1.weight, fc1.bias, ln=(ln.weight, ln.bias, ln.eps), act=ops.ACT_RELU)
         return ops.linear(h, fc2.weight, fc2.bias)
+
+    # --------------------------------------------------------------------------------------------- tensor-core convs
+    def _tc_applicable(self, blocks, skip_first):
+        """ the tcgen05 kernel covers plain 5x5, 64 -> 64 channel ConvBlocks """
+        if self.conv_mode not in ops.TC_PRECISION:
+            return False
+        blocks = list(blocks)[1:] if skip_first else list(blocks)
+        if not blocks:
+            return False
+        for b in blocks:
+            c = getattr(b, "conv", None)
+            if c is None or not b._plain or c.kernel_size != (5, 5) or c.in_channels != 64 or c.out_channels != 64:
+                return False
+        return True
+
+    def _tc_workspace(self, tag, n_img, H, W, device):
+        key = (tag, n_img, H, W, str(device))
+        if key not in self._tc_ws:
+            self._tc_ws[key] = ops.conv_tc_workspace(n_img, H, W, device)
+        return self._tc_ws[key]
+
+    def _tc_weight(self, block):
+        prec = ops.TC_PRECISION[self.conv_mode]
+        cache = self._tc_w.setdefault((id(block), prec), DerivedWeights())
+        w = block.conv.weight
+        return cache.get([w], lambda: ops.pack_conv_weight_tc(w, prec))
+
+    def _encode_convs_tc(self, x, posemb):
+        """ first conv (3 -> 64) on the CUDA cores, the 64 -> 64 layers on tcgen05; tokens + posemb out """
+        prec = ops.TC_PRECISION[self.conv_mode]
+        blocks = list(self.encoder.encoder)
+        M, _, H, W = x.shape
+        h = blocks[0].run(x)                                          # fp32 NCHW (M, 64, H, W)
+        a = self._tc_workspace("enc_a", M, H, W, x.device)
+        b = self._tc_workspace("enc_b", M, H, W, x.device)
+        ops.nchw_to_split(h, a, prec)
+        del h
+        for blk in blocks[1:-1]:
+            ops.conv5x5_tc(a, self._tc_weight(blk), blk.conv.bias, M, H, W, blk._relu, prec, act_out=b)
+            a, b = b, a
+        last = blocks[-1]
+        tokens = torch.empty(M, H * W, 64, device=x.device, dtype=torch.float32)
+        ops.conv5x5_tc(a, self._tc_weight(last), last.conv.bias, M, H, W, last._relu, prec, out_tokens=tokens, addend=posemb)
+        return tokens
 
     # --------------------------------------------------------------------------------------------- decode
     def _decoder_constants(self):
@@ -181,7 +242,8 @@ class SAVi(nn.Module):
             wsum = torch.stack(rows, dim=0).reshape(-1, w.shape[1]).contiguous()  # (ncls^2 * C1, D)
             pos = pe.table(channels_last=False)[None].contiguous()               # (1, D, H, W)
             P = ops.conv2d(pos, blocks[0].packed_weight(), conv1.bias, k, relu=False)   # conv1(posemb) + bias
-            return wsum, P[0].contiguous(), k
+            P = P[0].contiguous()
+            return wsum, P, k, P.permute(1, 2, 0).reshape(-1, P.shape[0]).contiguous()
         return self._dec_cache.get(srcs, build)
 
     def decode(self, slots):
@@ -199,8 +261,10 @@ class SAVi(nn.Module):
             raise NotImplementedError("SAVi.decode kernels cover upsample in (None, 1) and RGB outputs "
                                       "(every shipped config); got upsample=%r in_channels=%r" % (dec.upsample, self.in_channels))
         blocks = dec.conv_blocks()
-        wsum, P, k = self._decoder_constants()
+        wsum, P, k, P_hwc = self._decoder_constants()
         C1 = blocks[0].conv.out_channels
+        use_tc = C1 == 64 and self._tc_applicable(blocks, skip_first=True)
+        prec = ops.TC_PRECISION.get(self.conv_mode, 0)
         final = dec.final_conv()
         wfin = self._final_packed(final)
         recon_l, recons_l, masks_l = [], [], []
@@ -209,9 +273,20 @@ class SAVi(nn.Module):
             m1 = min(M, m0 + step)
             sl = slots[m0:m1].reshape((m1 - m0) * S, D)
             G = ops.linear(sl, wsum)                                           # (n_img, ncls^2 * C1)
-            h = ops.dec_expand(G, P, (m1 - m0) * S, C1, H, W, k)
-            for blk in blocks[1:]:
-                h = blk.run(h)
+            n_img = (m1 - m0) * S
+            if use_tc:
+                a = self._tc_workspace("dec_a", n_img, H, W, slots.device)
+                b = self._tc_workspace("dec_b", n_img, H, W, slots.device)
+                ops.dec_expand_split(G, P_hwc, a, n_img, H, W, k, prec)
+                for blk in blocks[1:-1]:
+                    ops.conv5x5_tc(a, self._tc_weight(blk), blk.conv.bias, n_img, H, W, blk._relu, prec, act_out=b)
+                    a, b = b, a
+                h = torch.empty(n_img, 64, H, W, device=slots.device, dtype=torch.float32)
+                ops.conv5x5_tc(a, self._tc_weight(blocks[-1]), blocks[-1].conv.bias, n_img, H, W, blocks[-1]._relu, prec, out_nchw=h)
+            else:
+                h = ops.dec_expand(G, P, n_img, C1, H, W, k)
+                for blk in blocks[1:]:
+                    h = blk.run(h)
             r, rs, ms = ops.dec_composite(h, wfin, final.bias, m1 - m0, S)
             recon_l.append(r); recons_l.append(rs); masks_l.append(ms)
         if len(recon_l) == 1:

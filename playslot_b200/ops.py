@@ -266,3 +266,74 @@ def vq_lookup(z, codebook):
     st = lib.ps_vq_lookup(_ptr(z), _ptr(codebook), _ptr(proto), _ptr(zq), _ptr(idx), _ptr(loss), n, A, K, _stream())
     _lib.check(st, "ps_vq_lookup")
     return proto, zq, idx, loss
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 convolution
+
+TC_PRECISION = {"fp16x3": 3, "fp16": 2, "bf16": 1}
+TC_LO_SCALE = 2048.0
+
+
+def conv_tc_workspace(n_img, H, W, device):
+    """ zero-initialised activation buffer in the padded NHWC bf16 [hi | lo] format of ps_conv5x5_tc """
+    elems = int(_lib.load().ps_conv_tc_plane_elems(n_img, H, W))
+    return torch.zeros(2, elems // 64, 64, device=device, dtype=torch.int16)
+
+
+def pack_conv_weight_tc(w, precision):
+    """
+    nn.Conv2d weight (64, 64, 5, 5) fp32 -> (16-bit tensor (25 taps, 2 [hi, lo], 64 cout, 64 cin), w_scale).
+    The weights are multiplied by a power of two w_scale that puts max|w| near 1 (exact; undone in the kernel's
+    epilogue) so that the fp16 parts stay far away from the subnormal range.
+    """
+    Cout, Cin, K, _ = w.shape
+    assert (Cout, Cin, K) == (64, 64, 5), "the tensor-core convolution covers 64 -> 64 channels, 5x5"
+    wt = w.detach().float().permute(2, 3, 0, 1).reshape(K * K, Cout, Cin)
+    amax = float(wt.abs().max())
+    scale = 1.0 if amax == 0.0 or precision == 1 else 2.0 ** (-round(__import__("math").log2(amax)))
+    wt = wt * scale
+    if precision == 1:
+        hi = wt.to(torch.bfloat16).view(torch.int16)
+        lo = torch.zeros_like(hi)
+    else:
+        h = wt.to(torch.float16)
+        hi = h.view(torch.int16)
+        lo = ((wt - h.float()) * TC_LO_SCALE).to(torch.float16).view(torch.int16)
+    return torch.stack([hi, lo], dim=1).contiguous(), scale
+
+
+def conv5x5_tc(act_in, w_packed, bias, n_img, H, W, relu, precision, act_out=None, out_nchw=None, out_tokens=None, addend=None):
+    """ w_packed = pack_conv_weight_tc(w, precision); exactly one of act_out (padded split), out_nchw (fp32
+    [n,64,H,W]) or out_tokens (fp32 [n,H*W,64]) receives the result """
+    lib = _lib.load()
+    w_tc, w_scale = w_packed
+    mode = 0 if act_out is not None else (1 if out_nchw is not None else 2)
+    f32 = out_nchw if mode == 1 else out_tokens
+    with _timed("conv5x5_tc_p%d" % precision, (n_img, 64, 64, H, W, 5)):
+        st = lib.ps_conv5x5_tc(_ptr(act_in), _ptr(w_tc), _ptr(bias), float(w_scale), _ptr(act_out), _ptr(f32), _ptr(addend),
+                               n_img, H, W, int(relu), mode, int(precision), _stream())
+    _lib.check(st, "ps_conv5x5_tc")
+    return act_out if mode == 0 else f32
+
+
+def dec_expand_split(G, P_hwc, act_out, n_img, H, W, ksize, precision):
+    lib = _lib.load()
+    _req(G, "G"); _req(P_hwc, "P_hwc")
+    with _timed("dec_expand_split"):
+        st = lib.ps_dec_expand_split(_ptr(G), _ptr(P_hwc), _ptr(act_out), n_img, H, W, ksize, int(precision), _stream())
+    _lib.check(st, "ps_dec_expand_split")
+    return act_out
+
+
+def nchw_to_split(x, act_out, precision):
+    lib = _lib.load()
+    _req(x, "x")
+    n, C, H, W = x.shape
+    assert C == 64
+    with _timed("nchw_to_split"):
+        for i0 in range(0, n, 65535):
+            i1 = min(n, i0 + 65535)
+            assert i0 == 0, "more than 65535 images per call are not supported"
+            st = lib.ps_nchw_to_split(_ptr(x), _ptr(act_out), n, H, W, int(precision), _stream())
+            _lib.check(st, "ps_nchw_to_split")
+    return act_out

@@ -104,6 +104,47 @@ def test_conv2d(n, Cin, Cout, H, W, k, relu):
     check("conv2d nhwc+addend", y2, (ref.permute(0, 2, 3, 1) + add.double().view(1, H, W, Cout)).float())
 
 
+def _unpack_split(act, n, H, W, precision):
+    """ padded NHWC [hi | lo] -> fp32 NCHW (test helper) and check that the borders are exactly zero """
+    if precision == 1:
+        full = act.view(torch.bfloat16).float().view(2, n, H + 4, W + 4, 64)[0]
+    else:
+        planes = act.view(torch.float16).float().view(2, n, H + 4, W + 4, 64)
+        full = planes[0] + (planes[1] / 2048.0 if precision == 3 else 0)
+    border = full.clone()
+    border[:, 2:H + 2, 2:W + 2] = 0
+    assert float(border.abs().max()) == 0.0, "zero border violated"
+    return full[:, 2:H + 2, 2:W + 2].permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("n,H,W", [(3, 64, 64), (1, 128, 128), (2, 32, 48)])
+@pytest.mark.parametrize("precision,tol", [(3, 1e-5), (2, 1e-3), (1, 8e-3)])
+def test_conv5x5_tensor_core(n, H, W, precision, tol):
+    """ tcgen05 implicit-GEMM conv vs torch fp64 conv; chained twice so the padded split format round-trips """
+    from playslot_b200 import ops
+    x = g(n, 64, H, W, seed=1)
+    w1, b1 = g(64, 64, 5, 5, seed=2, scale=1600 ** -0.5 * 1.5), g(64, seed=3, scale=0.1)
+    w2, b2 = g(64, 64, 5, 5, seed=4, scale=1600 ** -0.5 * 1.5), g(64, seed=5, scale=0.1)
+    r1 = F.relu(F.conv2d(x.double(), w1.double(), b1.double(), padding=2))
+    r2 = F.conv2d(r1, w2.double(), b2.double(), padding=2)
+    a0 = ops.conv_tc_workspace(n, H, W, DEV)
+    a1 = ops.conv_tc_workspace(n, H, W, DEV)
+    ops.nchw_to_split(x.to(DEV), a0, precision)
+    check("nchw_to_split", _unpack_split(a0, n, H, W, precision), x, {3: 5e-7, 2: 5e-4, 1: 4e-3}[precision])
+    ops.conv5x5_tc(a0, ops.pack_conv_weight_tc(w1.to(DEV), precision), b1.to(DEV), n, H, W, True, precision, act_out=a1)
+    check("tc conv -> split", _unpack_split(a1, n, H, W, precision), r1.float(), tol)
+    out = torch.empty(n, 64, H, W, device=DEV)
+    ops.conv5x5_tc(a1, ops.pack_conv_weight_tc(w2.to(DEV), precision), b2.to(DEV), n, H, W, False, precision, out_nchw=out)
+    check("tc conv -> nchw", out, r2.float(), 2 * tol)
+    add = g(H * W, 64, seed=6)
+    tok = torch.empty(n, H * W, 64, device=DEV)
+    ops.conv5x5_tc(a1, ops.pack_conv_weight_tc(w2.to(DEV), precision), b2.to(DEV), n, H, W, False, precision, out_tokens=tok, addend=add.to(DEV))
+    check("tc conv -> tokens", tok, (r2.permute(0, 2, 3, 1).reshape(n, H * W, 64) + add.double()).float(), 2 * tol)
+    # against the exact fp32 CUDA-core kernel of this library
+    y = ops.conv2d(x.to(DEV), ops.pack_conv_weight(w1.to(DEV)), b1.to(DEV), 5, True)
+    check("tc vs fp32 kernel", _unpack_split(a1, n, H, W, precision), y, tol)
+
+
 # ----------------------------------------------------------------------------------------------- SlotAttention
 
 def _sa_module(S, sd, mlp_hidden=256, it_first=3, it=1):
@@ -207,11 +248,13 @@ def test_transformer_block(E, H, dh, mlp, proj, spf, L):
     check("transformer block", out, ref)
 
 
+@pytest.mark.parametrize("conv_mode", ["fp16x3", "fp32"])
 @pytest.mark.parametrize("case", ["blockpush", "gridshapes5"])
-def test_encode_and_decode_vs_oracle(case):
+def test_encode_and_decode_vs_oracle(case, conv_mode):
     fx, ssd, psd, video, noise, init_noise = load_case(case)
     scfg = fx["savi_cfg"]
     savi = make_savi(scfg, ssd, DEV)
+    savi.conv_mode = conv_mode
     frames = video[:, :2].reshape(-1, *video.shape[2:])
     S, D = scfg["num_slots"], scfg["slot_dim"]
     slots = g(3, S, D, seed=2)
@@ -229,13 +272,30 @@ def test_encode_and_decode_vs_oracle(case):
 
 # ----------------------------------------------------------------------------------------------- whole pipeline
 
+@pytest.mark.parametrize("mode,tol", [("bf16", 1e-1), ("fp16", 1e-2)])
+def test_decode_half_precision_modes_stated_tolerance(mode, tol):
+    """ single-product tensor-core modes: stated tolerances on decoded frames and slot masks """
+    fx, ssd, psd, video, noise, init_noise = load_case("blockpush")
+    scfg = fx["savi_cfg"]
+    savi = make_savi(scfg, ssd, DEV)
+    savi.conv_mode = mode
+    slots = g(3, scfg["num_slots"], scfg["slot_dim"], seed=2)
+    with torch.no_grad():
+        recon, (recons, masks) = savi.decode(slots.to(DEV))
+        r_recon, r_recons, r_masks = O.decode(ssd, scfg, slots)
+    check("recon " + mode, recon, r_recon, tol)
+    check("masks " + mode, masks, r_masks, tol)
+
+
+@pytest.mark.parametrize("conv_mode", ["fp16x3", "fp32"])
 @pytest.mark.parametrize("case", PIPELINE_CASES)
-def test_pipeline_matches_reference_golden(case):
+def test_pipeline_matches_reference_golden(case, conv_mode):
     """ seed + rollout pipeline of 05_evaluate_PlaySlot.py:112-139 against vectors produced by the real reference """
     fx, ssd, psd, video, noise, init_noise = load_case(case)
     scfg, pcfg = fx["savi_cfg"], fx["predictor_cfg"]
     B, ns, npred = fx["B"], fx["num_seed"], fx["num_preds"]
     savi = make_savi(scfg, ssd, DEV)
+    savi.conv_mode = conv_mode
     pred = make_predictor(fx["predictor_name"], pcfg, psd, DEV)
     S, D = scfg["num_slots"], scfg["slot_dim"]
     with torch.no_grad():
