@@ -196,7 +196,7 @@ def slot_attention_config2(pk):
 
 def run_ours(args):
     import torch.distributed as dist
-    from playslot_b200 import configs, ops
+    from playslot_b200 import configs, ops, shard
     from playslot_b200.pipeline import seed_rollout, seed_rollout_host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,11 +223,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(ms, device="cuda")
 
     for _ in range(max(args.warmup, 3)):
         seed_rollout(savi, pred, video, NUM_SEED, NUM_PREDS)

@@ -152,16 +152,58 @@ def run_slot_attention_cases(setup_model):
     return res
 
 
+def run_aux_cases(setup_predictor):
+    """ rows a12 / a13: OCVPSeq behind PredictorWrapper and ActionCondtionalOCVP, built by the reference factory """
+    res = {}
+    g = torch.Generator().manual_seed(4242)
+    sh = torch.randn(2, 14, 8, 128, generator=g)
+    actions = torch.randn(2, 14, 4, generator=g)
+    # OCVP-Seq (experiments/BlockPush/predictors/OCVP) with a sliding buffer shorter than the roll-out
+    j = json.load(open(os.path.join(REF, "experiments", "BlockPush", "predictors", "OCVP", "experiment_params.json")))
+    j["prediction_params"]["input_buffer_size"] = 8
+    pred = setup_predictor(copy.deepcopy(j)).eval()
+    man = manifest_of(pred)
+    sd = synth_state_dict(man, 31)
+    sd["predictor.pe.pe"] = pred.state_dict()["predictor.pe.pe"].clone()
+    pred.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        full, _ = pred(sh, get_pred_only=False)
+        only, _ = pred(sh, get_pred_only=True)
+        single = pred.predictor(sh[:, :5])
+    res["ocvp_seq"] = {"manifest": man, "weight_seed": 31, "cfg": j["predictor"]["predictor_params"],
+                       "prediction_params": j["prediction_params"], "input_seed": 4242,
+                       "full": full.clone(), "pred_only": only.clone(), "single": single.clone(),
+                       "sh_checksum": float(sh.double().sum())}
+    # action-conditional OCVP (experiments/BlockPush/predictors/ActCondOCVP)
+    j = json.load(open(os.path.join(REF, "experiments", "BlockPush", "predictors", "ActCondOCVP", "experiment_params.json")))
+    pred = setup_predictor(copy.deepcopy(j)).eval()
+    man = manifest_of(pred)
+    sd = synth_state_dict(man, 32)
+    sd["dynamics_model.pos_emb.pe"] = pred.state_dict()["dynamics_model.pos_emb.pe"].clone()
+    pred.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out, _ = pred(sh, actions, num_seed=6, num_preds=8)
+    res["action_cond"] = {"manifest": man, "weight_seed": 32, "cfg": j["predictor"]["predictor_params"], "input_seed": 4242,
+                          "num_seed": 6, "num_preds": 8, "pred_slots": out.clone()}
+    return res
+
+
 def main():
     setup_model, setup_predictor = _import_reference()
     outdir = os.path.join(REPO, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
-    for name in CASES:
+    for name in ([] if os.environ.get("GOLDEN_ONLY_AUX") else CASES):
         fx = run_case(name, setup_model, setup_predictor)
         path = os.path.join(outdir, f"{name}.pt")
         torch.save(fx, path)
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB), vq margin {fx['vq_margin_min']:.3e}, "
               f"mask max {float(fx['masks'].max()):.3f}, sa mask max {float(fx['sa_masks_last'].max()):.3f}")
+    aux = run_aux_cases(setup_predictor)
+    path = os.path.join(outdir, "aux_predictors.pt")
+    torch.save(aux, path)
+    print(f"aux_predictors: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+    if os.environ.get("GOLDEN_ONLY_AUX"):
+        return
     sa = run_slot_attention_cases(setup_model)
     path = os.path.join(outdir, "slot_attention.pt")
     torch.save(sa, path)

@@ -400,6 +400,51 @@ def cocvp_train_unroll(sd, cfg, slots, protos, variab, num_seed, num_preds, p="d
 
 
 # --------------------------------------------------------------------------- #
+# OCVP-Seq + PredictorWrapper, action-conditional OCVP  
+# --------------------------------------------------------------------------- #
+
+def ocvp_seq(sd, cfg, inputs, p="predictor"):
+    """
+    OCVPSeq.forward (Predictors/transformers.py:231-340): inputs (B,F,S,D) -> (B,F,S,D).
+    cfg = predictor_params (token_dim, hidden_dim, num_layers, n_heads, residual).
+    """
+    B, Fr, S, D = inputs.shape
+    E, H = cfg["token_dim"], cfg["n_heads"]
+    t = _lin(sd, p + ".mlp_in", inputs) + sd[p + ".pe.pe"][:, :Fr]
+    for l in range(cfg["num_layers"]):
+        o = transformer_block(sd, f"{p}.transformer_encoders.{l}.object_encoder_block", t.reshape(B * Fr, S, E), H, E // H)
+        o = o.reshape(B, Fr, S, E).transpose(1, 2).reshape(B * S, Fr, E)
+        o = transformer_block(sd, f"{p}.transformer_encoders.{l}.time_encoder_block", o, H, E // H)
+        t = o.reshape(B, S, Fr, E).transpose(1, 2)
+    out = _lin(sd, p + ".mlp_out", t)
+    return out + inputs if cfg.get("residual", False) else out
+
+
+def wrapper_rollout(step_fn, slot_history, num_context, num_preds, buffer_size, get_pred_only):
+    """ PredictorWrapper.forward in eval mode (Predictors/predictor_wrappers.py:42-75): no teacher forcing """
+    start = num_context if get_pred_only else 1
+    n = num_preds if get_pred_only else num_context + num_preds - 1
+    buf = slot_history[:, :start]
+    preds = []
+    for _ in range(n):
+        cur = step_fn(buf)[:, -1]
+        buf = torch.cat([buf, cur.unsqueeze(1)], dim=1)
+        if buf.shape[1] > buffer_size:
+            buf = buf[:, buf.shape[1] - buffer_size:]
+        preds.append(cur)
+    return torch.stack(preds, dim=1)
+
+
+def action_conditional(sd, cfg, slot_history, actions, num_seed, num_preds):
+    """ ActionCondtionalOCVP.forward (Predictors/ActionConditional_OCVP.py:97-128); cfg = predictor_params """
+    n = num_seed + num_preds - 1
+    S = slot_history.shape[2]
+    emb = _lin(sd, "action_encoder.0", actions[:, :n]).unsqueeze(2).repeat(1, 1, S, 1)
+    dm = cfg["DynamicsModel"]["model_params"]
+    return cocvp_train_unroll(sd, dm, slot_history[:, :n], emb, None, num_seed, num_preds)
+
+
+# --------------------------------------------------------------------------- #
 # whole seed + rollout pipeline  (05_evaluate_PlaySlot.py:112-139)
 # --------------------------------------------------------------------------- #
 

@@ -359,3 +359,37 @@ def test_prior_rollout_runs_and_is_seeded():
         b, ib = pred.forward_multiple_samples(sh, 2, 6, 3, use_posterior=False)
     assert a.shape == (2, 2, 3, 8, 128) and torch.equal(a, b) and torch.equal(ia, ib)
     assert torch.isfinite(a).all()
+
+
+def test_aux_predictors_match_reference_golden():
+    """ rows a12 / a13 on the GPU: OCVPSeq behind PredictorWrapper, ActionCondtionalOCVP """
+    from playslot_b200.models.Predictors.transformers import OCVPSeq
+    from playslot_b200.models.Predictors.predictor_wrappers import PredictorWrapper
+    from playslot_b200.models.Predictors.ActionConditional_OCVP import ActionCondtionalOCVP
+    aux = torch.load(os.path.join(GOLDEN_DIR, "aux_predictors.pt"), weights_only=False)
+    gen = torch.Generator().manual_seed(4242)
+    sh = torch.randn(2, 14, 8, 128, generator=gen)
+    actions = torch.randn(2, 14, 4, generator=gen)
+    fx = aux["ocvp_seq"]
+    exp = {"prediction_params": fx["prediction_params"], "predictor": {"predictor_name": "OCVPSeq", "predictor_params": fx["cfg"]}}
+    pred = PredictorWrapper(exp_params=exp, predictor=OCVPSeq(num_slots=8, slot_dim=128, input_buffer_size=14, **fx["cfg"])).eval()
+    assert {k: list(v.shape) for k, v in pred.state_dict().items()} == fx["manifest"]
+    sd = synth_state_dict(fx["manifest"], fx["weight_seed"])
+    sd["predictor.pe.pe"] = pred.state_dict()["predictor.pe.pe"]
+    pred.load_state_dict(sd, strict=True)
+    pred = pred.to(DEV)
+    with torch.no_grad():
+        check("ocvp single", pred.predictor(sh[:, :5].to(DEV)), fx["single"])
+        check("ocvp full", pred(sh.to(DEV), get_pred_only=False)[0], fx["full"])
+        check("ocvp pred_only", pred(sh.to(DEV), get_pred_only=True)[0], fx["pred_only"])
+    fx = aux["action_cond"]
+    m = ActionCondtionalOCVP(**copy.deepcopy(fx["cfg"])).eval()
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == fx["manifest"]
+    sd = synth_state_dict(fx["manifest"], fx["weight_seed"])
+    sd["dynamics_model.pos_emb.pe"] = m.state_dict()["dynamics_model.pos_emb.pe"]
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    with torch.no_grad():
+        out, d = m(sh.to(DEV), actions.to(DEV), num_seed=fx["num_seed"], num_preds=fx["num_preds"])
+    check("action_cond pred_slots", out, fx["pred_slots"])
+    assert d["pred_slots"] is out

@@ -130,3 +130,59 @@ def test_restated_configs_equal_reference_json(name):
     j = json.load(open(f"/root/reference/experiments/{name}/predictors/PlaySlot/experiment_params.json"))
     c = configs.experiment(name)
     assert c["model"] == j["model"] and c["predictor"] == j["predictor"]
+
+
+def test_launcher_aliases_models_package():
+    """ `models.*` resolves to the mirror after launch.install(); reference-only sub-modules stay reachable """
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from playslot_b200 import launch\n"
+        "names = launch.install(reference_src=%r)\n"
+        "from models.SAVi import SAVi\n"
+        "from models.Predictors.LatentActionPredictors import SlotSingleActionPredictor\n"
+        "from models.Predictors.predictor_wrappers import PredictorWrapper\n"
+        "from models.Predictors.transformers import OCVPSeq\n"
+        "from models.Predictors.ActionConditional_OCVP import ActionCondtionalOCVP\n"
+        "import models\n"
+        "assert SAVi.__module__ == 'playslot_b200.models.SAVi', SAVi.__module__\n"
+        "assert models.SlotAttention.__module__.startswith('playslot_b200')\n"
+        "print('ok', len(names))\n"
+    ) % (ROOT, "/root/reference/src" if os.path.isdir("/root/reference/src") else None)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().startswith("ok")
+
+
+def test_ocvp_and_action_conditional_state_dict_layout():
+    """ OCVPSeq / ActionCondtionalOCVP parameter trees (a12, a13): key names as the reference builds them """
+    from playslot_b200.models.Predictors.transformers import OCVPSeq
+    from playslot_b200.models.Predictors.ActionConditional_OCVP import ActionCondtionalOCVP
+    m = OCVPSeq(num_slots=8, slot_dim=128, input_buffer_size=14, token_dim=256, hidden_dim=1024, num_layers=4, n_heads=8, residual=False)
+    keys = list(m.state_dict().keys())
+    assert "mlp_in.weight" in keys and "mlp_out.bias" in keys and "pe.pe" in keys
+    assert "transformer_encoders.3.time_encoder_block.attn.q.weight" in keys
+    assert "transformer_encoders.0.object_encoder_block.mlp.mlp.2.bias" in keys
+    assert m.state_dict()["pe.pe"].shape == (1, 14, 1, 256)
+    a = ActionCondtionalOCVP(slot_dim=128, raw_action_dim=4, action_embed_dim=16, condition_mode="sum", autoregressive_dynamics=True,
+                             DynamicsModel={"model_name": "SlotGPTDymamicsModel", "model_params": {
+                                 "residual": False, "embed_dim": 256, "head_dim": 64, "num_heads": 8, "mlp_size": 1024,
+                                 "num_layers": 4, "pos_enc_dropout": 0}})
+    keys = list(a.state_dict().keys())
+    assert "action_encoder.0.weight" in keys and "dynamics_model.pos_emb.pe" in keys
+    assert "dynamics_model.variability_emb.weight" not in keys
+
+
+def test_aux_predictor_manifests_match_reference():
+    from playslot_b200.models.Predictors.transformers import OCVPSeq
+    from playslot_b200.models.Predictors.predictor_wrappers import PredictorWrapper
+    from playslot_b200.models.Predictors.ActionConditional_OCVP import ActionCondtionalOCVP
+    aux = torch.load(os.path.join(GOLDEN_DIR, "aux_predictors.pt"), weights_only=False)
+    fx = aux["ocvp_seq"]
+    exp = {"prediction_params": fx["prediction_params"], "predictor": {"predictor_name": "OCVPSeq", "predictor_params": fx["cfg"]}}
+    pred = PredictorWrapper(exp_params=exp, predictor=OCVPSeq(num_slots=8, slot_dim=128, input_buffer_size=14, **fx["cfg"]))
+    assert list({k: list(v.shape) for k, v in pred.state_dict().items()}.items()) == list(fx["manifest"].items())
+    fx = aux["action_cond"]
+    m = ActionCondtionalOCVP(**copy.deepcopy(fx["cfg"]))
+    assert list({k: list(v.shape) for k, v in m.state_dict().items()}.items()) == list(fx["manifest"].items())

@@ -73,3 +73,28 @@ def test_sinusoid_pe_matches_reference_buffer():
     pe = O.sinusoid_pe(8, 256)
     assert pe.shape == (8, 256)
     assert float(pe[0, 1]) == 1.0 and float(pe[0, 0]) == 0.0
+
+
+def test_aux_predictors_oracle_matches_reference():
+    """ rows a12 / a13: OCVPSeq + PredictorWrapper and ActionCondtionalOCVP against the reference-made fixture """
+    aux = torch.load(os.path.join(GOLDEN_DIR, "aux_predictors.pt"), weights_only=False)
+    g = torch.Generator().manual_seed(4242)
+    sh = torch.randn(2, 14, 8, 128, generator=g)
+    actions = torch.randn(2, 14, 4, generator=g)
+    fx = aux["ocvp_seq"]
+    assert abs(float(sh.double().sum()) - fx["sh_checksum"]) < 1e-6 * max(1.0, abs(fx["sh_checksum"]))
+    sd = synth_state_dict(fx["manifest"], fx["weight_seed"])
+    sd["predictor.pe.pe"] = O.sinusoid_pe(14, fx["cfg"]["token_dim"]).view(1, 14, 1, -1)
+    pp = fx["prediction_params"]
+    with torch.no_grad():
+        step = lambda buf: O.ocvp_seq(sd, fx["cfg"], buf)
+        _check("ocvp single", step(sh[:, :5]), fx["single"])
+        _check("ocvp full", O.wrapper_rollout(step, sh, pp["num_context"], pp["num_preds"], pp["input_buffer_size"], False), fx["full"])
+        _check("ocvp pred_only", O.wrapper_rollout(step, sh, pp["num_context"], pp["num_preds"], pp["input_buffer_size"], True), fx["pred_only"])
+    fx = aux["action_cond"]
+    sd = synth_state_dict(fx["manifest"], fx["weight_seed"])
+    ctx = fx["cfg"]["DynamicsModel"]["model_params"].get("context_length", 8)
+    E = fx["cfg"]["DynamicsModel"]["model_params"]["embed_dim"]
+    sd["dynamics_model.pos_emb.pe"] = O.sinusoid_pe(ctx, E).view(1, ctx, 1, E)
+    with torch.no_grad():
+        _check("action_cond", O.action_conditional(sd, fx["cfg"], sh, actions, fx["num_seed"], fx["num_preds"]), fx["pred_slots"])
