@@ -46,6 +46,16 @@ int ps_linear(const float* X, int ldx, const float* W, const float* bias,
               const float* res, int ldres, int res_div, int res_mod,
               float* Y, int ldy, int M, int N, int K, int act, void* stream);
 
+/* ps_linear on the tensor cores (tcgen05 / TMEM, weights by TMA, activations split to fp16 hi/lo in the
+ * producer warps).  w_tc: 16-bit [2 (hi, lo)][Npad][Kp] holding W * w_scale (Kp = K rounded up to 64, Npad = N
+ * rounded up to 128, zero padded; w_scale a power of two chosen by the packer, undone in the epilogue).
+ * precision 3 ("fp16x3"): three products, fp32-grade result; 2 ("fp16") / 1 ("bf16"): one product.
+ * Same reference call sites as ps_linear. */
+int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_scale, int Kp, int Npad, const float* bias,
+                 const float* ln_gamma, const float* ln_beta, float ln_eps,
+                 const float* res, int ldres, int res_div, int res_mod,
+                 float* Y, int ldy, int M, int N, int K, int act, int precision, void* stream);
+
 /* Multi-head self attention over n_seq independent sequences of L tokens.
  * qkv: [n_seq*L, ld] rows holding q | k | v (each n_heads*head_dim wide, head-major); out: [n_seq*L, ldo].
  * slots_per_frame > 0 applies the block-causal (time x slot staircase) mask: token j is visible to token i
@@ -79,6 +89,12 @@ int ps_sa_main(const float* x, const float* A, const float* a0, const float* a1,
                float* masks /* may be NULL */, int B, int N, int S, int dim, int n_chunks, float ln_eps,
                float attn_eps, void* stream);
 
+/* ps_sa_main on the tensor cores: both contractions as tcgen05.mma over fp16 hi/lo split operands (fp32-grade),
+ * the token tile read once from HBM, normalised and kept in shared memory as the K-major A operand of the
+ * logits GEMM and, untransposed, as the MN-major A operand of the weighted-sum GEMM.  Same outputs. */
+int ps_sa_main_tc(const float* x, const float* A, const float* a0, float* partial, float* masks /* may be NULL */,
+                  int B, int N, int S, int dim, int n_chunks, float ln_eps, float attn_eps, void* stream);
+
 /* Per-slot update: reduce the partials, renormalise over locations (:109), to_v (:94), nn.GRUCell (:112-115),
  * residual MLP (:117), then (do_prep) the folded queries of the next iteration.  With do_update = 0 it only
  * prepares A/a0/a1 from slots_in.  Weight matrices suffixed T are transposed to [in][out]. */
@@ -91,6 +107,18 @@ int ps_sa_update(const float* partial, int n_chunks, const float* slots_in, floa
                  float* A, float* a0, float* a1,
                  int B, int S, int dim, int mlp_hidden, float scale, float ln_eps,
                  int do_update, int do_prep, void* stream);
+
+/* ps_sa_update with two weight-only re-associations prepared by the caller (W_iv = W_ih W_v; M_A = scale *
+ * diag(gamma_in) W_k^T W_q and v0 = scale * beta_in^T W_k^T W_q, stored transposed [in][out]) and every mat-vec
+ * split over K so that a stage costs about one L2 round trip.  mlp_hidden in {128, 256, 384}. */
+int ps_sa_update2(const float* partial, int n_chunks, const float* slots_in, float* slots_out,
+                  const float* ln_in_g, const float* ln_in_b,
+                  const float* WivT, const float* WhhT, const float* b_ih, const float* b_hh,
+                  const float* ln_mlp_g, const float* ln_mlp_b,
+                  const float* W1T, const float* b1, const float* W2T, const float* b2,
+                  const float* ln_slot_g, const float* ln_slot_b, const float* MAT, const float* v0,
+                  float* A, float* a0, int B, int S, int dim, int mlp_hidden, float ln_eps,
+                  int do_update, int do_prep, void* stream);
 
 /* ---- spatial-broadcast decoder (src/models/SAVi.py:220-248, EncodersDecoders/decoders.py:89-113) -------- */
 

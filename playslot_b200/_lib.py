@@ -17,11 +17,14 @@ SIGNATURES = {
     "ps_reset_launch_count": (None, []),
     "ps_device_info": (c_i, [ctypes.POINTER(c_i)] * 3),
     "ps_linear": (c_i, [c_f, c_i, c_f, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_linear_tc": (c_i, [c_f, c_i, c_f, c_fl, c_i, c_i, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_mha": (c_i, [c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_conv2d": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_sa_partial_floats": (c_i, [c_i]),
     "ps_sa_main": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),
+    "ps_sa_main_tc": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),
     "ps_sa_update": (c_i, [c_f, c_i, c_f, c_f] + [c_f] * 17 + [c_f, c_f, c_f] + [c_i, c_i, c_i, c_i, c_fl, c_fl, c_i, c_i, c_f]),
+    "ps_sa_update2": (c_i, [c_f, c_i, c_f, c_f] + [c_f] * 16 + [c_f, c_f] + [c_i, c_i, c_i, c_i, c_fl, c_i, c_i, c_f]),
     "ps_dec_expand": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_dec_composite": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_invdyn_tail": (c_i, [c_f] * 9 + [c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),

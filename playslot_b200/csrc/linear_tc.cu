@@ -1,0 +1,345 @@
+// tcgen05 linear layer:  Y[M,N] = act( LN?(X)[M,K] * W[N,K]^T + bias ) + res   with fp32-grade accuracy.
+// Replaces the nn.LayerNorm + nn.Linear (+ReLU / GELU / residual) chains of the reference on the tensor
+// cores: encoder MLP (src/models/SAVi.py:111-116,214-216), transformer q/k/v/out projections and MLPs
+// (src/models/BlocksUtils/attention.py:296,462-475,539-563; model_blocks.py:293-309), the cOCVP embeddings and
+// regression head (Predictors/DynamicsModels.py:119-148,487-510), the InvDyn encoders (LatentAction.py).
+//
+// Arithmetic.  Same "fp16x3" scheme as conv_tc.cu: x = hi + lo/2048 with hi = fp16(x), lo = fp16((x-hi)*2048);
+// D0 += A_hi*W_hi and D1 += A_hi*W_lo + A_lo*W_hi in two TMEM accumulators, Y = D0 + D1/2048 (22 mantissa bits).
+// precision 2 / 1: a single fp16 / bf16 product.
+//
+// Structure.  One CTA per (128-row, BN-column) output tile, 320 threads:
+//   warps 0-7 : A producers -- read the fp32 activations (coalesced float4, 8 loads in flight per thread), apply
+//               the LayerNorm (two-pass statistics held in registers), split to fp16 hi/lo and store them
+//               128B-swizzled K-major into the stage ring; afterwards the epilogue (TMEM -> registers ->
+//               shared-memory transpose -> bias / activation / residual -> coalesced 128-byte row stores)
+//   warp 8    : MMA issuer (one elected thread) and TMEM owner
+//   warp 9    : TMA producer of the packed weights [hi | lo][Npad][Kp] (128B swizzle)
+// K is consumed in blocks of 64 (one 128-byte swizzle row of fp16) through an mbarrier ring.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/playslot_b200.h"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int KB = 64;                     // K elements per stage
+constexpr int A_TILE = BM * 128;           // bytes of one 16-bit A tile
+constexpr int LT_MAX_STAGES = 4;
+constexpr int LT_THREADS = 320;
+constexpr float LT_LO_SCALE = 2048.0f;
+
+struct LinTcParams {
+    const float* X; int ldx;
+    const float* bias;
+    const float* ln_g; const float* ln_b; float ln_eps;
+    const float* res; int ldres; int res_div; int res_mod;
+    float* Y; int ldy;
+    int M, N, K, nkb, npad;
+    int act, stages, bf16;
+    float out_scale;
+};
+
+// 4 consecutive K elements -> 8 bytes of the hi tile (and of the lo tile)
+template <int NSPLIT>
+__device__ __forceinline__ void split_store4(const float4 v, uint8_t* hi, uint8_t* lo, bool bf16) {
+    if (bf16) {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(hi) = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+        return;
+    }
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(hi) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    if (NSPLIT == 2) {
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn((v.x - f0.x) * LT_LO_SCALE, (v.y - f0.y) * LT_LO_SCALE);
+        const __half2 l1 = __floats2half2_rn((v.z - f1.x) * LT_LO_SCALE, (v.w - f1.y) * LT_LO_SCALE);
+        *reinterpret_cast<uint2*>(lo) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
+}
+
+template <int BN, int NSPLIT>
+__global__ void __launch_bounds__(LT_THREADS, 2) linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const LinTcParams p) {
+    constexpr int NPROD = (NSPLIT == 2) ? 3 : 1;
+    constexpr int W_TILE = BN * 128;
+    constexpr int STAGE_BYTES = NSPLIT * (A_TILE + W_TILE);
+    constexpr int TM_COLS = (NSPLIT * BN < 32) ? 32 : NSPLIT * BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar_afull[LT_MAX_STAGES], bar_wfull[LT_MAX_STAGES], bar_empty[LT_MAX_STAGES], bar_acc;
+    __shared__ uint32_t tmem_base;
+    __shared__ float s_mean[BM], s_rstd[BM];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int STAGES = p.stages;
+
+    if (tid == 0) {
+        for (int s = 0; s < LT_MAX_STAGES; ++s) {
+            tc::mbar_init(&bar_afull[s], 8);      // one arrive per producer warp
+            tc::mbar_init(&bar_wfull[s], 1);
+            tc::mbar_init(&bar_empty[s], 1);
+        }
+        tc::mbar_init(&bar_acc, 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 8) tc::tmem_alloc(&tmem_base, TM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tm = tmem_base;
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ A producers
+        const int r_sub = tid >> 4;               // 0..15
+        const int c4 = tid & 15;                  // float4 index inside the 64-wide K block
+        const bool ln = p.ln_g != nullptr;
+        if (ln) {
+            // two-pass LayerNorm statistics, 16 lanes per row, 2 rows per round.  K <= 256: the row slice stays in
+            // registers between the passes; larger K re-reads (L1-resident).
+            const int nk = (p.K + 63) >> 6;
+#pragma unroll 1
+            for (int i0 = 0; i0 < 8; i0 += 2) {
+                float4 v[2][4];
+                float s[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int m = m0 + (i0 + i) * 16 + r_sub;
+                    s[i] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int k = c * 64 + c4 * 4;
+                        v[i][c] = (m < p.M && k < p.K) ? *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (nk > 4 && m < p.M)
+                        for (int k = 256 + c4 * 4; k < p.K; k += 64) {
+                            const float4 t = *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k);
+                            s[i] += (t.x + t.y) + (t.z + t.w);
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[i] += (v[i][c].x + v[i][c].y) + (v[i][c].z + v[i][c].w);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int row = (i0 + i) * 16 + r_sub;
+                    const int m = m0 + row;
+                    const float mean = s[i] / (float)p.K;
+                    float ss = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 64 + c4 * 4 < p.K) {
+                            const float a = v[i][c].x - mean, b = v[i][c].y - mean, cc = v[i][c].z - mean, d = v[i][c].w - mean;
+                            ss += (a * a + b * b) + (cc * cc + d * d);
+                        }
+                    }
+                    if (nk > 4 && m < p.M)
+                        for (int k = 256 + c4 * 4; k < p.K; k += 64) {
+                            const float4 t = *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k);
+                            const float a = t.x - mean, b = t.y - mean, cc = t.z - mean, d = t.w - mean;
+                            ss += (a * a + b * b) + (cc * cc + d * d);
+                        }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                    if (c4 == 0) { s_mean[row] = mean; s_rstd[row] = 1.0f / sqrtf(ss / (float)p.K + p.ln_eps); }
+                }
+            }
+            __syncwarp();                          // the rows a warp normalises are the rows it measured
+        }
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            const int s = kb % STAGES;
+            uint8_t* a_hi = smem + s * STAGE_BYTES;
+            uint8_t* a_lo = a_hi + A_TILE;
+            const int k = kb * KB + c4 * 4;
+            const bool k_ok = k < p.K;
+            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ln && k_ok) {
+                g4 = *reinterpret_cast<const float4*>(p.ln_g + k);
+                b4 = *reinterpret_cast<const float4*>(p.ln_b + k);
+            }
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + i * 16 + r_sub;
+                v[i] = (m < p.M && k_ok) ? *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], ((kb / STAGES) - 1) & 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = i * 16 + r_sub;
+                float4 x = v[i];
+                if (ln) {
+                    const float mu = s_mean[row], rs = s_rstd[row];
+                    x.x = (x.x - mu) * rs * g4.x + b4.x; x.y = (x.y - mu) * rs * g4.y + b4.y;
+                    x.z = (x.z - mu) * rs * g4.z + b4.z; x.w = (x.w - mu) * rs * g4.w + b4.w;
+                    if (!(m0 + row < p.M && k_ok)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const int off = row * 128 + ((((c4 >> 1) ^ (row & 7))) << 4) + ((c4 & 1) << 3);
+                split_store4<NSPLIT>(x, a_hi + off, a_lo + off, p.bf16 != 0);
+            }
+            tc::fence_async_proxy();               // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_afull[s]);
+        }
+        // ------------------------------------------------------------------ epilogue
+        // warp w owns TMEM lanes (w % 4) * 32 .. +31 (rows) and the column half w / 4.  Each 32 x CW chunk is
+        // transposed through shared memory so that every global store instruction writes one contiguous row piece.
+        constexpr int CW = (BN >= 64) ? 32 : 16;                     // chunk width
+        constexpr int CHUNKS = BN / (2 * CW);                        // chunks per warp
+        tc::mbar_wait(&bar_acc, 0);
+        tc::tc_fence_after();
+        const int q = warp & 3, ch = warp >> 2;
+        float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // stage ring is dead now
+        const uint32_t tl = tm + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int col0 = (ch * CHUNKS + c) * CW;
+            float v[CW];
+            if constexpr (CW == 32) tc::tmem_ld_32x32(tl + col0, v); else tc::tmem_ld_32x16(tl + col0, v);
+            if (NSPLIT == 2) {
+                float u[CW];
+                if constexpr (CW == 32) tc::tmem_ld_32x32(tl + BN + col0, u); else tc::tmem_ld_32x16(tl + BN + col0, u);
+#pragma unroll
+                for (int j = 0; j < CW; ++j) v[j] = fmaf(u[j], 1.0f / LT_LO_SCALE, v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) scratch[lane * 33 + j] = v[j] * p.out_scale;
+            __syncwarp();
+            // lanes now walk along a row: lane = column (two rows per instruction when CW == 16)
+            constexpr int RPI = 32 / CW;                             // rows per instruction
+            const int jj = lane % CW, rsub = lane / CW;
+            const int n = n0 + col0 + jj;
+            const bool n_ok = n < p.N;
+            const float bv = (p.bias && n_ok) ? __ldg(p.bias + n) : 0.f;
+#pragma unroll 4
+            for (int r = 0; r < 32; r += RPI) {
+                const int row = q * 32 + r + rsub;
+                const int m = m0 + row;
+                float t = scratch[(r + rsub) * 33 + jj] + bv;
+                if (p.act == 1) t = fmaxf(t, 0.f);
+                else if (p.act == 2) t = gelu_erf(t);
+                else if (p.act == 3) t = fabsf(t);
+                if (m < p.M && n_ok) {
+                    if (p.res) t += __ldg(p.res + (size_t)((m / p.res_div) % p.res_mod) * p.ldres + n);
+                    p.Y[(size_t)m * p.ldy + n] = t;
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (tc::elect_one()) {
+            const uint32_t idesc = p.bf16 ? tc::umma_idesc_bf16(BM, BN) : tc::umma_idesc_f16(BM, BN);
+            const uint32_t base = tc::smem_u32(smem);
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                tc::mbar_wait(&bar_wfull[s], ph);
+                tc::mbar_wait(&bar_afull[s], ph);
+                tc::tc_fence_after();
+                const uint32_t a_base = base + s * STAGE_BYTES;
+                const uint32_t w_base = a_base + NSPLIT * A_TILE;
+#pragma unroll
+                for (int pr = 0; pr < NPROD; ++pr) {
+                    const int as = (pr == 2) ? 1 : 0;           // (A_hi,W_hi), (A_hi,W_lo), (A_lo,W_hi)
+                    const int ws = (pr == 1) ? 1 : 0;
+#pragma unroll
+                    for (int k = 0; k < KB / 16; ++k) {
+                        const uint32_t a_addr = a_base + as * A_TILE + k * 32;
+                        const uint32_t b_addr = w_base + ws * W_TILE + k * 32;
+                        const uint32_t acc = tm + (pr ? BN : 0);
+                        const uint32_t accumulate = (pr <= 1) ? (uint32_t)(kb | k) : 1u;
+                        tc::umma_bf16(acc, tc::umma_desc_sw128(a_addr, 1024, 0), tc::umma_desc_sw128(b_addr, 1024, 0), idesc,
+                                      accumulate != 0 ? 1u : 0u);
+                    }
+                }
+                tc::umma_commit(&bar_empty[s]);
+            }
+            tc::umma_commit(&bar_acc);
+        }
+    } else {
+        // ------------------------------------------------------------------ TMA producer of the weights
+        if (tc::elect_one()) {
+            tc::tma_prefetch_desc(&mapW);
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % STAGES;
+                if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], ((kb / STAGES) - 1) & 1);
+                uint8_t* w_hi = smem + s * STAGE_BYTES + NSPLIT * A_TILE;
+                tc::mbar_expect_tx(&bar_wfull[s], NSPLIT * W_TILE);
+                tc::tma_load_2d(w_hi, &mapW, &bar_wfull[s], kb * KB, n0);
+                if (NSPLIT == 2) tc::tma_load_2d(w_hi + W_TILE, &mapW, &bar_wfull[s], kb * KB, p.npad + n0);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tm, TM_COLS);
+}
+
+template <int BN, int NSPLIT>
+int launch_linear_tc(const CUtensorMap& mW, const LinTcParams& p, cudaStream_t st) {
+    constexpr int STAGE_BYTES = NSPLIT * (A_TILE + BN * 128);
+    size_t smem = (size_t)p.stages * STAGE_BYTES;
+    if (smem < 8 * 32 * 33 * sizeof(float)) smem = 8 * 32 * 33 * sizeof(float);      // epilogue transpose scratch
+    smem += 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PS_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
+    linear_tc_kernel<BN, NSPLIT><<<grid, LT_THREADS, smem, st>>>(mW, p);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
+
+}  // namespace
+
+extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_scale, int Kp, int Npad, const float* bias,
+                            const float* ln_gamma, const float* ln_beta, float ln_eps,
+                            const float* res, int ldres, int res_div, int res_mod,
+                            float* Y, int ldy, int M, int N, int K, int act, int precision, void* stream) {
+    PS_REQUIRE(X && w_tc && Y, "ps_linear_tc: null pointer");
+    PS_REQUIRE(M >= 0 && N > 0 && K > 0, "ps_linear_tc: bad shape M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return PS_OK;
+    PS_REQUIRE(precision >= 1 && precision <= 3, "ps_linear_tc: precision must be 1 (bf16), 2 (fp16) or 3 (fp16x3)");
+    PS_REQUIRE(K % 4 == 0 && ldx % 4 == 0 && ps_aligned16(X), "ps_linear_tc: K (%d), ldx (%d) must be multiples of 4 and X 16-byte aligned", K, ldx);
+    PS_REQUIRE(Kp % KB == 0 && Kp >= K && Npad % 128 == 0 && Npad >= N, "ps_linear_tc: packed weight geometry Kp=%d Npad=%d does not cover K=%d N=%d", Kp, Npad, K, N);
+    PS_REQUIRE((ln_gamma == nullptr) == (ln_beta == nullptr), "ps_linear_tc: LayerNorm needs both gamma and beta");
+    PS_REQUIRE(!ln_gamma || (ps_aligned16(ln_gamma) && ps_aligned16(ln_beta)), "ps_linear_tc: LN params must be 16-byte aligned");
+    PS_REQUIRE(act >= 0 && act <= 3, "ps_linear_tc: unknown activation %d", act);
+    PS_REQUIRE(w_scale > 0.f, "ps_linear_tc: w_scale must be positive");
+    PS_REQUIRE((N + 31) / 32 <= 65535, "ps_linear_tc: N too large");
+    const int nsplit = precision == 3 ? 2 : 1;
+    LinTcParams p;
+    p.X = X; p.ldx = ldx; p.bias = bias; p.ln_g = ln_gamma; p.ln_b = ln_beta; p.ln_eps = ln_eps;
+    p.res = res; p.ldres = ldres; p.res_div = res_div > 0 ? res_div : 1; p.res_mod = res_mod > 0 ? res_mod : M;
+    p.Y = Y; p.ldy = ldy; p.M = M; p.N = N; p.K = K; p.nkb = Kp / KB; p.npad = Npad;
+    p.act = act; p.bf16 = precision == 1 ? 1 : 0; p.out_scale = 1.0f / w_scale;
+    // column tile: the widest that still gives the grid about two CTAs per SM
+    const long long mt = (M + BM - 1) / BM;
+    int bn = 128;
+    while (bn > 32 && (mt * ((N + bn - 1) / bn) < 2 * 148 || bn / 2 >= ((N + 31) / 32) * 32)) bn >>= 1;
+    const int stage_bytes = nsplit * (A_TILE + bn * 128);
+    int stages = (100 * 1024) / stage_bytes;         // at most ~100 KB per CTA: two CTAs per SM overlap each other's phases
+    if (stages < 1) stages = 1;
+    if (stages > LT_MAX_STAGES) stages = LT_MAX_STAGES;
+    if (stages > p.nkb) stages = p.nkb;
+    p.stages = stages;
+    CUtensorMap mW;
+    const int r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 2ull * Npad, (uint64_t)Kp, (uint32_t)bn, KB);
+    PS_REQUIRE(r == 0, "ps_linear_tc: cuTensorMapEncodeTiled(W) failed (%d)", r);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 128) return nsplit == 2 ? launch_linear_tc<128, 2>(mW, p, st) : launch_linear_tc<128, 1>(mW, p, st);
+    if (bn == 64) return nsplit == 2 ? launch_linear_tc<64, 2>(mW, p, st) : launch_linear_tc<64, 1>(mW, p, st);
+    return nsplit == 2 ? launch_linear_tc<32, 2>(mW, p, st) : launch_linear_tc<32, 1>(mW, p, st);
+}

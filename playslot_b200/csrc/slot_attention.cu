@@ -490,3 +490,182 @@ extern "C" int ps_sa_update(const float* partial, int n_chunks, const float* slo
     PS_LAUNCH_CHECK();
     return PS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// slot update, latency-optimised variant (ps_sa_update2).  Same mathematics as ps_sa_update with two weight-only
+// re-associations done once by the caller (exact up to fp32 rounding):
+//   W_iv  = W_ih W_v                       gi = W_iv u + b_ih            (drops the separate v projection)
+//   M_A   = scale * diag(gamma_in) W_k^T W_q,  v0 = scale * beta_in^T W_k^T W_q
+//                                          A = M_A LN_slot(slots),  a0 = v0 . LN_slot(slots)
+// One CTA per (frame, group of 4 slots), 768 threads; every mat-vec is split over K so that each thread issues
+// all of its (<= 32) weight loads before the first FMA: a stage costs about one L2 round trip.
+// ------------------------------------------------------------------------------------------------
+#define SU2_THREADS 768
+
+struct SaUpd2Params {
+    const float* partial; int CH;
+    const float* slots_in; float* slots_out;
+    const float* ln_in_g; const float* ln_in_b;
+    const float* WivT; const float* WhhT; const float* b_ih; const float* b_hh;      // [128][384]
+    const float* ln_mlp_g; const float* ln_mlp_b;
+    const float* W1T; const float* b1; const float* W2T; const float* b2;            // [128][Hm], [Hm][128]
+    const float* ln_slot_g; const float* ln_slot_b;
+    const float* MAT; const float* v0;                                               // [128 e][128 c], [128]
+    float* A; float* a0;
+    int B, S, Hm;
+    float ln_eps;
+    int do_update, do_prep;
+};
+
+// partial[(ks*N + o)*4 + r] = sum_{k in slice ks} Wt[k*ld + o] * in[k*4 + r]   for all (o, ks) tasks
+template <int KS>
+__device__ __forceinline__ void su2_matvec(const float* __restrict__ Wt, int ld, int K, int N, const float* in,
+                                           float* part, int tid) {
+    const int kper = K / KS;
+    for (int task = tid; task < N * KS; task += SU2_THREADS) {
+        const int o = task % N, ks = task / N;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k0 = ks * kper; k0 < (ks + 1) * kper; k0 += 32) {
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __ldg(Wt + (size_t)(k0 + j) * ld + o);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 x = *reinterpret_cast<const float4*>(in + (k0 + j) * 4);
+                acc[0] = fmaf(w[j], x.x, acc[0]); acc[1] = fmaf(w[j], x.y, acc[1]);
+                acc[2] = fmaf(w[j], x.z, acc[2]); acc[3] = fmaf(w[j], x.w, acc[3]);
+            }
+        }
+        *reinterpret_cast<float4*>(part + (size_t)task * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+__device__ __forceinline__ float su2_sum(const float* part, int N, int KS, int o, int r) {
+    float v = 0.f;
+    for (int ks = 0; ks < KS; ++ks) v += part[(size_t)(ks * N + o) * 4 + r];
+    return v;
+}
+
+__global__ __launch_bounds__(SU2_THREADS) void sa_update2_kernel(SaUpd2Params p) {
+    __shared__ __align__(16) float s_h[SA_D * 4];            // hidden state / new slots, [d][r]
+    __shared__ __align__(16) float s_u[SA_D * 4];            // normalised updates / LayerNorm outputs
+    __shared__ __align__(16) float s_hid[512 * 4];           // MLP hidden
+    __shared__ __align__(16) float s_p0[2 * 384 * 4];        // mat-vec partials
+    __shared__ __align__(16) float s_p1[2 * 384 * 4];
+    __shared__ float s_rs[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, r0 = blockIdx.x * 4;
+    const int S = p.S;
+    const int nr = min(4, S - r0);
+
+    for (int idx = tid; idx < SA_D * 4; idx += SU2_THREADS) {
+        const int r = idx / SA_D, d = idx - r * SA_D;
+        s_h[d * 4 + r] = (r < nr) ? p.slots_in[((size_t)b * S + r0 + r) * SA_D + d] : 0.f;
+    }
+    if (p.do_update) {
+        const int pstride = S * SA_D + S;
+        const float* pb = p.partial + (size_t)b * p.CH * pstride;
+        if (tid < 4) {
+            float v = 0.f;
+            if (tid < nr)
+                for (int c = 0; c < p.CH; ++c) v += pb[(size_t)c * pstride + S * SA_D + r0 + tid];
+            s_rs[tid] = v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < SA_D * 4; idx += SU2_THREADS) {
+            const int r = idx / SA_D, c = idx - r * SA_D;
+            float v = 0.f;
+            if (r < nr) {
+                float u = 0.f;
+                for (int ch = 0; ch < p.CH; ++ch) u += pb[(size_t)ch * pstride + (r0 + r) * SA_D + c];
+                const float rs = s_rs[r];
+                v = (p.ln_in_g[c] * u + p.ln_in_b[c] * rs) / rs;
+            }
+            s_u[c * 4 + r] = v;
+        }
+        __syncthreads();
+        // GRU gates (gate order r, z, n): gi = W_iv u + b_ih, gh = W_hh h + b_hh
+        su2_matvec<2>(p.WivT, 3 * SA_D, SA_D, 3 * SA_D, s_u, s_p0, tid);
+        su2_matvec<2>(p.WhhT, 3 * SA_D, SA_D, 3 * SA_D, s_h, s_p1, tid);
+        __syncthreads();
+        if (tid < SA_D * 4) {
+            const int d = tid >> 2, r = tid & 3;
+            const float gir = su2_sum(s_p0, 384, 2, d, r) + p.b_ih[d], ghr = su2_sum(s_p1, 384, 2, d, r) + p.b_hh[d];
+            const float giz = su2_sum(s_p0, 384, 2, SA_D + d, r) + p.b_ih[SA_D + d], ghz = su2_sum(s_p1, 384, 2, SA_D + d, r) + p.b_hh[SA_D + d];
+            const float gin = su2_sum(s_p0, 384, 2, 2 * SA_D + d, r) + p.b_ih[2 * SA_D + d], ghn = su2_sum(s_p1, 384, 2, 2 * SA_D + d, r) + p.b_hh[2 * SA_D + d];
+            const float rg = sigmoidf_(gir + ghr), zg = sigmoidf_(giz + ghz);
+            const float ng = tanhf(gin + rg * ghn);
+            s_h[tid] = (1.0f - zg) * ng + zg * s_h[tid];
+        }
+        __syncthreads();
+        su_layernorm(s_h, s_u, p.ln_mlp_g, p.ln_mlp_b, p.ln_eps, warp, lane);
+        __syncthreads();
+        su2_matvec<2>(p.W1T, p.Hm, SA_D, p.Hm, s_u, s_p0, tid);           // Hm <= 384: 2 x Hm x 4 floats fit s_p0
+        __syncthreads();
+        for (int idx = tid; idx < p.Hm * 4; idx += SU2_THREADS) {
+            const int o = idx >> 2, r = idx & 3;
+            s_hid[idx] = fmaxf(su2_sum(s_p0, p.Hm, 2, o, r) + p.b1[o], 0.f);
+        }
+        __syncthreads();
+        su2_matvec<4>(p.W2T, SA_D, p.Hm, SA_D, s_hid, s_p1, tid);
+        __syncthreads();
+        if (tid < SA_D * 4) {
+            const int d = tid >> 2, r = tid & 3;
+            const float v = s_h[tid] + su2_sum(s_p1, SA_D, 4, d, r) + p.b2[d];
+            s_h[tid] = v;
+            if (r < nr) p.slots_out[((size_t)b * S + r0 + r) * SA_D + d] = v;
+        }
+        __syncthreads();
+    } else {
+        __syncthreads();
+    }
+    if (p.do_prep) {
+        su_layernorm(s_h, s_u, p.ln_slot_g, p.ln_slot_b, p.ln_eps, warp, lane);
+        __syncthreads();
+        su2_matvec<4>(p.MAT, SA_D, SA_D, SA_D, s_u, s_p0, tid);
+        if (warp >= 16 && warp < 16 + nr) {                               // a0 = v0 . n, one warp per slot row
+            const int r = warp - 16;
+            float s0 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s0 = fmaf(p.v0[lane + 32 * i], s_u[(lane + 32 * i) * 4 + r], s0);
+            s0 = warp_sum(s0);
+            if (lane == 0) p.a0[b * S + r0 + r] = s0;
+        }
+        __syncthreads();
+        if (tid < SA_D * 4) {
+            const int c = tid >> 2, r = tid & 3;
+            if (r < nr) p.A[((size_t)b * S + r0 + r) * SA_D + c] = su2_sum(s_p0, SA_D, 4, c, r);
+        }
+    }
+}
+
+extern "C" int ps_sa_update2(const float* partial, int n_chunks, const float* slots_in, float* slots_out,
+                             const float* ln_in_g, const float* ln_in_b,
+                             const float* WivT, const float* WhhT, const float* b_ih, const float* b_hh,
+                             const float* ln_mlp_g, const float* ln_mlp_b,
+                             const float* W1T, const float* b1, const float* W2T, const float* b2,
+                             const float* ln_slot_g, const float* ln_slot_b, const float* MAT, const float* v0,
+                             float* A, float* a0, int B, int S, int dim, int mlp_hidden, float ln_eps,
+                             int do_update, int do_prep, void* stream) {
+    PS_REQUIRE(dim == SA_D, "ps_sa_update2: slot dim must be %d (got %d)", SA_D, dim);
+    PS_REQUIRE(S >= 1 && S <= 16, "ps_sa_update2: 1 <= num_slots <= 16 (got %d)", S);
+    PS_REQUIRE(mlp_hidden >= 32 && mlp_hidden <= 384 && mlp_hidden % 128 == 0,
+               "ps_sa_update2: mlp_hidden must be 128, 256 or 384 (got %d)", mlp_hidden);
+    PS_REQUIRE(slots_in, "ps_sa_update2: null slots");
+    PS_REQUIRE(!do_update || (partial && slots_out && WivT && WhhT && b_ih && b_hh && W1T && W2T && b1 && b2 && ln_mlp_g && ln_mlp_b && ln_in_g && ln_in_b),
+               "ps_sa_update2: update requested with null weights");
+    PS_REQUIRE(!do_prep || (A && a0 && MAT && v0 && ln_slot_g && ln_slot_b), "ps_sa_update2: prep requested with null buffers");
+    if (B == 0) return PS_OK;
+    PS_REQUIRE(B <= 65535, "ps_sa_update2: batch too large for one launch");
+    SaUpd2Params p;
+    p.partial = partial; p.CH = n_chunks; p.slots_in = slots_in; p.slots_out = slots_out;
+    p.ln_in_g = ln_in_g; p.ln_in_b = ln_in_b; p.WivT = WivT; p.WhhT = WhhT; p.b_ih = b_ih; p.b_hh = b_hh;
+    p.ln_mlp_g = ln_mlp_g; p.ln_mlp_b = ln_mlp_b; p.W1T = W1T; p.b1 = b1; p.W2T = W2T; p.b2 = b2;
+    p.ln_slot_g = ln_slot_g; p.ln_slot_b = ln_slot_b; p.MAT = MAT; p.v0 = v0; p.A = A; p.a0 = a0;
+    p.B = B; p.S = S; p.Hm = mlp_hidden; p.ln_eps = ln_eps; p.do_update = do_update; p.do_prep = do_prep;
+    dim3 grid((S + 3) / 4, B);
+    sa_update2_kernel<<<grid, SU2_THREADS, 0, (cudaStream_t)stream>>>(p);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}

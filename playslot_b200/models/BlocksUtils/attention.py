@@ -2,6 +2,8 @@
 Attention modules -- mirror of src/models/BlocksUtils/attention.py (same class names, constructor arguments,
 parameter tree and forward signatures); every forward launches playslot_b200 kernels.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -33,7 +35,9 @@ class SlotAttention(nn.Module):
     q.k^T = (q W_k).LN(x)^T and attn.v = (attn.LN(x)) W_v^T, exact up to fp32 rounding).
     """
 
-    TOKENS_PER_CTA = 256
+    TOKENS_PER_CTA = int(os.environ.get("PLAYSLOT_SA_TOKENS", "256"))
+    # "tc": both contractions on tcgen05 (fp16 hi/lo split operands, fp32-grade); "fp32": exact FFMA kernel
+    MODES = ("tc", "fp32")
 
     def __init__(self, dim_feats, dim_slots, num_slots, num_iters_first=2, num_iters=2,
                  mlp_hidden=128, epsilon=1e-8):
@@ -61,6 +65,9 @@ class SlotAttention(nn.Module):
         )
         self.attention_masks = None
         self._cache = DerivedWeights()
+        self.mode = os.environ.get("PLAYSLOT_SA_MODE", "tc")
+        if self.mode not in self.MODES:
+            raise ValueError(f"PLAYSLOT_SA_MODE={self.mode!r}; expected one of {self.MODES}")
 
     def _weights(self):
         """ transposed ([in][out]) copies of the small per-slot matrices, rebuilt when a parameter changes """
@@ -82,6 +89,12 @@ class SlotAttention(nn.Module):
                 "W2T": t(self.mlp[2].weight), "b2": c(self.mlp[2].bias),
                 "ln_slot_g": c(self.norm_slot.weight), "ln_slot_b": c(self.norm_slot.bias),
                 "WqT": t(self.to_q.weight), "Wk": c(self.to_k.weight),
+                # weight-only re-associations of ps_sa_update2 (products formed in fp64, rounded once)
+                "WivT": (self.gru.weight_ih.detach().double() @ self.to_v.weight.detach().double()).t().float().contiguous(),
+                "MAT": (self.scale * self.norm_input.weight.detach().double()[:, None]
+                        * (self.to_k.weight.detach().double().t() @ self.to_q.weight.detach().double())).t().float().contiguous(),
+                "v0": (self.scale * (self.norm_input.bias.detach().double()
+                                     @ (self.to_k.weight.detach().double().t() @ self.to_q.weight.detach().double()))).float().contiguous(),
             }
         return self._cache.get(src, build)
 
@@ -107,12 +120,22 @@ class SlotAttention(nn.Module):
         out = torch.empty_like(slots)
         hidden = self.mlp[0].weight.shape[0]
         eps_ln = self.norm_input.eps
+        fast_update = hidden in (128, 256, 384)
+
+        def update(partial_, src, dst, do_update, do_prep):
+            if fast_update:
+                ops.sa_update2(partial_, n_chunks, src, dst, w, A, a0, hidden, eps_ln, do_update, do_prep)
+            else:
+                ops.sa_update(partial_, n_chunks, src, dst, w, A, a0, a1, hidden, self.scale, eps_ln, do_update, do_prep)
         # folded queries of the first iteration
-        ops.sa_update(None, n_chunks, cur, None, w, A, a0, a1, hidden, self.scale, eps_ln, False, True)
+        update(None, cur, None, False, True)
         for it in range(num_iters):
             last = it == num_iters - 1
-            ops.sa_main(x, A, a0, a1, partial, masks if last else None, n_chunks, eps_ln, self.epsilon)
-            ops.sa_update(partial, n_chunks, cur, out, w, A, a0, a1, hidden, self.scale, eps_ln, True, not last)
+            if self.mode == "tc":
+                ops.sa_main_tc(x, A, a0, partial, masks if last else None, n_chunks, eps_ln, self.epsilon)
+            else:
+                ops.sa_main(x, A, a0, a1, partial, masks if last else None, n_chunks, eps_ln, self.epsilon)
+            update(partial, cur, out, True, not last)
             cur = out
         self.attention_masks = masks
         return out

@@ -5,11 +5,31 @@ PyTorch is used for device memory, streams and (later) autograd plumbing only: e
 its arguments, allocates the outputs with torch.empty and launches hand-written kernels on the current
 CUDA stream.  CPU tensors are rejected -- there is no fallback.
 """
+import math
+import os
+
 import torch
 
 from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_ABS = 0, 1, 2, 3
+
+# arithmetic of the Linear layers: "fp16x3" (tcgen05, split fp16 operands, three products, fp32-grade),
+# "fp16" / "bf16" (tcgen05, one half-precision product) or "fp32" (exact FFMA kernel on the CUDA cores)
+LINEAR_MODES = ("fp16x3", "fp16", "bf16", "fp32")
+_LINEAR_MODE = os.environ.get("PLAYSLOT_LINEAR_MODE", "fp16x3")
+LINEAR_TC_MIN_ROWS = 128          # below one row tile the CUDA-core kernel is used
+
+
+def set_linear_mode(mode):
+    global _LINEAR_MODE
+    if mode not in LINEAR_MODES:
+        raise ValueError(f"linear mode {mode!r}; expected one of {LINEAR_MODES}")
+    _LINEAR_MODE = mode
+
+
+def linear_mode():
+    return _LINEAR_MODE
 
 
 def _ptr(t):
@@ -117,11 +137,53 @@ def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res
         ldres = N
         if res_mod is None:
             res_mod = res.shape[0]
+    if _LINEAR_MODE != "fp32" and M >= LINEAR_TC_MIN_ROWS:
+        prec = TC_PRECISION[_LINEAR_MODE]
+        w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, prec)
+        with _timed("linear_tc_p%d" % prec, (M, N, K)):
+            st = lib.ps_linear_tc(_ptr(x2), K, _ptr(w_tc), float(w_scale), Kp, Npad, _ptr(bias), _ptr(g), _ptr(b), float(eps),
+                                  _ptr(res), ldres, int(res_div), int(res_mod or 0), _ptr(y2), N, M, N, K, int(act), prec, _stream())
+        _lib.check(st, "ps_linear_tc")
+        return out
     with _timed("linear", (M, N, K)):
         st = lib.ps_linear(_ptr(x2), K, _ptr(weight), _ptr(bias), _ptr(g), _ptr(b), float(eps),
                            _ptr(res), ldres, int(res_div), int(res_mod or 0), _ptr(y2), N, M, N, K, int(act), _stream())
     _lib.check(st, "ps_linear")
     return out
+
+
+def pack_linear_weight_tc(w, precision):
+    """
+    nn.Linear weight (N, K) fp32 -> (16-bit tensor (2 [hi, lo], Npad, Kp), w_scale, Kp, Npad): K padded to a
+    multiple of 64 and N to a multiple of 128 with zeros; weights multiplied by a power of two that puts max|w|
+    near 1 (exact; undone in the kernel epilogue) so the fp16 parts stay away from the subnormal range.
+    """
+    N, K = w.shape
+    Kp, Npad = (K + 63) // 64 * 64, (N + 127) // 128 * 128
+    wt = torch.zeros(Npad, Kp, device=w.device, dtype=torch.float32)
+    wt[:N, :K] = w.detach().float()
+    amax = float(wt.abs().max())
+    scale = 1.0 if amax == 0.0 or precision == 1 else 2.0 ** (-round(math.log2(amax)))
+    wt = wt * scale
+    if precision == 1:
+        hi = wt.to(torch.bfloat16).view(torch.int16)
+        lo = torch.zeros_like(hi)
+    else:
+        h = wt.to(torch.float16)
+        hi = h.view(torch.int16)
+        lo = ((wt - h.float()) * TC_LO_SCALE).to(torch.float16).view(torch.int16)
+    return torch.stack([hi, lo], dim=0).contiguous(), scale, Kp, Npad
+
+
+def _packed_linear_weight(weight, precision):
+    """ packed copy cached on the weight tensor object, rebuilt when the tensor is modified in place or moved """
+    key = (weight._version, weight.data_ptr(), precision)
+    c = getattr(weight, "_ps_tc_pack", None)
+    if c is None or c[0] != key:
+        with torch.no_grad():
+            c = (key, pack_linear_weight_tc(weight, precision))
+        weight._ps_tc_pack = c
+    return c[1]
 
 
 def mha(qkv, n_seq, L, n_heads, head_dim, slots_per_frame=0, res=None):
@@ -182,6 +244,17 @@ def sa_main(x, A, a0, a1, partial, masks, n_chunks, ln_eps, attn_eps):
     _lib.check(st, "ps_sa_main")
 
 
+def sa_main_tc(x, A, a0, partial, masks, n_chunks, ln_eps, attn_eps):
+    lib = _lib.load()
+    _req(x, "feats"); _req(A, "A"); _req(partial, "partial")
+    B, N, D = x.shape
+    S = A.shape[1]
+    with _timed("sa_main_tc", (B, N, S, D, masks is not None)):
+        st = lib.ps_sa_main_tc(_ptr(x), _ptr(A), _ptr(a0), _ptr(partial), _ptr(masks), B, N, S, D, n_chunks,
+                               float(ln_eps), float(attn_eps), _stream())
+    _lib.check(st, "ps_sa_main_tc")
+
+
 def sa_update(partial, n_chunks, slots_in, slots_out, w, A, a0, a1, mlp_hidden, scale, ln_eps, do_update, do_prep):
     """ w: dict of prepared SlotAttention weights (see models.BlocksUtils.attention.SlotAttention._weights) """
     lib = _lib.load()
@@ -196,6 +269,21 @@ def sa_update(partial, n_chunks, slots_in, slots_out, w, A, a0, a1, mlp_hidden, 
                           _ptr(A), _ptr(a0), _ptr(a1), B, S, D, int(mlp_hidden), float(scale), float(ln_eps),
                           int(do_update), int(do_prep), _stream())
     _lib.check(st, "ps_sa_update")
+
+
+def sa_update2(partial, n_chunks, slots_in, slots_out, w, A, a0, mlp_hidden, ln_eps, do_update, do_prep):
+    """ latency-optimised slot update with the folded weights w["WivT"], w["MAT"], w["v0"] """
+    lib = _lib.load()
+    B, S, D = slots_in.shape
+    with _timed("sa_update"):
+        st = lib.ps_sa_update2(_ptr(partial), n_chunks, _ptr(slots_in), _ptr(slots_out),
+                               _ptr(w["ln_in_g"]), _ptr(w["ln_in_b"]),
+                               _ptr(w["WivT"]), _ptr(w["WhhT"]), _ptr(w["b_ih"]), _ptr(w["b_hh"]),
+                               _ptr(w["ln_mlp_g"]), _ptr(w["ln_mlp_b"]),
+                               _ptr(w["W1T"]), _ptr(w["b1"]), _ptr(w["W2T"]), _ptr(w["b2"]),
+                               _ptr(w["ln_slot_g"]), _ptr(w["ln_slot_b"]), _ptr(w["MAT"]), _ptr(w["v0"]),
+                               _ptr(A), _ptr(a0), B, S, D, int(mlp_hidden), float(ln_eps), int(do_update), int(do_prep), _stream())
+    _lib.check(st, "ps_sa_update2")
 
 
 # ------------------------------------------------------------------------------------------------ decoder

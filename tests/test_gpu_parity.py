@@ -49,10 +49,25 @@ def g(*shape, seed=0, scale=1.0):
 
 # ----------------------------------------------------------------------------------------------- primitives
 
-@pytest.mark.parametrize("M,N,K", [(1, 8, 16), (64, 64, 16), (130, 72, 36), (515, 384, 128), (4096, 1024, 256), (300, 128, 1024)])
-@pytest.mark.parametrize("mode", ["plain", "ln_gelu_res", "relu_bcast"])
-def test_linear(M, N, K, mode):
+@pytest.fixture
+def linear_mode_guard():
     from playslot_b200 import ops
+    old = ops.linear_mode()
+    yield ops
+    ops.set_linear_mode(old)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 8, 16), (64, 64, 16), (130, 72, 36), (515, 384, 128), (4096, 1024, 256), (300, 128, 1024),
+                                   (3072, 1536, 128), (3072, 128, 136), (128, 16, 256), (1000, 1600, 128), (20000, 128, 64), (257, 48, 32)])
+@pytest.mark.parametrize("mode", ["plain", "ln_gelu_res", "relu_bcast"])
+@pytest.mark.parametrize("lmode,tol", [("fp32", 1e-4), ("fp16x3", 1e-4), ("fp16", 4e-3), ("bf16", 3e-2)])
+def test_linear(M, N, K, mode, lmode, tol, linear_mode_guard):
+    """ ps_linear (fp32 FFMA) and ps_linear_tc (tcgen05; rows >= 128) against an fp64 evaluation """
+    ops = linear_mode_guard
+    ops.set_linear_mode(lmode)
+    if lmode != "fp32" and M < ops.LINEAR_TC_MIN_ROWS:
+        pytest.skip("below one row tile the CUDA-core kernel runs in every mode")
+    TOL = tol
     x, w, b = g(M, K, seed=1), g(N, K, seed=2, scale=K ** -0.5), g(N, seed=3, scale=0.1)
     xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
     if mode == "plain":
@@ -70,7 +85,7 @@ def test_linear(M, N, K, mode):
         y = ops.linear(xd, wd, None, act=ops.ACT_RELU, res=table.to(DEV), res_div=div, res_mod=R)
         rows = (torch.arange(M) // div) % R
         ref = F.relu(F.linear(x.double(), w.double())) + table.double()[rows]
-    check(f"linear[{mode}]", y, ref.float())
+    check(f"linear[{mode}/{lmode}]", y, ref.float(), TOL)
 
 
 @pytest.mark.parametrize("n_seq,L,H,dh,spf", [(3, 9, 4, 64, 0), (2, 64, 8, 64, 8), (5, 8, 4, 32, 0), (2, 160, 8, 64, 16), (4, 30, 8, 64, 6)])
@@ -154,8 +169,12 @@ def _sa_module(S, sd, mlp_hidden=256, it_first=3, it=1):
     return m.to(DEV)
 
 
+SA_MODES = ["tc", "fp32"]
+
+
+@pytest.mark.parametrize("sa_mode", SA_MODES)
 @pytest.mark.parametrize("key", ["S8", "S4"])
-def test_slot_attention_golden(key):
+def test_slot_attention_golden(key, sa_mode):
     """ against the real reference's SlotAttention (fixture made by oracle/make_golden.py) """
     fx = torch.load(os.path.join(GOLDEN_DIR, "slot_attention.pt"), weights_only=False)[key]
     S = int(key[1:])
@@ -164,6 +183,7 @@ def test_slot_attention_golden(key):
     feats = torch.randn(2, 4096, 128, generator=gen)
     slots = torch.randn(2, S, 128, generator=gen)
     m = _sa_module(S, sd)
+    m.mode = sa_mode
     with torch.no_grad():
         o3 = m(feats.to(DEV), slots.to(DEV), step=0)
         m3 = m.get_attention_masks().clone()
@@ -176,8 +196,10 @@ def test_slot_attention_golden(key):
 
 
 @pytest.mark.parametrize("B,N,S,hidden,iters,sharpen", [(3, 1000, 6, 128, 2, 1.0), (1, 16384, 16, 256, 3, 4.0), (5, 4096, 3, 256, 1, 8.0),
-                                                         (2, 77, 8, 256, 3, 1.0), (2, 256, 1, 128, 2, 1.0)])
-def test_slot_attention_oracle(B, N, S, hidden, iters, sharpen):
+                                                         (2, 77, 8, 256, 3, 1.0), (2, 256, 1, 128, 2, 1.0), (2, 300, 16, 256, 2, 1.0),
+                                                         (3, 4096, 4, 256, 3, 1.0)])
+@pytest.mark.parametrize("sa_mode", SA_MODES)
+def test_slot_attention_oracle(B, N, S, hidden, iters, sharpen, sa_mode):
     """ ragged / large token counts, 1..16 slots, vs the CPU oracle """
     from playslot_b200.models.BlocksUtils.attention import SlotAttention
     ref_mod = SlotAttention(128, 128, S, iters, iters, hidden)
@@ -190,6 +212,7 @@ def test_slot_attention_oracle(B, N, S, hidden, iters, sharpen):
         sd64 = {k: v.double() for k, v in sd.items()}
         ro64, rm64 = O.slot_attention(sd64, feats.double(), slots.double(), iters)
         m = _sa_module(S, sd, hidden, iters, iters)
+        m.mode = sa_mode
         o = m(feats.to(DEV), slots.to(DEV), step=0)
         mk = m.get_attention_masks()
     if sharpen > 1.0:       # logits scaled by sharpen^2: compare conditioning-aware against the fp64 evaluation
@@ -200,13 +223,15 @@ def test_slot_attention_oracle(B, N, S, hidden, iters, sharpen):
         check("masks", mk, rm)
 
 
-def test_slot_attention_full_size_properties():
+@pytest.mark.parametrize("sa_mode", SA_MODES)
+def test_slot_attention_full_size_properties(sa_mode):
     """ config-2 size (B=64, N=4096, D=128, S=8, 3 iterations): size-independent properties """
     from playslot_b200.models.BlocksUtils.attention import SlotAttention
     S = 8
     man = {"slot_attention." + k: list(v.shape) for k, v in SlotAttention(128, 128, S, 3, 1, 256).state_dict().items()}
     sd = synth_state_dict(man, 77, 4.0)
     m = _sa_module(S, sd)
+    m.mode = sa_mode
     feats, slots = g(64, 4096, 128, seed=5).to(DEV), g(64, S, 128, seed=6).to(DEV)
     with torch.no_grad():
         o = m(feats, slots, step=0)
@@ -289,13 +314,16 @@ def test_decode_half_precision_modes_stated_tolerance(mode, tol):
 
 @pytest.mark.parametrize("conv_mode", ["fp16x3", "fp32"])
 @pytest.mark.parametrize("case", PIPELINE_CASES)
-def test_pipeline_matches_reference_golden(case, conv_mode):
-    """ seed + rollout pipeline of 05_evaluate_PlaySlot.py:112-139 against vectors produced by the real reference """
+def test_pipeline_matches_reference_golden(case, conv_mode, linear_mode_guard):
+    """ seed + rollout pipeline of 05_evaluate_PlaySlot.py:112-139 against vectors produced by the real reference;
+    "fp16x3" = every tensor-core path (convolutions, linears, SlotAttention), "fp32" = every exact CUDA-core path """
     fx, ssd, psd, video, noise, init_noise = load_case(case)
     scfg, pcfg = fx["savi_cfg"], fx["predictor_cfg"]
     B, ns, npred = fx["B"], fx["num_seed"], fx["num_preds"]
     savi = make_savi(scfg, ssd, DEV)
     savi.conv_mode = conv_mode
+    linear_mode_guard.set_linear_mode(conv_mode)
+    savi.slot_attention.mode = "fp32" if conv_mode == "fp32" else "tc"
     pred = make_predictor(fx["predictor_name"], pcfg, psd, DEV)
     S, D = scfg["num_slots"], scfg["slot_dim"]
     with torch.no_grad():

@@ -1,0 +1,26 @@
+""" development tool: a short program that launches the kernels we want to look at under ncu """
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from playslot_b200 import ops
+from playslot_b200.models.BlocksUtils.attention import SlotAttention
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+torch.manual_seed(0)
+if what in ("all", "linear"):
+    for (M, N, K, ln) in ((1 << 20, 128, 128, False), (3072, 1536, 128, True), (3072, 128, 512, False)):
+        x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") * K ** -0.5; b = torch.randn(N, device="cuda")
+        g, be = torch.ones(K, device="cuda"), torch.zeros(K, device="cuda")
+        for _ in range(3):
+            y = ops.linear(x, w, b, ln=(g, be, 1e-6) if ln else None)
+        torch.cuda.synchronize()
+if what in ("all", "sa"):
+    S = 8
+    m = SlotAttention(128, 128, S, 3, 1, 256).eval().cuda()
+    feats = torch.randn(64, 4096, 128, device="cuda"); slots = torch.randn(64, S, 128, device="cuda")
+    with torch.no_grad():
+        for _ in range(2):
+            m(feats, slots, step=0)
+    torch.cuda.synchronize()
+print("done")
