@@ -168,6 +168,51 @@ int ps_dec_expand_split(const float* G, const float* P_hwc, void* act_out, int n
 /* fp32 NCHW [n,64,H,W] -> padded NHWC split (feeds the first tensor-core layer after a CUDA-core layer). */
 int ps_nchw_to_split(const float* x, void* act_out, int n_img, int H, int W, int precision, void* stream);
 
+/* ---- training step: backward kernels (src/04_train_PlaySlot.py:32-122, base/basePredictorTrainer.py:320-333) ---- */
+
+/* Un-fused LayerNorm of the training path (keeps mean / rstd [M]) and its backward (dgamma / dbeta [K] are overwritten). */
+int ps_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean, float* rstd,
+                     int M, int K, void* stream);
+int ps_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx,
+                     float* dgamma, float* dbeta, int M, int K, void* stream);
+
+/* Weight gradient of nn.Linear: dW[N,K] = dY[M,N]^T X[M,K], db[N] = column sums of dY (db may be NULL); outputs overwritten.
+ * The data gradient dX = dY W is ps_linear with the transposed weight. */
+int ps_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int N, int K, void* stream);
+
+/* activation forward on saved pre-activations / backward; act: 1 ReLU, 2 GELU (exact erf), 3 |x| */
+int ps_act_fwd(const float* z, float* y, long long n, int act, void* stream);
+int ps_act_bwd(const float* dy, const float* z, float* dz, long long n, int act, void* stream);
+
+/* Backward of ps_mha (no residual): dqkv laid out like qkv; sequences of at most 96 tokens x head_dim 64. */
+int ps_mha_bwd(const float* qkv, int ld, const float* dout, int ldo, float* dqkv, int n_seq, int L, int n_heads, int head_dim,
+               int slots_per_frame, void* stream);
+
+/* Backward of ps_invdyn_tail w.r.t. mv: incoming gradients (any may be NULL) for action_dist, the sampled latent, the
+ * straight-through prototype, the variability and the per-vector quantisation loss mean_A (sg(z_q) - z)^2. */
+int ps_invdyn_tail_bwd(const float* mv, const float* noise, const float* z, const long long* idx, const float* codebook,
+                       const float* g_dist, const float* g_z, const float* g_proto, const float* g_var, const float* g_quant,
+                       float* d_mv, int B, int T, int R, int A, int K, int per_slot, float eps, void* stream);
+
+/* Decoder data gradient (the decoder is frozen in 04_train_PlaySlot.py: no weight gradients).
+ * ps_dec_composite_bwd: gradients of recon / recons / masks (any may be NULL) -> g_o [M*S,4,H,W], the gradient of the
+ *   last convolution's RGB+alpha output (slot softmax + compositing, SAVi.py:226-234).
+ * ps_dec_final_dgrad : data gradient of that 3x3 convolution (w_packed [64][9][4]) and of the ReLU in front of it
+ *   (h = its fp32 NCHW input), written as padded NHWC split planes for ps_conv5x5_tc_dgrad.
+ * ps_conv5x5_tc_dgrad: data gradient of Conv2d(64,64,5)+ReLU on tcgen05: w_tc_flipped packs W'[ci][co][ky][kx] =
+ *   W[co][ci][4-ky][4-kx]; the result is masked by (mask_act > 0), mask_act = the block's saved input (padded split).
+ * ps_dec_expand_bwd  : gradient of the collapsed first convolution: sums of g [n,H*W,64] over the (2*pad+1)^2 border
+ *   classes -> dG [n, ksize*ksize*64] (then dSlots = dG * Wsum via ps_linear).
+ * g_scale (device scalar, may be NULL): a power of two the gradients are multiplied by on entry (ps_dec_final_dgrad) and
+ *   divided by on exit (ps_dec_expand_bwd) so that loss gradients of any magnitude stay inside the fp16 split's range. */
+int ps_dec_composite_bwd(const float* recons, const float* masks, const float* g_recon, const float* g_recons,
+                         const float* g_masks, float* g_o, int M, int S, int H, int W, void* stream);
+int ps_dec_final_dgrad(const float* g_o, const float* w_packed, const float* h, void* act_out, const float* g_scale,
+                       int n_img, int H, int W, int precision, void* stream);
+int ps_conv5x5_tc_dgrad(const void* g_in, const void* w_tc_flipped, float w_scale, const void* mask_act, void* act_out,
+                        float* out_tokens, int n_img, int H, int W, int out_mode, int precision, void* stream);
+int ps_dec_expand_bwd(const float* g_tokens, float* dG, const float* g_scale, int n_img, int H, int W, int ksize, void* stream);
+
 /* Stand-alone nearest-codeword lookup (VectorQuantizer.forward, quantization.py:294-322): z [n,A] ->
  * proto = z + (z_q - z), exact codewords z_q, int64 indices, per-vector mean_A (z_q - z)^2. */
 int ps_vq_lookup(const float* z, const float* codebook, float* proto_out, float* zq_out, long long* idx_out,

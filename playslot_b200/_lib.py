@@ -32,6 +32,17 @@ SIGNATURES = {
     "ps_conv_tc_plane_elems": (ctypes.c_longlong, [c_i, c_i, c_i]),
     "ps_conv5x5_tc": (c_i, [c_f, c_f, c_f, c_fl, c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
     "ps_dec_expand_split": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_layernorm_fwd": (c_i, [c_f, c_f, c_f, c_fl, c_f, c_f, c_f, c_i, c_i, c_f]),
+    "ps_layernorm_bwd": (c_i, [c_f] * 8 + [c_i, c_i, c_f]),
+    "ps_linear_wgrad": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "ps_act_fwd": (c_i, [c_f, c_f, ctypes.c_longlong, c_i, c_f]),
+    "ps_act_bwd": (c_i, [c_f, c_f, c_f, ctypes.c_longlong, c_i, c_f]),
+    "ps_mha_bwd": (c_i, [c_f, c_i, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_invdyn_tail_bwd": (c_i, [c_f] * 11 + [c_i] * 6 + [c_fl, c_f]),
+    "ps_dec_composite_bwd": (c_i, [c_f] * 6 + [c_i, c_i, c_i, c_i, c_f]),
+    "ps_dec_final_dgrad": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
+    "ps_conv5x5_tc_dgrad": (c_i, [c_f, c_f, c_fl, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_dec_expand_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_nchw_to_split": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
 }
 

@@ -1,0 +1,162 @@
+"""
+Differentiable front-ends of the kernels (torch.autograd.Function plumbing around the C ABI).
+
+The reference trains the predictor with plain PyTorch autograd (src/04_train_PlaySlot.py:32-122: SAVi frozen and
+run without gradients, InvDyn + cOCVP forward, decoder with gradients w.r.t. its input slots, three losses,
+`loss.backward()`).  Here every arithmetic node of that graph is one of our kernels with a hand-written backward
+kernel (csrc/backward.cu); autograd only strings them together (views, concatenations, residual additions).
+
+When no gradient is needed the functions below fall through to the fused inference kernels of `ops`.
+"""
+import torch
+
+from . import ops
+
+
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = _c(x)
+        y, mean, rstd = ops.layernorm_fwd(x, _c(gamma.detach()), _c(beta.detach()), eps)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(_c(dy), x, mean, rstd, _c(gamma.detach()))
+        return dx, dg, db, None
+
+
+class _Linear(torch.autograd.Function):
+    """ y = x W^T + b in exact fp32 (the weights change every optimiser step, see ops.linear) """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return ops.linear(x, _c(weight.detach()), None if bias is None else _c(bias.detach()), mode="fp32")
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        N, K = weight.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear(dy, weight.detach().t().contiguous(), None, mode="fp32").view(x.shape)     # dX = dY W
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.linear_wgrad(dy.view(-1, N), x.view(-1, K), want_bias=ctx.has_bias)
+        return dx, dw, db
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, act):
+        z = _c(z)
+        ctx.save_for_backward(z)
+        ctx.act = act
+        return ops.act_fwd(z, act)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (z,) = ctx.saved_tensors
+        return ops.act_bwd(_c(dy), z, ctx.act), None
+
+
+class _MHA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, n_seq, L, n_heads, head_dim, spf):
+        qkv = _c(qkv)
+        ctx.save_for_backward(qkv)
+        ctx.geom = (n_seq, L, n_heads, head_dim, spf)
+        return ops.mha(qkv, n_seq, L, n_heads, head_dim, spf)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        n_seq, L, H, dh, spf = ctx.geom
+        return ops.mha_bwd(qkv, _c(dout), n_seq, L, H, dh, spf), None, None, None, None, None
+
+
+def layer_norm(x, gamma, beta, eps):
+    return _LayerNorm.apply(x, gamma, beta, eps)
+
+
+def linear(x, weight, bias=None, ln=None, act=ops.ACT_NONE, res=None, res_div=1, res_mod=None):
+    """ same contract as ops.linear; differentiable w.r.t. x, weight, bias, the LayerNorm parameters and res """
+    ln_params = ln[:2] if ln is not None else ()
+    if not _needs_grad(x, weight, bias, res, *ln_params):
+        d = lambda t: None if t is None else t.detach()
+        return ops.linear(x.detach(), d(weight), d(bias), ln=None if ln is None else (d(ln[0]), d(ln[1]), ln[2]),
+                          act=act, res=d(res), res_div=res_div, res_mod=res_mod)
+    h = x
+    if ln is not None:
+        h = _LayerNorm.apply(h, ln[0], ln[1], ln[2])
+    y = _Linear.apply(h, weight, bias)
+    if act != ops.ACT_NONE:
+        y = _Act.apply(y, act)
+    if res is not None:
+        N = y.shape[-1]
+        r2 = res.reshape(-1, N)
+        if res_div == 1 and (res_mod is None or res_mod == r2.shape[0]) and r2.shape[0] == y.numel() // N:
+            y = y + r2.view(y.shape)
+        else:
+            M = y.numel() // N
+            rows = (torch.arange(M, device=y.device) // res_div) % (res_mod or r2.shape[0])
+            y = y + r2[rows].view(y.shape)
+    return y
+
+
+def mha(qkv, n_seq, L, n_heads, head_dim, slots_per_frame=0, res=None):
+    if not _needs_grad(qkv, res):
+        return ops.mha(qkv.detach(), n_seq, L, n_heads, head_dim, slots_per_frame, res=None if res is None else res.detach())
+    out = _MHA.apply(qkv, n_seq, L, n_heads, head_dim, slots_per_frame)
+    if res is not None:
+        out = out + res.reshape(out.shape)
+    return out
+
+
+class _InvDynTail(torch.autograd.Function):
+    """ ps_invdyn_tail with gradients w.r.t. the mean / variance head outputs (and, for a trainable codebook, the
+    commitment-loss gradient w.r.t. the codewords). """
+
+    @staticmethod
+    def forward(ctx, mv, noise, codebook, per_slot):
+        mv, codebook_c = _c(mv), _c(codebook.detach())
+        out = ops.invdyn_tail(mv, noise, codebook_c, per_slot)
+        ctx.save_for_backward(mv, noise, out["z"], out["idx"], codebook_c)
+        ctx.per_slot = per_slot
+        ctx.mark_non_differentiable(out["idx"])
+        return out["action_dist"], out["z"], out["proto"], out["variability"], out["idx"], out["loss"], out["loss"].clone()
+
+    @staticmethod
+    def backward(ctx, g_dist, g_z, g_proto, g_var, _g_idx, g_quant, g_commit):
+        mv, noise, z, idx, codebook = ctx.saved_tensors
+        d_mv = ops.invdyn_tail_bwd(mv, noise, z, idx, codebook, g_dist, g_z, g_proto, g_var, g_quant, ctx.per_slot)
+        d_cb = None
+        if ctx.needs_input_grad[2] and g_commit is not None:
+            A = codebook.shape[1]
+            zq = codebook[idx.reshape(-1)]
+            contrib = (2.0 / A) * (zq - z.reshape(-1, A)) * g_commit.reshape(-1, 1)       # commit = mean_A (z_q - sg(z))^2
+            d_cb = torch.zeros_like(codebook).index_add_(0, idx.reshape(-1), contrib)
+        return d_mv, None, d_cb, None
+
+
+def invdyn_tail(mv, noise, codebook, per_slot):
+    """ dict like ops.invdyn_tail plus separate "quant" / "commit" per-vector losses; differentiable when needed """
+    if not _needs_grad(mv, codebook):
+        out = ops.invdyn_tail(mv.detach(), noise, codebook.detach(), per_slot)
+        out["quant"], out["commit"] = out["loss"], out["loss"].clone()
+        return out
+    dist, z, proto, var, idx, quant, commit = _InvDynTail.apply(mv, noise, codebook, per_slot)
+    return {"action_dist": dist, "z": z, "proto": proto, "variability": var, "idx": idx, "quant": quant, "commit": commit}

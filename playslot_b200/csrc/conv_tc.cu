@@ -63,6 +63,7 @@ __device__ __forceinline__ void split_store8(const float* v, uint16_t* hi, uint1
 struct ConvTcParams {
     const float* bias;
     const float* addend;     // mode 2: [H*W][64]
+    const uint16_t* mask_hi; // optional: hi plane of a padded split activation; outputs are zeroed where it is <= 0
     uint16_t* out_hi;        // mode 0
     uint16_t* out_lo;        // mode 0 (null in the single-product modes)
     float* out_f32;          // mode 1 (NCHW) / mode 2 (NHWC)
@@ -197,6 +198,19 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 if (p.relu) t = fmaxf(t, 0.f);
                 v[c] = interior ? t : 0.f;
             }
+            if (p.mask_hi && interior) {                    // ReLU data gradient: pass where the saved activation was positive
+                const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + ((size_t)img_base + pp) * C);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const uint4 m4 = __ldg(mk + g);
+                    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if ((mw[j] & 0x7FFFu) == 0u || (mw[j] & 0x8000u)) v[g * 8 + 2 * j] = 0.f;
+                        if ((mw[j] & 0x7FFF0000u) == 0u || (mw[j] & 0x80000000u)) v[g * 8 + 2 * j + 1] = 0.f;
+                    }
+                }
+            }
             if (p.out_mode == 0) {
                 if (row_ok) {
                     const size_t o = ((size_t)img_base + pp) * C;
@@ -251,9 +265,9 @@ extern "C" long long ps_conv_tc_plane_elems(int n_img, int H, int W) {
     return (long long)n_img * (H + 4) * (W + 4) * C;
 }
 
-extern "C" int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* bias, float w_scale, void* act_out,
-                             float* out_f32, const float* addend, int n_img, int H, int W, int relu, int out_mode,
-                             int precision, void* stream) {
+static int conv5x5_tc_run(const void* act_in, const void* w_tc, const float* bias, float w_scale, void* act_out,
+                          float* out_f32, const float* addend, const void* mask_act, int n_img, int H, int W, int relu,
+                          int out_mode, int precision, void* stream) {
     PS_REQUIRE(act_in && w_tc, "ps_conv5x5_tc: null pointer");
     PS_REQUIRE(precision >= 1 && precision <= 3, "ps_conv5x5_tc: precision must be 1 (bf16), 2 (fp16) or 3 (fp16x3)");
     PS_REQUIRE(w_scale > 0.f, "ps_conv5x5_tc: w_scale must be positive");
@@ -278,6 +292,7 @@ extern "C" int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* 
     PS_REQUIRE(stages_for(tiles) >= 2, "ps_conv5x5_tc: image width %d does not fit the shared-memory staging", W);
     ConvTcParams p;
     p.bias = bias; p.addend = addend; p.out_f32 = out_f32;
+    p.mask_hi = reinterpret_cast<const uint16_t*>(mask_act);
     p.out_hi = reinterpret_cast<uint16_t*>(act_out);
     p.out_lo = (act_out && precision == 3) ? p.out_hi + P * C : nullptr;
     p.bf16 = precision == 1 ? 1 : 0;
@@ -298,6 +313,23 @@ extern "C" int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     if (tiles == 2) return nsplit == 2 ? launch_conv_tc<2, 2>(mA_hi, mA_lo, mW, p, st) : launch_conv_tc<2, 1>(mA_hi, mA_lo, mW, p, st);
     return nsplit == 2 ? launch_conv_tc<1, 2>(mA_hi, mA_lo, mW, p, st) : launch_conv_tc<1, 1>(mA_hi, mA_lo, mW, p, st);
+}
+
+extern "C" int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* bias, float w_scale, void* act_out,
+                             float* out_f32, const float* addend, int n_img, int H, int W, int relu, int out_mode,
+                             int precision, void* stream) {
+    return conv5x5_tc_run(act_in, w_tc, bias, w_scale, act_out, out_f32, addend, nullptr, n_img, H, W, relu, out_mode, precision, stream);
+}
+
+// Data gradient of ConvBlock(64, 64, 5) = Conv2d + ReLU w.r.t. its input, given the gradient w.r.t. the conv output
+// (already multiplied by relu' of THIS block by the caller chain) : conv with the flipped / transposed weights,
+// then masked by relu' of the PREVIOUS block (mask_act = that block's saved output = this block's input).
+extern "C" int ps_conv5x5_tc_dgrad(const void* g_in, const void* w_tc_flipped, float w_scale, const void* mask_act,
+                                   void* act_out, float* out_tokens, int n_img, int H, int W, int out_mode, int precision,
+                                   void* stream) {
+    PS_REQUIRE(out_mode == 0 || out_mode == 2, "ps_conv5x5_tc_dgrad: out_mode must be 0 (padded split) or 2 (fp32 NHWC tokens)");
+    PS_REQUIRE(precision == 2 || precision == 3, "ps_conv5x5_tc_dgrad: precision must be 2 (fp16) or 3 (fp16x3)");
+    return conv5x5_tc_run(g_in, w_tc_flipped, nullptr, w_scale, act_out, out_tokens, nullptr, mask_act, n_img, H, W, 0, out_mode, precision, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@
 #include "tc_common.cuh"
 #include "../../include/playslot_b200.h"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -39,6 +40,7 @@ struct SaTcParams {
     float* masks;         // [B][S][N] or null
     int B, N, S, CH, tpc;
     float ln_eps, attn_eps;
+    int debug;            // timing experiments only (results invalid when non-zero)
 };
 
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
@@ -56,7 +58,7 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 }
 
 template <int SPAD>
-__global__ void __launch_bounds__(288, 3) sa_main_tc_kernel(const SaTcParams p) {
+__global__ void __launch_bounds__(288, 2) sa_main_tc_kernel(const SaTcParams p) {
     constexpr int NB = SPAD / 8;                     // 8-slot blocks per part
     constexpr int N1 = 2 * SPAD;                     // operand rows / accumulator columns: [hi | lo]
     constexpr int AOP_HALF = N1 * 128;               // folded queries, bytes per 64-feature half
@@ -120,62 +122,71 @@ __global__ void __launch_bounds__(288, 3) sa_main_tc_kernel(const SaTcParams p) 
 #pragma unroll
         for (int s = 0; s < SPAD; ++s) rs[s] = 0.f;
 
-        for (int t = 0; t < ntiles; ++t) {
-            // ---------------------------------------------------------------- load, normalise, split, store
-#pragma unroll 1
-            for (int gp = 0; gp < 2; ++gp) {
-                float4 v[2][4];
+        // Software pipeline over "group pairs" (2 x 4 tokens per warp): the loads of the next pair -- across tile
+        // boundaries too -- are in flight while the current pair is normalised, split and stored, and (warps 0-3)
+        // while the softmax of the finished tile runs.
+        auto load_pair = [&](float4 (&v)[2][4], int t, int gp) {
 #pragma unroll
-                for (int g2 = 0; g2 < 2; ++g2) {
-                    const int r = warp * 16 + (gp * 2 + g2) * 4 + q;
-                    const int tok = t * TILE + r;
-                    const float* src = xb + (size_t)tok * SA_D + 8 * j;
-                    if (tok < ntok) {
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            v[g2][2 * i] = __ldg(reinterpret_cast<const float4*>(src + 64 * i));
-                            v[g2][2 * i + 1] = __ldg(reinterpret_cast<const float4*>(src + 64 * i + 4));
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[g2][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                if (gp == 0 && t > 0) tc::mbar_wait(&bar_v, (t - 1) & 1);      // previous tile fully consumed
-#pragma unroll
-                for (int g2 = 0; g2 < 2; ++g2) {
-                    const int r = warp * 16 + (gp * 2 + g2) * 4 + q;
-                    float f[16];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { f[4 * i] = v[g2][i].x; f[4 * i + 1] = v[g2][i].y; f[4 * i + 2] = v[g2][i].z; f[4 * i + 3] = v[g2][i].w; }
-                    float s = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) s += f[i];
-                    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    const float mean = s * (1.0f / SA_D);
-                    float ss = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { f[i] -= mean; ss = fmaf(f[i], f[i], ss); }
-                    ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-                    const float rstd = 1.0f / sqrtf(ss * (1.0f / SA_D) + p.ln_eps);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] *= rstd;
-                    const int off = r * 128 + ((j ^ (r & 7)) << 4);
+            for (int g2 = 0; g2 < 2; ++g2) {
+                const int r = warp * 16 + (gp * 2 + g2) * 4 + q;
+                const int tok = t * TILE + r;
+                const float* src = xb + (size_t)tok * SA_D + 8 * j;
+                if (t < ntiles && tok < ntok) {
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        uint4 hi, lo;
-                        split8(f + 8 * i, hi, lo);
-                        *reinterpret_cast<uint4*>(c_hi + i * C_HALF + off) = hi;
-                        *reinterpret_cast<uint4*>(c_lo + i * C_HALF + off) = lo;
+                        v[g2][2 * i] = __ldg(reinterpret_cast<const float4*>(src + 64 * i));
+                        v[g2][2 * i + 1] = __ldg(reinterpret_cast<const float4*>(src + 64 * i + 4));
                     }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[g2][i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+        };
+        auto store_pair = [&](const float4 (&v)[2][4], int gp) {
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+                const int r = warp * 16 + (gp * 2 + g2) * 4 + q;
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { f[4 * i] = v[g2][i].x; f[4 * i + 1] = v[g2][i].y; f[4 * i + 2] = v[g2][i].z; f[4 * i + 3] = v[g2][i].w; }
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) s += f[i];
+                s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+                const float mean = s * (1.0f / SA_D);
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { f[i] -= mean; ss = fmaf(f[i], f[i], ss); }
+                ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+                const float rstd = 1.0f / sqrtf(ss * (1.0f / SA_D) + p.ln_eps);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] *= rstd;
+                const int off = r * 128 + ((j ^ (r & 7)) << 4);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    uint4 hi, lo;
+                    split8(f + 8 * i, hi, lo);
+                    *reinterpret_cast<uint4*>(c_hi + i * C_HALF + off) = hi;
+                    *reinterpret_cast<uint4*>(c_lo + i * C_HALF + off) = lo;
+                }
+            }
+        };
+        float4 va[2][4], vb[2][4];
+        load_pair(va, 0, 0);
+        for (int t = 0; t < ntiles; ++t) {
+            // ---------------------------------------------------------------- load, normalise, split, store
+            load_pair(vb, t, 1);
+            if (t > 0 && !p.debug) tc::mbar_wait(&bar_v, (t - 1) & 1);         // previous tile fully consumed
+            store_pair(va, 0);
+            load_pair(va, t + 1, 0);                                           // zeros past the last tile
+            store_pair(vb, 1);
             tc::fence_async_proxy();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar_cfull);
 
             // ---------------------------------------------------------------- softmax over slots (warps 0-3)
-            if (warp < 4) {
+            if (warp < 4 && !p.debug) {
                 tc::mbar_wait(&bar_l, t & 1);
                 __syncwarp();
                 tc::tc_fence_after();
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(288, 3) sa_main_tc_kernel(const SaTcParams p) 
         }
 
         // -------------------------------------------------------------------- epilogue: partial sums of this CTA
-        if (warp < 4) {
+        if (warp < 4 && !p.debug) {
             tc::mbar_wait(&bar_v, (ntiles - 1) & 1);
             __syncwarp();
             tc::tc_fence_after();
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(288, 3) sa_main_tc_kernel(const SaTcParams p) 
         }
     } else {
         // ------------------------------------------------------------------------ MMA issuer (warp 8)
-        if (tc::elect_one()) {
+        if (!p.debug && tc::elect_one()) {
             const uint32_t idesc1 = tc::umma_idesc_f16_major(128, N1, 0, 0);
             const uint32_t idesc2 = tc::umma_idesc_f16_major(128, N1, 1, 1);
             const uint32_t chi = tc::smem_u32(c_hi), clo = tc::smem_u32(c_lo);
@@ -318,6 +329,7 @@ extern "C" int ps_sa_main_tc(const float* x, const float* A, const float* a0, fl
     p.x = x; p.A = A; p.a0 = a0; p.partial = partial; p.masks = masks;
     p.B = B; p.N = N; p.S = S; p.CH = n_chunks; p.tpc = (N + n_chunks - 1) / n_chunks;
     p.ln_eps = ln_eps; p.attn_eps = attn_eps;
+    { const char* e = getenv("PLAYSLOT_SA_DEBUG"); p.debug = e ? atoi(e) : 0; }
     PS_REQUIRE((size_t)(n_chunks - 1) * p.tpc < (size_t)N, "ps_sa_main_tc: n_chunks=%d leaves empty chunks for N=%d", n_chunks, N);
     cudaStream_t st = (cudaStream_t)stream;
     if (S <= 8) return launch_sa_main_tc<8>(p, st);

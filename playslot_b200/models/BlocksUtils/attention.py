@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from ... import autograd as AG
 from .._common import DerivedWeights, require_cuda, no_grad_only, f32c
 from .model_blocks import MLP
 
@@ -221,6 +222,8 @@ class MetaAttention(nn.Module):
     # -- kernel path ---------------------------------------------------------------------------------------
     def qkv_weight(self):
         srcs = [self.q.weight, self.k.weight, self.v.weight]
+        if torch.is_grad_enabled() and any(w.requires_grad for w in srcs):
+            return torch.cat(srcs, dim=0)              # training: keep the autograd link to q / k / v
         return self._cache.get(srcs, lambda: torch.cat([w.detach() for w in srcs], dim=0).contiguous())
 
     def has_out_proj(self):
@@ -237,12 +240,12 @@ class MetaAttention(nn.Module):
     def run(self, x, ln=None, res=None, slots_per_frame=0):
         """ x (B, L, E) contiguous -> attention output (B, L, E) (+ res); `ln` fuses the pre-LayerNorm """
         B, L, E = x.shape
-        qkv = ops.linear(x, self.qkv_weight(), None, ln=ln)
+        qkv = AG.linear(x, self.qkv_weight(), None, ln=ln)
         if self.has_out_proj():
-            att = ops.mha(qkv, B, L, self.num_heads, self.head_dim, slots_per_frame)
+            att = AG.mha(qkv, B, L, self.num_heads, self.head_dim, slots_per_frame)
             lin = self.out_proj[0]
-            return ops.linear(att.view(B, L, -1), lin.weight, lin.bias, res=res)
-        att = ops.mha(qkv, B, L, self.num_heads, self.head_dim, slots_per_frame, res=res)
+            return AG.linear(att.view(B, L, -1), lin.weight, lin.bias, res=res)
+        att = AG.mha(qkv, B, L, self.num_heads, self.head_dim, slots_per_frame, res=res)
         return att.view(B, L, E)
 
 
@@ -255,7 +258,6 @@ class MultiHeadSelfAttention(MetaAttention):
 
     def forward(self, x, mask=None, **kwargs):
         require_cuda(x, "MultiHeadSelfAttention")
-        no_grad_only("MultiHeadSelfAttention", x, self.q.weight)
         x = f32c(x)
         return self.run(x, slots_per_frame=self.spf_of(mask, x.shape[1]))
 
@@ -315,7 +317,6 @@ class TransformerEncoderBlock(TransformerBlock):
     def forward(self, inputs, mask=None):
         assert inputs.ndim == 3
         require_cuda(inputs, "TransformerEncoderBlock")
-        no_grad_only("TransformerEncoderBlock", inputs, self.attn.q.weight)
         x = f32c(inputs)
         return self.run(x, self.attn.spf_of(mask, x.shape[1]))
 
@@ -344,7 +345,6 @@ class TransformerDecoder(TransformerBlock):
         if self.use_cross_attn:
             raise NotImplementedError("TransformerDecoder with cross-attention has no kernel (unused by PlaySlot configs)")
         require_cuda(queries, "TransformerDecoder")
-        no_grad_only("TransformerDecoder", queries, self.attn.q.weight)
         x = f32c(queries)
         spf = slots_per_frame if slots_per_frame is not None else self.attn.spf_of(self_attn_mask, x.shape[1])
         return self.run(x, spf)

@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from ... import autograd as AG
 from .._common import DerivedWeights, require_cuda, no_grad_only, f32c
 from .model_utils import build_grid
 
@@ -195,10 +196,9 @@ class MLP(nn.Module):
 
     def run(self, x, ln=None, res=None):
         """ kernel path: optional fused pre-LayerNorm and residual """
-        h = ops.linear(x, self.mlp[0].weight, self.mlp[0].bias, ln=ln, act=self._act)
-        return ops.linear(h, self.mlp[2].weight, self.mlp[2].bias, res=res)
+        h = AG.linear(x, self.mlp[0].weight, self.mlp[0].bias, ln=ln, act=self._act)
+        return AG.linear(h, self.mlp[2].weight, self.mlp[2].bias, res=res)
 
     def forward(self, x):
         require_cuda(x, "MLP")
-        no_grad_only("MLP", x, self.mlp[0].weight)
         return self.run(f32c(x))

@@ -130,6 +130,7 @@ class EmaVectorQuantizer(nn.Module):
         self.ema_alpha = ema_alpha
         self.epsilon = 1e-6
         self.update = True
+        self.sync_stats = True        # all-reduce the EMA statistics when torch.distributed is initialised
         self.vq = VectorQuantizer(num_embs=num_embs, emb_dim=emb_dim, nbooks=nbooks, balance=balance).requires_grad_(False)
         self.register_buffer('ema_count', torch.zeros(self.num_embs))
         self.register_buffer('ema_weight', torch.empty((self.num_embs, self.emb_dim)).uniform_(-1 / num_embs, 1 / num_embs))
@@ -140,9 +141,17 @@ class EmaVectorQuantizer(nn.Module):
         B = z.shape[0]
         zf = z.flatten(0, -2)
         enc = F.one_hot(idx.reshape(-1), num_classes=self.num_embs).to(zf.dtype)
-        cnt = self.ema_alpha * self.ema_count + (1 - self.ema_alpha) * enc.sum(0)
+        enc_sum, dw = enc.sum(0), enc.t() @ zf
+        if self.sync_stats and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            # batch-sharded training: the statistics of the GLOBAL batch make every rank's codebook identical to the
+            # single-GPU run on the concatenated batch (one all-reduce of K + K*A + 1 floats)
+            packed = torch.cat([enc_sum, dw.flatten(), torch.tensor([float(B)], device=zf.device, dtype=zf.dtype)])
+            torch.distributed.all_reduce(packed)
+            enc_sum, dw, B = packed[:self.num_embs], packed[self.num_embs:-1].view_as(dw), float(packed[-1])
+        cnt = self.ema_alpha * self.ema_count + (1 - self.ema_alpha) * enc_sum
         self.ema_count = (cnt + self.epsilon) / (B + self.num_embs * self.epsilon) * B
-        self.ema_weight = self.ema_alpha * self.ema_weight + (1 - self.ema_alpha) * (enc.t() @ zf)
+        self.ema_weight = self.ema_alpha * self.ema_weight + (1 - self.ema_alpha) * dw
         self.vq.embeddings['0'].weight.data = self.ema_weight / (self.ema_count.unsqueeze(1) + 1e-8)
 
     def forward(self, z):

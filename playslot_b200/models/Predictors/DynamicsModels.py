@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from ... import autograd as AG
 from .._common import DerivedWeights, require_cuda, no_grad_only, f32c
 from ..BlocksUtils.attention import TransformerDecoder
 from ..BlocksUtils.model_blocks import SlotPositionalEncoding
@@ -63,10 +64,10 @@ class BaseSlotDynamicsModel(nn.Module):
         (`_embed`) does embedding + conditioning (+ time encoding) in one GEMM instead. """
         assert action_protos is not None, "'action_protos' not provided..."
         if self.condition_mode == "sum":
-            out = tokens + ops.linear(f32c(action_protos), self.action_emb.weight, self.action_emb.bias)
+            out = tokens + AG.linear(f32c(action_protos), self.action_emb.weight, self.action_emb.bias)
             if self.use_variability:
                 assert action_vars is not None, "'action_vars' not provided..."
-                out = out + ops.linear(f32c(action_vars), self.variability_emb.weight, self.variability_emb.bias)
+                out = out + AG.linear(f32c(action_vars), self.variability_emb.weight, self.variability_emb.bias)
             return out
         parts = [tokens, action_protos] + ([action_vars] if self.use_variability else [])
         return torch.cat(parts, dim=-1)
@@ -89,13 +90,18 @@ class BaseSlotDynamicsModel(nn.Module):
                     ws.append(self.variability_emb.weight.detach())
                     b = b + self.variability_emb.bias.detach()
                 return torch.cat(ws, dim=1).contiguous(), b.contiguous()
-            w, b = self._emb_cache.get(srcs, build)
+            if torch.is_grad_enabled() and any(t.requires_grad for t in srcs):
+                # training: concatenate the live parameters so that autograd reaches the three embeddings
+                w = torch.cat([self.tok_emb.weight, self.action_emb.weight] + ([self.variability_emb.weight] if use_var else []), dim=1)
+                b = self.tok_emb.bias + self.action_emb.bias + (self.variability_emb.bias if use_var else 0)
+            else:
+                w, b = self._emb_cache.get(srcs, build)
             parts = [slots, action_protos] + ([action_vars] if use_var else [])
             x = torch.cat([p.reshape(M, -1) for p in parts], dim=1)              # (M, D + A [+ A])
             if pe_table is not None:
-                return ops.linear(x, w, b, res=pe_table, res_div=S, res_mod=n_frames)
-            return ops.linear(x, w, b)
-        tok = ops.linear(slots.reshape(M, -1), self.tok_emb.weight, self.tok_emb.bias)
+                return AG.linear(x, w, b, res=pe_table, res_div=S, res_mod=n_frames)
+            return AG.linear(x, w, b)
+        tok = AG.linear(slots.reshape(M, -1), self.tok_emb.weight, self.tok_emb.bias)
         parts = [tok, action_protos.reshape(M, -1)] + ([action_vars.reshape(M, -1)] if use_var else [])
         x = torch.cat(parts, dim=1)
         if pe_table is not None:
@@ -104,7 +110,7 @@ class BaseSlotDynamicsModel(nn.Module):
 
     def _head(self, tokens):
         ln, fc = self.regression_head[0], self.regression_head[1]
-        return ops.linear(tokens, fc.weight, fc.bias, ln=(ln.weight, ln.bias, ln.eps))
+        return AG.linear(tokens, fc.weight, fc.bias, ln=(ln.weight, ln.bias, ln.eps))
 
     def _check_inputs(self, slots, action_protos, action_vars):
         if action_protos is None:
@@ -121,7 +127,6 @@ class BaseSlotDynamicsModel(nn.Module):
         if self.use_variability and action_vars is None:
             raise ValueError(f"If {self.use_variability = }, latents must be provided...")
         require_cuda(slots, type(self).__name__)
-        no_grad_only(type(self).__name__, slots, action_protos, self.tok_emb.weight)
         return f32c(slots), f32c(action_protos), (f32c(action_vars) if action_vars is not None else None)
 
 

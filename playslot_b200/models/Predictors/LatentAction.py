@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from ... import autograd as AG
 from .._common import DerivedWeights, require_cuda, no_grad_only, f32c
 from ..BlocksUtils.attention import TransformerEncoderBlock
 from ..BlocksUtils.quantization import VectorQuantizer, EmaVectorQuantizer
@@ -74,6 +75,10 @@ class BaseSlotLatentAction(nn.Module):
     def _heads(self, tokens):
         """ one GEMM for both heads: (..., E) -> (..., 2A) = [mean_fc | variance_fc] """
         srcs = [self.mean_fc.weight, self.mean_fc.bias, self.variance_fc.weight, self.variance_fc.bias]
+        if torch.is_grad_enabled() and (tokens.requires_grad or any(t.requires_grad for t in srcs)):
+            w = torch.cat([self.mean_fc.weight, self.variance_fc.weight], 0)         # training: live parameters
+            b = torch.cat([self.mean_fc.bias, self.variance_fc.bias], 0)
+            return AG.linear(tokens, w, b)
         w, b = self._head_cache.get(srcs, lambda: (
             torch.cat([self.mean_fc.weight.detach(), self.variance_fc.weight.detach()], 0).contiguous(),
             torch.cat([self.mean_fc.bias.detach(), self.variance_fc.bias.detach()], 0).contiguous()))
@@ -84,15 +89,22 @@ class BaseSlotLatentAction(nn.Module):
         A = self.action_dim
         shape = (B, T - 1, A) if not per_slot else (B, T - 1, R, A)
         noise = torch.randn(shape, dtype=torch.float32).to(mv.device)       # same RNG call as the reference
-        out = ops.invdyn_tail(mv, f32c(noise.view(B, T - 1, R, A)), self._codebook(), per_slot)
+        codebook = self.quantizer.get_codewords()
+        out = AG.invdyn_tail(mv, f32c(noise.view(B, T - 1, R, A)), codebook, per_slot)
         idx = out["idx"]
+        variability = out["variability"]
         if self.training:
-            self._train_side_effects(out["z"], idx)
+            self._train_side_effects(out["z"].detach(), idx)
+            if self.use_ema_vq and self.quantizer.update and not per_slot:
+                # the reference looks the codeword up a second time for the variability (quantization.py:365-368), i.e.
+                # AFTER the EMA update of the codebook in train mode; z keeps its gradient, the codeword does not
+                _, zq2, _, _ = ops.vq_lookup(f32c(out["z"].detach()), self._codebook())
+                variability = out["z"] - zq2
         if per_slot:
             res = {
                 "action_dist": out["action_dist"],                            # (B, T-1, 2, S, A)
                 "sampled_latent_action": out["z"],
-                "action_variability": out["variability"],
+                "action_variability": variability,
                 "action_proto": out["proto"],
                 "action_idxs": idx.view(B, T - 1, R, 1),
             }
@@ -100,12 +112,11 @@ class BaseSlotLatentAction(nn.Module):
             res = {
                 "action_dist": out["action_dist"].view(B, T - 1, 2, A),
                 "sampled_latent_action": out["z"].view(B, T - 1, A),
-                "action_variability": out["variability"].view(B, T - 1, A),
+                "action_variability": variability.view(B, T - 1, A),
                 "action_proto": out["proto"].view(B, T - 1, A),
                 "action_idxs": idx.view(B, T - 1, 1),
             }
-        loss = out["loss"].mean()
-        res["vq_losses"] = {"quant_loss": loss, "commit_loss": loss.clone()}
+        res["vq_losses"] = {"quant_loss": out["quant"].mean(), "commit_loss": out["commit"].mean()}
         return res
 
     def _train_side_effects(self, z, idx):
@@ -139,13 +150,16 @@ class VQSingleSlotLatentAction(BaseSlotLatentAction):
         if len(slots.shape) != 4:
             raise ValueError(f"{slots.shape = } must be (B, N, num_slots, slot_dim)")
         require_cuda(slots, "VQSingleSlotLatentAction")
-        no_grad_only("VQSingleSlotLatentAction", slots, self.mean_fc.weight)
         slots = f32c(slots)
         B, T, S, _ = slots.shape
         ln, fc = self.slot_encoder[0], self.slot_encoder[1]
-        tokens = torch.empty(B * T, S + 1, self.emb_dim, device=slots.device, dtype=torch.float32)
-        tokens[:, 0] = self.act_token.detach().view(1, -1)
-        tokens[:, 1:] = ops.linear(slots.view(B * T, S, -1), fc.weight, fc.bias, ln=(ln.weight, ln.bias, ln.eps))
+        emb = AG.linear(slots.view(B * T, S, -1), fc.weight, fc.bias, ln=(ln.weight, ln.bias, ln.eps))
+        if torch.is_grad_enabled() and (emb.requires_grad or self.act_token.requires_grad):
+            tokens = torch.cat([self.act_token.view(1, 1, -1).expand(B * T, 1, -1), emb], dim=1).contiguous()
+        else:
+            tokens = torch.empty(B * T, S + 1, self.emb_dim, device=slots.device, dtype=torch.float32)
+            tokens[:, 0] = self.act_token.detach().view(1, -1)
+            tokens[:, 1:] = emb
         for blk in self.transformer:
             tokens = blk.run(tokens)
         act = tokens[:, 0].contiguous()                                       # (B*T, E)
@@ -174,11 +188,10 @@ class VQSimpleMLPSlotLatentAction(BaseSlotLatentAction):
         action_idxs (B,T-1,S,1), vq_losses) """
         assert len(slots.shape) == 4, f"{slots.shape = } must be (B, N, num_slots, slot_dim)"
         require_cuda(slots, "VQSimpleMLPSlotLatentAction")
-        no_grad_only("VQSimpleMLPSlotLatentAction", slots, self.mean_fc.weight)
         slots = f32c(slots)
         B, T, S, _ = slots.shape
         fc1, ln, fc2 = self.slot_encoder[0], self.slot_encoder[2], self.slot_encoder[3]
-        h = ops.linear(slots, fc1.weight, fc1.bias, act=ops.ACT_RELU)
-        e = ops.linear(h, fc2.weight, fc2.bias, ln=(ln.weight, ln.bias, ln.eps))
+        h = AG.linear(slots, fc1.weight, fc1.bias, act=ops.ACT_RELU)
+        e = AG.linear(h, fc2.weight, fc2.bias, ln=(ln.weight, ln.bias, ln.eps))
         mv = self._heads(e).view(B, T, S, -1)
         return self._tail(mv, B, T, S, per_slot=True)

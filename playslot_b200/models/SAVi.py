@@ -28,6 +28,23 @@ from .EncodersDecoders.encoders import get_encoder
 from .EncodersDecoders.decoders import get_decoder
 
 
+class _DecodeFn(torch.autograd.Function):
+    """ SAVi.decode with a data gradient w.r.t. the slots (the decoder is frozen in 04_train_PlaySlot.py:87-90) """
+
+    @staticmethod
+    def forward(ctx, slots, savi):
+        recon, recons, masks, saved = savi._decode_impl(slots.detach(), keep=True)
+        ctx.savi, ctx.saved_acts = savi, saved
+        ctx.save_for_backward(recons, masks)
+        ctx.set_materialize_grads(False)
+        return recon, recons, masks
+
+    @staticmethod
+    def backward(ctx, g_recon, g_recons, g_masks):
+        recons, masks = ctx.saved_tensors
+        return ctx.savi._decode_backward(ctx.saved_acts, recons, masks, g_recon, g_recons, g_masks), None
+
+
 class SAVi(nn.Module):
     """
     Args mirror the reference (SAVi.py:29-56): num_slots, slot_dim, num_iterations, num_iterations_first,
@@ -249,11 +266,19 @@ class SAVi(nn.Module):
     def decode(self, slots):
         """
         slots (M, S, D) -> recon_combined (M, C, H, W), (recons (M, S, C, H, W) un-masked, masks (M, S, 1, H, W))
-        (SAVi.py:220-234).
+        (SAVi.py:220-234).  Differentiable w.r.t. `slots` (data gradient only: the training script keeps SAVi frozen).
         """
         require_cuda(slots, "SAVi.decode")
-        no_grad_only("SAVi.decode", slots, self.decoder.final_conv().weight)
-        slots = f32c(slots)
+        if torch.is_grad_enabled() and slots.requires_grad:
+            no_grad_only("SAVi.decode (decoder weight gradients; SAVi training is not part of this path)",
+                         self.decoder.final_conv().weight, self.decoder_pos_embedding.projection.weight)
+            recon, recons, masks = _DecodeFn.apply(f32c(slots), self)
+            return recon, (recons, masks)
+        recon, recons, masks, _ = self._decode_impl(f32c(slots.detach()), keep=False)
+        return recon, (recons, masks)
+
+    def _decode_impl(self, slots, keep):
+        """ forward kernels; with keep=True the per-layer activations needed by the data gradient are returned """
         M, S, D = slots.shape
         H, W = self.decoder_resolution
         dec = self.decoder
@@ -265,9 +290,12 @@ class SAVi(nn.Module):
         C1 = blocks[0].conv.out_channels
         use_tc = C1 == 64 and self._tc_applicable(blocks, skip_first=True)
         prec = ops.TC_PRECISION.get(self.conv_mode, 0)
+        if keep and not (use_tc and prec in (2, 3) and len(blocks) == 4 and all(b._relu for b in blocks)):
+            raise NotImplementedError("the decoder data gradient is implemented for the tensor-core path (conv_mode fp16x3 / fp16) "
+                                      "of the 4-block 64-channel decoder of the shipped configs")
         final = dec.final_conv()
         wfin = self._final_packed(final)
-        recon_l, recons_l, masks_l = [], [], []
+        recon_l, recons_l, masks_l, saved = [], [], [], []
         step = max(1, self.DECODE_CHUNK_IMAGES // S)
         for m0 in range(0, M, step):
             m1 = min(M, m0 + step)
@@ -275,23 +303,66 @@ class SAVi(nn.Module):
             G = ops.linear(sl, wsum)                                           # (n_img, ncls^2 * C1)
             n_img = (m1 - m0) * S
             if use_tc:
-                a = self._tc_workspace("dec_a", n_img, H, W, slots.device)
-                b = self._tc_workspace("dec_b", n_img, H, W, slots.device)
-                ops.dec_expand_split(G, P_hwc, a, n_img, H, W, k, prec)
-                for blk in blocks[1:-1]:
-                    ops.conv5x5_tc(a, self._tc_weight(blk), blk.conv.bias, n_img, H, W, blk._relu, prec, act_out=b)
-                    a, b = b, a
+                if keep:
+                    acts = [ops.conv_tc_workspace(n_img, H, W, slots.device) for _ in range(3)]      # h1, h2, h3
+                else:
+                    a = self._tc_workspace("dec_a", n_img, H, W, slots.device)
+                    b = self._tc_workspace("dec_b", n_img, H, W, slots.device)
+                    acts = [a if i % 2 == 0 else b for i in range(len(blocks) - 1)]
+                ops.dec_expand_split(G, P_hwc, acts[0], n_img, H, W, k, prec)
+                for i, blk in enumerate(blocks[1:-1]):
+                    ops.conv5x5_tc(acts[i], self._tc_weight(blk), blk.conv.bias, n_img, H, W, blk._relu, prec, act_out=acts[i + 1])
                 h = torch.empty(n_img, 64, H, W, device=slots.device, dtype=torch.float32)
-                ops.conv5x5_tc(a, self._tc_weight(blocks[-1]), blocks[-1].conv.bias, n_img, H, W, blocks[-1]._relu, prec, out_nchw=h)
+                ops.conv5x5_tc(acts[len(blocks) - 2], self._tc_weight(blocks[-1]), blocks[-1].conv.bias, n_img, H, W, blocks[-1]._relu, prec, out_nchw=h)
             else:
                 h = ops.dec_expand(G, P, n_img, C1, H, W, k)
                 for blk in blocks[1:]:
                     h = blk.run(h)
             r, rs, ms = ops.dec_composite(h, wfin, final.bias, m1 - m0, S)
             recon_l.append(r); recons_l.append(rs); masks_l.append(ms)
+            if keep:
+                saved.append((m0, m1, acts, h))
         if len(recon_l) == 1:
-            return recon_l[0], (recons_l[0], masks_l[0])
-        return torch.cat(recon_l), (torch.cat(recons_l), torch.cat(masks_l))
+            return recon_l[0], recons_l[0], masks_l[0], saved
+        return torch.cat(recon_l), torch.cat(recons_l), torch.cat(masks_l), saved
+
+    def _tc_weight_flipped(self, block):
+        """ packed weights of the data gradient: W'[ci][co][ky][kx] = W[co][ci][K-1-ky][K-1-kx] """
+        prec = ops.TC_PRECISION[self.conv_mode]
+        cache = self._tc_w.setdefault((id(block), prec, "flip"), DerivedWeights())
+        w = block.conv.weight
+        return cache.get([w], lambda: ops.pack_conv_weight_tc(w.detach().flip(2, 3).transpose(0, 1).contiguous(), prec))
+
+    def _decode_backward(self, saved, recons, masks, g_recon, g_recons, g_masks):
+        """ d loss / d slots through compositing, the 3x3 and the three 5x5 convolutions and the collapsed first one """
+        M, S = recons.shape[:2]
+        H, W = self.decoder_resolution
+        blocks = self.decoder.conv_blocks()
+        wsum, _, k, _ = self._decoder_constants()
+        if not hasattr(self, "_wsum_t_cache"):
+            self._wsum_t_cache = DerivedWeights()
+        wsum_t = self._wsum_t_cache.get([wsum], lambda: wsum.t().contiguous())            # (D, ncls^2 * C1)
+        wfin = self._final_packed(self.decoder.final_conv())
+        prec = ops.TC_PRECISION[self.conv_mode]
+        cg = lambda g, m0, m1: None if g is None else f32c(g[m0:m1])
+        out = torch.empty(M, S, self.slot_dim, device=recons.device, dtype=torch.float32)
+        for m0, m1, acts, h in saved:
+            n_img = (m1 - m0) * S
+            g_o = ops.dec_composite_bwd(f32c(recons[m0:m1]), f32c(masks[m0:m1]), cg(g_recon, m0, m1), cg(g_recons, m0, m1), cg(g_masks, m0, m1))
+            ga = self._tc_workspace("dec_ga", n_img, H, W, recons.device)
+            gb = self._tc_workspace("dec_gb", n_img, H, W, recons.device)
+            # power-of-two gradient scale computed on the device (no host sync): MSE-mean gradients are ~1e-6 per pixel,
+            # far below fp16's normal range; the convolutions are linear, so the scale is undone exactly at the end
+            amax = g_o.abs().max().clamp_min(1e-30)
+            g_scale = torch.exp2(-torch.floor(torch.log2(amax))).reshape(1)
+            ops.dec_final_dgrad(g_o, wfin, h, ga, prec, g_scale)                                   # through conv3x3 and relu(h4)
+            ops.conv5x5_tc_dgrad(ga, self._tc_weight_flipped(blocks[3]), acts[2], n_img, H, W, prec, act_out=gb)
+            ops.conv5x5_tc_dgrad(gb, self._tc_weight_flipped(blocks[2]), acts[1], n_img, H, W, prec, act_out=ga)
+            tokens = torch.empty(n_img, H * W, 64, device=recons.device, dtype=torch.float32)
+            ops.conv5x5_tc_dgrad(ga, self._tc_weight_flipped(blocks[1]), acts[0], n_img, H, W, prec, out_tokens=tokens)
+            dG = ops.dec_expand_bwd(tokens, n_img, H, W, k, g_scale)
+            out[m0:m1] = ops.linear(dG, wsum_t, mode="fp32").view(m1 - m0, S, self.slot_dim)
+        return out
 
     def _final_packed(self, conv):
         if not hasattr(self, "_fin_cache"):

@@ -106,11 +106,13 @@ def reset_launch_count():
 
 # ------------------------------------------------------------------------------------------------ dense
 
-def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res_mod=None, out=None):
+def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res_mod=None, out=None, mode=None):
     """
     y = act(LN(x) @ weight.T + bias) + res_rows.   x: (..., K) contiguous; weight (N, K).
     ln = (gamma, beta, eps) fuses a LayerNorm over K in front.  `res` is a 2-D (R, N) tensor; output
     row m receives res[(m // res_div) % res_mod] (defaults: plain residual of the same shape).
+    `mode` overrides the global linear mode for this call (the training path passes "fp32": its weights change
+    every optimiser step, so a packed tensor-core copy would be rebuilt per call).
     """
     lib = _lib.load()
     _req(x, "x"); _req(weight, "weight")
@@ -137,8 +139,9 @@ def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res
         ldres = N
         if res_mod is None:
             res_mod = res.shape[0]
-    if _LINEAR_MODE != "fp32" and M >= LINEAR_TC_MIN_ROWS:
-        prec = TC_PRECISION[_LINEAR_MODE]
+    lmode = mode or _LINEAR_MODE
+    if lmode != "fp32" and M >= LINEAR_TC_MIN_ROWS:
+        prec = TC_PRECISION[lmode]
         w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, prec)
         with _timed("linear_tc_p%d" % prec, (M, N, K)):
             st = lib.ps_linear_tc(_ptr(x2), K, _ptr(w_tc), float(w_scale), Kp, Npad, _ptr(bias), _ptr(g), _ptr(b), float(eps),
@@ -425,3 +428,134 @@ def nchw_to_split(x, act_out, precision):
             st = lib.ps_nchw_to_split(_ptr(x), _ptr(act_out), n, H, W, int(precision), _stream())
             _lib.check(st, "ps_nchw_to_split")
     return act_out
+
+
+# ------------------------------------------------------------------------------------------------ training kernels
+
+def layernorm_fwd(x, gamma, beta, eps):
+    """ x (..., K) -> (y, mean (M,), rstd (M,)): un-fused LayerNorm of the training path (keeps the statistics) """
+    lib = _lib.load()
+    _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta")
+    K = x.shape[-1]
+    M = x.numel() // K
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    with _timed("layernorm_fwd"):
+        st = lib.ps_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(y), _ptr(mean), _ptr(rstd), M, K, _stream())
+    _lib.check(st, "ps_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma):
+    lib = _lib.load()
+    _req(dy, "dy"); _req(x, "x")
+    K = x.shape[-1]
+    M = x.numel() // K
+    dx = torch.empty_like(x)
+    dg = torch.empty(K, device=x.device, dtype=torch.float32)
+    db = torch.empty(K, device=x.device, dtype=torch.float32)
+    with _timed("layernorm_bwd"):
+        st = lib.ps_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx), _ptr(dg), _ptr(db), M, K, _stream())
+    _lib.check(st, "ps_layernorm_bwd")
+    return dx, dg, db
+
+
+def linear_wgrad(dy, x, want_bias=True):
+    """ dy (M, N), x (M, K) -> (dW (N, K), db (N,) or None) """
+    lib = _lib.load()
+    _req(dy, "dy"); _req(x, "x")
+    M, N = dy.shape
+    K = x.shape[1]
+    dW = torch.empty(N, K, device=x.device, dtype=torch.float32)
+    db = torch.empty(N, device=x.device, dtype=torch.float32) if want_bias else None
+    with _timed("linear_wgrad", (M, N, K)):
+        st = lib.ps_linear_wgrad(_ptr(dy), N, _ptr(x), K, _ptr(dW), _ptr(db), M, N, K, _stream())
+    _lib.check(st, "ps_linear_wgrad")
+    return dW, db
+
+
+def act_fwd(z, act):
+    lib = _lib.load()
+    _req(z, "z")
+    y = torch.empty_like(z)
+    with _timed("act_fwd"):
+        st = lib.ps_act_fwd(_ptr(z), _ptr(y), z.numel(), int(act), _stream())
+    _lib.check(st, "ps_act_fwd")
+    return y
+
+
+def act_bwd(dy, z, act):
+    lib = _lib.load()
+    _req(dy, "dy"); _req(z, "z")
+    dz = torch.empty_like(z)
+    with _timed("act_bwd"):
+        st = lib.ps_act_bwd(_ptr(dy), _ptr(z), _ptr(dz), z.numel(), int(act), _stream())
+    _lib.check(st, "ps_act_bwd")
+    return dz
+
+
+def mha_bwd(qkv, dout, n_seq, L, n_heads, head_dim, slots_per_frame=0):
+    lib = _lib.load()
+    _req(qkv, "qkv"); _req(dout, "dout")
+    inner = n_heads * head_dim
+    dqkv = torch.empty_like(qkv)
+    with _timed("mha_bwd"):
+        st = lib.ps_mha_bwd(_ptr(qkv), 3 * inner, _ptr(dout), inner, _ptr(dqkv), n_seq, L, n_heads, head_dim, int(slots_per_frame), _stream())
+    _lib.check(st, "ps_mha_bwd")
+    return dqkv
+
+
+def invdyn_tail_bwd(mv, noise, z, idx, codebook, g_dist, g_z, g_proto, g_var, g_quant, per_slot, eps=1e-6):
+    lib = _lib.load()
+    B, T, R, A2 = mv.shape
+    A = A2 // 2
+    d_mv = torch.empty_like(mv)
+    c = lambda t: None if t is None else _req(t.contiguous(), "grad")
+    gs = [c(g) for g in (g_dist, g_z, g_proto, g_var, g_quant)]
+    st = lib.ps_invdyn_tail_bwd(_ptr(mv), _ptr(noise), _ptr(z), _ptr(idx), _ptr(codebook), *[_ptr(g) for g in gs], _ptr(d_mv),
+                                B, T, R, A, codebook.shape[0], int(per_slot), float(eps), _stream())
+    _lib.check(st, "ps_invdyn_tail_bwd")
+    return d_mv
+
+
+def dec_composite_bwd(recons, masks, g_recon, g_recons, g_masks):
+    """ gradients w.r.t. the 4-channel output of the last decoder convolution, (M*S, 4, H, W) """
+    lib = _lib.load()
+    M, S, _, H, W = recons.shape
+    g_o = torch.empty(M * S, 4, H, W, device=recons.device, dtype=torch.float32)
+    with _timed("dec_composite_bwd"):
+        st = lib.ps_dec_composite_bwd(_ptr(recons), _ptr(masks), _ptr(g_recon), _ptr(g_recons), _ptr(g_masks), _ptr(g_o), M, S, H, W, _stream())
+    _lib.check(st, "ps_dec_composite_bwd")
+    return g_o
+
+
+def dec_final_dgrad(g_o, w_packed, h, act_out, precision, g_scale=None):
+    lib = _lib.load()
+    n_img, _, H, W = h.shape
+    with _timed("dec_final_dgrad"):
+        st = lib.ps_dec_final_dgrad(_ptr(g_o), _ptr(w_packed), _ptr(h), _ptr(act_out), _ptr(g_scale), n_img, H, W, int(precision), _stream())
+    _lib.check(st, "ps_dec_final_dgrad")
+    return act_out
+
+
+def conv5x5_tc_dgrad(g_in, w_packed_flipped, mask_act, n_img, H, W, precision, act_out=None, out_tokens=None):
+    """ data gradient of a 64 -> 64 5x5 convolution + the ReLU in front of it: conv(g_in, flipped weights) masked by
+    (mask_act > 0); result as padded split (act_out) or fp32 NHWC tokens (out_tokens) """
+    lib = _lib.load()
+    w_tc, w_scale = w_packed_flipped
+    mode = 0 if act_out is not None else 2
+    with _timed("conv5x5_tc_dgrad_p%d" % precision, (n_img, 64, 64, H, W, 5)):
+        st = lib.ps_conv5x5_tc_dgrad(_ptr(g_in), _ptr(w_tc), float(w_scale), _ptr(mask_act), _ptr(act_out), _ptr(out_tokens),
+                                     n_img, H, W, mode, int(precision), _stream())
+    _lib.check(st, "ps_conv5x5_tc_dgrad")
+    return act_out if mode == 0 else out_tokens
+
+
+def dec_expand_bwd(g_tokens, n_img, H, W, ksize, g_scale=None):
+    lib = _lib.load()
+    dG = torch.empty(n_img, ksize * ksize * 64, device=g_tokens.device, dtype=torch.float32)
+    with _timed("dec_expand_bwd"):
+        st = lib.ps_dec_expand_bwd(_ptr(g_tokens), _ptr(dG), _ptr(g_scale), n_img, H, W, ksize, _stream())
+    _lib.check(st, "ps_dec_expand_bwd")
+    return dG
