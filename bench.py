@@ -115,6 +115,34 @@ def oracle_step(cfg, ssd, psd, B, seed):
     return time.perf_counter() - t0
 
 
+def torch_cuda_baseline(cfg, ssd, psd, B):
+    """ the same workload through the oracle port on the GPU: eager ATen / cuDNN / cuBLAS launches with PyTorch's default
+    flags (cuDNN TF32 convolutions on), i.e. what the reference's own nn.Modules dispatch to on CUDA.  Informational. """
+    from oracle import playslot_oracle as O
+    scfg, pcfg = cfg["model"]["model_params"], cfg["predictor"]["predictor_params"]
+    dev = "cuda"
+    ssd = {k: v.to(dev) for k, v in ssd.items()}
+    psd = {k: v.to(dev) for k, v in psd.items()}
+    T = NUM_SEED + NUM_PREDS
+    S, D, A = scfg["num_slots"], scfg["slot_dim"], pcfg["action_dim"]
+    video = torch.rand(B, T, 3, 64, 64, device=dev)
+    per_slot = pcfg["LatentAction"]["model_name"] == "VQSimpleMLPSlotLatentAction"
+    noise = torch.randn((B, T - 1, S, A) if per_slot else (B, T - 1, A), device=dev)
+    init_noise = torch.randn(B, S, D, device=dev) if scfg["initializer"] == "LearnedRandom" else None
+    ts = []
+    with torch.no_grad():
+        for i in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            O.seed_rollout_pipeline(ssd, scfg, psd, pcfg, video, NUM_SEED, NUM_PREDS, noise, init_noise)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+    ms = min(ts[1:])
+    return {"value": B * T / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "kind": "oracle port run with torch on cuda:0 (eager ATen/cuDNN/cuBLAS, "
+            "default flags: TF32 convolutions)", "batch": B}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -210,6 +238,8 @@ def run_ours(args):
     torch.manual_seed(0)                                           # same random-init weights on every rank
     savi, pred = configs.build_models(cfg, "cuda")
     savi.conv_mode = args.conv_mode
+    ops.set_linear_mode(args.conv_mode)                            # one arithmetic mode for every tensor-core path
+    savi.slot_attention.mode = "fp32" if args.conv_mode == "fp32" else "tc"
     B, T = args.batch, NUM_SEED + NUM_PREDS
     g = torch.Generator().manual_seed(1234 + rank)                 # a different synthetic shard per rank
     video_host = torch.rand(B, T, 3, 64, 64, generator=g).pin_memory()
@@ -225,8 +255,13 @@ def run_ours(args):
     def max_over_ranks(ms):
         return shard.max_over_ranks(ms, device="cuda")
 
+    from playslot_b200.pipeline import GraphedSeedRollout
+    graphed = None if args.eager else GraphedSeedRollout(savi, pred, B, NUM_SEED, NUM_PREDS)
+    step = (lambda: graphed(video)) if graphed else (lambda: seed_rollout(savi, pred, video, NUM_SEED, NUM_PREDS))
+    step_host = (lambda: graphed.run_host(video_host, out_host)) if graphed else \
+        (lambda: seed_rollout_host(savi, pred, video_host, NUM_SEED, NUM_PREDS, out_host))
     for _ in range(max(args.warmup, 3)):
-        seed_rollout(savi, pred, video, NUM_SEED, NUM_PREDS)
+        step()
     barrier()
 
     # ---- device-resident timing -------------------------------------------------------------------------
@@ -235,32 +270,37 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)
     ops.reset_launch_count()
-    ops.profile_start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        seed_rollout(savi, pred, video, NUM_SEED, NUM_PREDS)
+        step()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = ops.launch_count()
-    prof = ops.profile_stop()
+    launches = graphed.launches_per_replay * args.steps if graphed else ops.launch_count()
 
     # ---- end-to-end timing: pinned host video in, predicted frames back to the host, every step ------------
     for _ in range(2):
-        seed_rollout_host(savi, pred, video_host, NUM_SEED, NUM_PREDS, out_host)
+        step_host()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     e2.record()
     for _ in range(args.steps):
-        seed_rollout_host(savi, pred, video_host, NUM_SEED, NUM_PREDS, out_host)
+        step_host()
     e3.record()
     barrier()
     wall_e2e = time.perf_counter() - t_host0
     ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), 1e3 * wall_e2e))
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel device times: the same step once more, eagerly, with CUDA events around every launch (the graph
+    #      replays exactly these kernels; events cannot be placed inside a captured graph) -----------------------------
+    ops.profile_start()
+    seed_rollout(savi, pred, video, NUM_SEED, NUM_PREDS)
+    prof = ops.profile_stop()
+    barrier()
 
     frames_per_step = B * T * world
     value = frames_per_step * args.steps / (ms_total * 1e-3)
@@ -286,23 +326,27 @@ def run_ours(args):
                     "launches": dom[1]["calls"], "avg_launch_ms": dom[1]["ms"] / dom[1]["calls"]}
         if dom[0].startswith("conv5x5_tc_p3"):
             roofline["issued_tensor_TFLOPs"] = 3 * ach * (68.0 / 64.0)
-    sa = prof.get("sa_main")
+    sa_name = "sa_main_tc" if "sa_main_tc" in prof else "sa_main"
+    sa = prof.get(sa_name)
     roofline_sa = None
     if sa:
         by = sum(sa_main_bytes(m) for m in sa["meta"])
         ach = by / (sa["ms"] * 1e-3) / 1e9
-        roofline_sa = {"kernel": "sa_main", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        roofline_sa = {"kernel": sa_name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                        "frac": ach / pk["hbm_gbs"], "traffic": None, "launches": sa["calls"],
-                       "avg_launch_us": 1e3 * sa["ms"] / sa["calls"], "share_of_step": shares.get("sa_main")}
+                       "avg_launch_us": 1e3 * sa["ms"] / sa["calls"], "share_of_step": shares.get(sa_name),
+                       "note": "one streaming pass of a SlotAttention iteration over 64 frames x 4096 tokens x 128 features (fp32, read once) "
+                               "+ masks on the last iteration; algorithmic bytes per SURVEY.md 8(d)"}
         if roofline is None:
             roofline = roofline_sa
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp16x3": "f32 (64->64 convs: fp16x3 split tensor-core products, 22-bit mantissa, fp32 accumulate)",
-                  "fp16": "fp16 convs + f32", "bf16": "bf16 convs + f32", "fp32": "f32"}[args.conv_mode],
-        "data": "synthetic", "config": dict(workload_config(B, world), conv_mode=args.conv_mode),
+        "dtype": {"fp16x3": "f32 (convolutions, linears and SlotAttention contractions as fp16x3 split tensor-core products: 22-bit mantissa, fp32 accumulate)",
+                  "fp16": "fp16 tensor-core products + f32", "bf16": "bf16 tensor-core products + f32", "fp32": "f32 (CUDA cores)"}[args.conv_mode],
+        "data": "synthetic", "config": dict(workload_config(B, world), conv_mode=args.conv_mode, linear_mode=ops.linear_mode(),
+                                            slot_attention_mode=savi.slot_attention.mode),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": video_host.numel() * 4 * world,
                 "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps},
@@ -318,6 +362,10 @@ def run_ours(args):
         oracle_step(cfg, ssd, psd, 1, 7)                                # warm-up
         bs = args.ref_batch
         dt = oracle_step(cfg, ssd, psd, bs, 8)
+        try:
+            line["torch_cuda_baseline"] = torch_cuda_baseline(cfg, ssd, psd, B)
+        except Exception as e:                                         # informational only
+            line["torch_cuda_baseline"] = {"error": repr(e)[:200]}
         line["cpu_baseline"] = {"value": bs * T / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{bs} videos x {T} frames of the same workload, one pass after a 1-video warm-up "
                                           f"({dt:.1f} s), torch CPU fp32 oracle port, {cores} threads"}
@@ -336,6 +384,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4, help="videos per step of the CPU arm (bounded sample)")
     ap.add_argument("--conv-mode", default=os.environ.get("PLAYSLOT_CONV_MODE", "fp16x3"), choices=["fp16x3", "fp16", "bf16", "fp32"],
                     help="arithmetic of the 64->64 5x5 convolutions (fp16x3 = split fp16 tensor-core products, fp32-grade)")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--skip-extras", action="store_true", help="skip the config-2 SlotAttention sweep and the CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -64,7 +64,7 @@ def soft_position_embedding(sd, p, H, W):
     """
     w = sd[p + ".projection.weight"]             # (C, 4, 1, 1)
     b = sd[p + ".projection.bias"]
-    g = position_grid(H, W, w.dtype)
+    g = position_grid(H, W, w.dtype).to(w.device)
     return torch.einsum("ck,khw->chw", w[:, :, 0, 0], g) + b[:, None, None]
 
 
@@ -348,7 +348,7 @@ def cocvp_step(sd, cfg, slots, protos, variab=None, p="dynamics_model"):
         t = t + _lin(sd, p + ".variability_emb", variab)
     pe = sd[p + ".pos_emb.pe"][0, :Fr]                   # (F,1,E)
     t = (t + pe[None]).reshape(B, Fr * S, -1)
-    mask = block_causal_mask(Fr, S, t.dtype)
+    mask = block_causal_mask(Fr, S, t.dtype).to(t.device)
     for l in range(cfg["num_layers"]):
         t = transformer_block(sd, f"{p}.dynamics_model.{l}", t, cfg["num_heads"], cfg["head_dim"], mask)
     out = _lin(sd, p + ".regression_head.1", _ln(sd, p + ".regression_head.0", t, 1e-5))

@@ -96,9 +96,9 @@ def linear(x, weight, bias=None, ln=None, act=ops.ACT_NONE, res=None, res_div=1,
     """ same contract as ops.linear; differentiable w.r.t. x, weight, bias, the LayerNorm parameters and res """
     ln_params = ln[:2] if ln is not None else ()
     if not _needs_grad(x, weight, bias, res, *ln_params):
-        d = lambda t: None if t is None else t.detach()
-        return ops.linear(x.detach(), d(weight), d(bias), ln=None if ln is None else (d(ln[0]), d(ln[1]), ln[2]),
-                          act=act, res=d(res), res_div=res_div, res_mod=res_mod)
+        # inference: the fused kernel.  The parameter OBJECTS are passed through untouched -- ops caches the packed
+        # tensor-core copy of a weight on the tensor object itself, a detach() would defeat it.
+        return ops.linear(x, weight, bias, ln=ln, act=act, res=res, res_div=res_div, res_mod=res_mod)
     h = x
     if ln is not None:
         h = _LayerNorm.apply(h, ln[0], ln[1], ln[2])
@@ -119,7 +119,7 @@ def linear(x, weight, bias=None, ln=None, act=ops.ACT_NONE, res=None, res_div=1,
 
 def mha(qkv, n_seq, L, n_heads, head_dim, slots_per_frame=0, res=None):
     if not _needs_grad(qkv, res):
-        return ops.mha(qkv.detach(), n_seq, L, n_heads, head_dim, slots_per_frame, res=None if res is None else res.detach())
+        return ops.mha(qkv, n_seq, L, n_heads, head_dim, slots_per_frame, res=res)
     out = _MHA.apply(qkv, n_seq, L, n_heads, head_dim, slots_per_frame)
     if res is not None:
         out = out + res.reshape(out.shape)

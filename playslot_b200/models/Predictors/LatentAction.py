@@ -88,7 +88,14 @@ class BaseSlotLatentAction(nn.Module):
         """ mv (B, T, R, 2A) -> output dict of `forward` """
         A = self.action_dim
         shape = (B, T - 1, A) if not per_slot else (B, T - 1, R, A)
-        noise = torch.randn(shape, dtype=torch.float32).to(mv.device)       # same RNG call as the reference
+        static = getattr(self, "_static_noise", None)
+        if static is not None:
+            # CUDA-graph replay (pipeline.GraphedSeedRollout): the host draws the noise with the same call as below
+            # and uploads it into this fixed device buffer before every replay
+            assert static.numel() == B * (T - 1) * R * A, "static noise buffer does not match the captured shape"
+            noise = static
+        else:
+            noise = torch.randn(shape, dtype=torch.float32).to(mv.device)   # same RNG call as the reference
         codebook = self.quantizer.get_codewords()
         out = AG.invdyn_tail(mv, f32c(noise.view(B, T - 1, R, A)), codebook, per_slot)
         idx = out["idx"]

@@ -43,3 +43,69 @@ def seed_rollout_host(savi, predictor, videos_host, num_seed, num_preds, out_hos
     out_host.copy_(imgs, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return out_host, res
+
+
+class GraphedSeedRollout:
+    """
+    `seed_rollout` for a fixed batch shape, captured once in a CUDA graph and replayed: the ~800 kernel launches of
+    a step (15 sequential cOCVP steps x 8 layers on <= 48 tokens, 21 SlotAttention frames, ...) are latency-bound
+    and a Python / ctypes launch loop cannot feed them fast enough.  Everything data-dependent on the host stays
+    outside the graph: the video is copied into a static device buffer and the InvDyn noise is drawn on the host
+    with the reference's own call (torch.randn on the CPU generator, LatentAction.py:73) and uploaded before each
+    replay, so results are identical to the eager path under the same seed.
+    """
+
+    def __init__(self, savi, predictor, batch, num_seed, num_preds, resolution=(64, 64), num_samples=1, device="cuda", warmup=2):
+        if num_samples != 1:
+            raise NotImplementedError("the graphed path covers the posterior rollout (num_samples=1); prior samples draw "
+                                      "random codebook indices on the host and use the eager path")
+        self.savi, self.predictor = savi, predictor
+        self.num_seed, self.num_preds = num_seed, num_preds
+        T = num_seed + num_preds
+        H, W = resolution
+        la = predictor.latent_action
+        S, A = savi.num_slots, la.action_dim
+        per_slot = type(la).__name__ == "VQSimpleMLPSlotLatentAction"
+        self.noise_shape = (batch, T - 1, S, A) if per_slot else (batch, T - 1, A)
+        self.video = torch.zeros(batch, T, 3, H, W, device=device)
+        self.noise = torch.zeros(self.noise_shape, device=device)
+        self._noise_pinned = torch.empty(self.noise_shape, pin_memory=True)
+        la._static_noise = self.noise
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):                       # allocates workspaces, packs weights, configures kernels
+                    seed_rollout(savi, predictor, self.video, num_seed, num_preds)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            from . import ops
+            n0 = ops.launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = seed_rollout(savi, predictor, self.video, num_seed, num_preds)
+            self.launches_per_replay = ops.launch_count() - n0        # playslot_b200 kernels inside the graph
+        finally:
+            la._static_noise = None
+        self._la = la
+
+    def draw_noise(self):
+        """ the reference's RNG call for the Gaussian latent sample (host generator) """
+        return torch.randn(self.noise_shape, dtype=torch.float32)
+
+    @torch.no_grad()
+    def __call__(self, videos, noise=None):
+        """ videos: (B, T, 3, H, W) on the host (pinned) or on the device; returns the static output dict """
+        self.video.copy_(videos, non_blocking=True)
+        self._noise_pinned.copy_(self.draw_noise() if noise is None else noise)
+        self.noise.copy_(self._noise_pinned, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+    @torch.no_grad()
+    def run_host(self, videos_host, out_host):
+        """ end-to-end: pinned host video in, predicted frames back in `out_host` (pinned) """
+        res = self(videos_host)
+        out_host.copy_(res["pred_imgs"][:, 0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host

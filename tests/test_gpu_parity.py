@@ -421,3 +421,28 @@ def test_aux_predictors_match_reference_golden():
         out, d = m(sh.to(DEV), actions.to(DEV), num_seed=fx["num_seed"], num_preds=fx["num_preds"])
     check("action_cond pred_slots", out, fx["pred_slots"])
     assert d["pred_slots"] is out
+
+
+def test_graphed_seed_rollout_equals_eager():
+    """ the CUDA-graph replay of the pipeline returns bit-identical tensors to the eager launches (same noise) """
+    from playslot_b200.pipeline import seed_rollout, GraphedSeedRollout
+    fx, ssd, psd, video, noise, init_noise = load_case("blockpush")
+    scfg, pcfg = fx["savi_cfg"], fx["predictor_cfg"]
+    B, ns, npred = fx["B"], fx["num_seed"], fx["num_preds"]
+    savi = make_savi(scfg, ssd, DEV)
+    pred = make_predictor(fx["predictor_name"], pcfg, psd, DEV)
+    v = video.to(DEV)
+    with FixedRandn(noise):
+        eager = seed_rollout(savi, pred, v, ns, npred)
+    g = GraphedSeedRollout(savi, pred, B, ns, npred)
+    assert g.launches_per_replay > 100
+    for rep in range(2):                                        # replays are repeatable
+        out = g(v, noise=noise)
+        for k in ("slot_history", "pred_slots", "pred_imgs", "pred_masks"):
+            assert torch.equal(out[k], eager[k]), f"{k} differs between graph replay {rep} and eager launches"
+    check("pred_slots vs reference", out["pred_slots"][:, 0], fx["pred_slots"], 5e-4)
+    # a different video through the same graph
+    v2 = torch.rand_like(v)
+    with FixedRandn(noise):
+        eager2 = seed_rollout(savi, pred, v2, ns, npred)
+    assert torch.equal(g(v2, noise=noise)["pred_imgs"], eager2["pred_imgs"])

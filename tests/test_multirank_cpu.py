@@ -63,3 +63,79 @@ def test_shard_range_covers_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ------------------------------------------------------------------------------------------------ training collectives
+
+def _train_worker(rank, world_size, port, q):
+    """ gradient bucket all-reduce and EMA-VQ statistic sync of playslot_b200.train / quantization on CPU tensors """
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from playslot_b200 import train
+        from playslot_b200.models.BlocksUtils.quantization import EmaVectorQuantizer
+        torch.manual_seed(0)
+        lin = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+        frozen = torch.nn.Linear(3, 3).requires_grad_(False)
+        bucket = train.GradientBucket(list(lin.parameters()) + list(frozen.parameters()))
+        g = torch.Generator().manual_seed(100)
+        x_all = torch.randn(6 * world_size, 5, generator=g)
+        a, b = shard.shard_range(x_all.shape[0], rank, world_size)
+        lin(x_all[a:b]).pow(2).mean().backward()          # per-rank mean loss on the shard (DDP convention)
+        lin[1].bias.grad = None                           # a parameter without gradient on this rank must still take part
+        nbytes = bucket.all_reduce_mean()
+        grads = [None if p.grad is None else p.grad.clone() for p in lin.parameters()]
+        # EMA codebook statistics on the global batch
+        torch.manual_seed(1)
+        vq = EmaVectorQuantizer(num_embs=4, emb_dim=3)
+        z_all = torch.randn(4 * world_size, 5, 3, generator=g)
+        idx_all = torch.randint(0, 4, (4 * world_size, 5, 1), generator=g)
+        a2, b2 = shard.shard_range(z_all.shape[0], rank, world_size)
+        vq.ema_update(z_all[a2:b2], idx_all[a2:b2])
+        q.put((rank, nbytes, [None if t is None else t.tolist() for t in grads], vq.ema_count.tolist(), vq.ema_weight.tolist(),
+               vq.vq.embeddings["0"].weight.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world_size", [2])
+def test_training_collectives_equal_single_process(world_size):
+    from playslot_b200.models.BlocksUtils.quantization import EmaVectorQuantizer
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world_size, port, q)) for r in range(world_size)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference: mean over ranks of the per-shard gradients
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    g = torch.Generator().manual_seed(100)
+    x_all = torch.randn(6 * world_size, 5, generator=g)
+    acc = [torch.zeros_like(p) for p in lin.parameters()]
+    for r in range(world_size):
+        a, b = shard.shard_range(x_all.shape[0], r, world_size)
+        lin.zero_grad()
+        lin(x_all[a:b]).pow(2).mean().backward()
+        for i, p in enumerate(lin.parameters()):
+            if i != 3:                                     # lin[1].bias was dropped on every rank
+                acc[i] += p.grad / world_size
+    torch.manual_seed(1)
+    vq = EmaVectorQuantizer(num_embs=4, emb_dim=3)
+    vq.sync_stats = False
+    z_all = torch.randn(4 * world_size, 5, 3, generator=g)
+    idx_all = torch.randint(0, 4, (4 * world_size, 5, 1), generator=g)
+    vq.ema_update(z_all, idx_all)
+    n_float = sum(p.numel() for p in lin.parameters())
+    for rank, nbytes, grads, cnt, wgt, emb in res:
+        assert nbytes == 4 * n_float                       # one flat bucket of every trainable parameter
+        for got, ref in zip(grads, acc):
+            assert got is not None
+            assert torch.allclose(torch.tensor(got), ref, atol=1e-6)
+        assert torch.allclose(torch.tensor(cnt), vq.ema_count, atol=1e-6)          # == single GPU on the global batch
+        assert torch.allclose(torch.tensor(wgt), vq.ema_weight, atol=1e-6)
+        assert torch.allclose(torch.tensor(emb), vq.vq.embeddings["0"].weight, atol=1e-6)
