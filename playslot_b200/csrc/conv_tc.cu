@@ -71,41 +71,43 @@ struct ConvTcParams {
     int items_per_img;       // work items (NPOS positions each) per image
     int halo, a_rows;        // halo rows on each side, staged A rows (multiple of ABOX)
     int stages;              // weight ring depth (2..MAX_STAGES)
+    int n_ctas;              // persistent grid size (one CTA per SM)
     int relu, out_mode;
     int bf16;                // operand format: 1 = bf16, 0 = fp16
     float out_scale;         // 1 / (power-of-two scale folded into the packed weights)
 };
 
+// Persistent: every CTA walks over work items (NPOS consecutive positions of one image) with stride gridDim.x.  The
+// accumulators are double-buffered in TMEM, so the epilogue of item i (TMEM -> registers -> global) overlaps the TMA
+// loads and the MMAs of item i+1; the weight ring keeps streaming across items.
 template <int TILES, int NSPLIT>
 __global__ void __launch_bounds__(192, 1)
 conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                   const __grid_constant__ CUtensorMap mapW, const ConvTcParams p) {
     constexpr int NPOS = TILE_M * TILES;
-    constexpr int NPROD = (NSPLIT == 2) ? 3 : 1;
+    constexpr uint32_t ACC_COLS = 64 * TILES * NSPLIT;      // TMEM columns of one accumulator buffer
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = p.a_rows * ROWB;
     uint8_t* sA[2] = {smem, smem + a_bytes};
     uint8_t* sW = smem + NSPLIT * a_bytes;                 // stages x NSPLIT x 8 KB
-    __shared__ uint64_t bar_a, bar_wfull[MAX_STAGES], bar_wempty[MAX_STAGES], bar_acc;
+    __shared__ uint64_t bar_afull, bar_aempty, bar_wfull[MAX_STAGES], bar_wempty[MAX_STAGES], bar_accfull[2], bar_accempty[2];
     const int STAGES = p.stages;
     __shared__ uint32_t tmem_base;
     __shared__ float s_bias[C];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int img = blockIdx.x / p.items_per_img;
-    const int item = blockIdx.x - img * p.items_per_img;
-    const int p0 = 2 * p.Wp + item * NPOS;                 // first output position (padded-linear, per image)
-    const long long img_base = (long long)img * p.Hp * p.Wp;
+    const int n_items = p.n_img * p.items_per_img;
 
     if (tid == 0) {
-        tc::mbar_init(&bar_a, 1);
-        tc::mbar_init(&bar_acc, 1);
+        tc::mbar_init(&bar_afull, 1);
+        tc::mbar_init(&bar_aempty, 1);
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_accfull[b], 1); tc::mbar_init(&bar_accempty[b], 4); }
         for (int s = 0; s < MAX_STAGES; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
         tc::fence_mbar_init();
     }
     if (tid < C) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
-    if (warp == 1) tc::tmem_alloc(&tmem_base, 64 * TILES * NSPLIT);
+    if (warp == 1) tc::tmem_alloc(&tmem_base, 2 * ACC_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -116,123 +118,171 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&mapA_hi);
             tc::tma_prefetch_desc(&mapW);
-            const int g0 = (int)(img_base + p0 - p.halo);
-            tc::mbar_expect_tx(&bar_a, (uint32_t)(NSPLIT * a_bytes));
-            for (int r = 0; r < p.a_rows; r += ABOX) {
-                tc::tma_load_2d(sA[0] + r * ROWB, &mapA_hi, &bar_a, 0, g0 + r);
-                if (NSPLIT == 2) tc::tma_load_2d(sA[1] + r * ROWB, &mapA_lo, &bar_a, 0, g0 + r);
-            }
-            for (int tap = 0; tap < 25; ++tap) {
-                const int s = tap % STAGES;
-                if (tap >= STAGES) tc::mbar_wait(&bar_wempty[s], ((tap / STAGES) - 1) & 1);
-                tc::mbar_expect_tx(&bar_wfull[s], NSPLIT * WTAP_BYTES);
-                tc::tma_load_2d(sW + s * NSPLIT * WTAP_BYTES, &mapW, &bar_wfull[s], 0, tap * 128);
+            int i = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+                const int img = it / p.items_per_img;
+                const int item = it - img * p.items_per_img;
+                const int p0 = 2 * p.Wp + item * NPOS;
+                const int g0 = (int)((long long)img * p.Hp * p.Wp + p0 - p.halo);
+                auto load_w = [&](int tap) {
+                    const int g = i * 25 + tap;
+                    const int s = g % STAGES;
+                    if (g >= STAGES) tc::mbar_wait(&bar_wempty[s], ((g / STAGES) - 1) & 1);
+                    tc::mbar_expect_tx(&bar_wfull[s], NSPLIT * WTAP_BYTES);
+                    tc::tma_load_2d(sW + s * NSPLIT * WTAP_BYTES, &mapW, &bar_wfull[s], 0, tap * 128);
+                };
+                // the first weight taps of this item stream in while the previous item's last MMAs still run
+                for (int tap = 0; tap < STAGES; ++tap) load_w(tap);
+                if (i > 0) tc::mbar_wait(&bar_aempty, (i - 1) & 1);            // MMAs of the previous item have read the region
+                tc::mbar_expect_tx(&bar_afull, (uint32_t)(NSPLIT * a_bytes));
+                for (int r = 0; r < p.a_rows; r += ABOX) {
+                    tc::tma_load_2d(sA[0] + r * ROWB, &mapA_hi, &bar_afull, 0, g0 + r);
+                    if (NSPLIT == 2) tc::tma_load_2d(sA[1] + r * ROWB, &mapA_lo, &bar_afull, 0, g0 + r);
+                }
+                for (int tap = STAGES; tap < 25; ++tap) load_w(tap);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (tc::elect_one()) {
             const uint32_t idesc = p.bf16 ? tc::umma_idesc_bf16(TILE_M, C) : tc::umma_idesc_f16(TILE_M, C);
+            const uint32_t idesc2 = tc::umma_idesc_f16(TILE_M, 2 * C);
+            // Descriptors are built once: per MMA only the 14-bit start-address field changes, so the issue loop adds a
+            // (16-byte unit) offset to the low word -- the single issuing thread must not become the bottleneck.
             const uint32_t a_base[2] = {tc::smem_u32(sA[0]), tc::smem_u32(sA[1])};
             const uint32_t w_base = tc::smem_u32(sW);
-            tc::mbar_wait(&bar_a, 0);
-            tc::tc_fence_after();
-            for (int tap = 0; tap < 25; ++tap) {
-                const int s = tap % STAGES;
-                tc::mbar_wait(&bar_wfull[s], (tap / STAGES) & 1);
+            uint64_t adesc[2][TILES][C / 16];
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                for (int tile = 0; tile < TILES; ++tile)
+#pragma unroll
+                    for (int k = 0; k < C / 16; ++k)
+                        adesc[pl][tile][k] = tc::umma_desc_sw128(a_base[pl] + (uint32_t)(p.halo + tile * TILE_M) * ROWB + k * 32, 1024, 0);
+            const uint64_t bdesc0 = tc::umma_desc_sw128(w_base, 1024, 0);
+            int i = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+                const int buf = i & 1;
+                if (i >= 2) tc::mbar_wait(&bar_accempty[buf], ((i >> 1) - 1) & 1);   // epilogue drained this accumulator buffer
+                tc::mbar_wait(&bar_afull, i & 1);
                 tc::tc_fence_after();
-                const int ky = tap / 5, kx = tap - ky * 5;
-                const int off = (ky - 2) * p.Wp + (kx - 2);
+                int g = i * 25;
+                for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
-                for (int tile = 0; tile < TILES; ++tile) {
-                    const uint32_t row0 = (uint32_t)(p.halo + tile * TILE_M + off);
+                    for (int kx = 0; kx < 5; ++kx, ++g) {
+                        const int s = g % STAGES;
+                        tc::mbar_wait(&bar_wfull[s], (g / STAGES) & 1);
+                        tc::tc_fence_after();
+                        const int64_t a_off = (int64_t)(((ky - 2) * p.Wp + (kx - 2)) * (ROWB / 16));     // tap shift, 16-byte units
+                        const uint64_t b_st = bdesc0 + (uint64_t)(s * NSPLIT * (WTAP_BYTES / 16));
 #pragma unroll
-                    for (int pr = 0; pr < NPROD; ++pr) {
-                        const int as = (pr == 2) ? 1 : 0;       // (A_hi,W_hi), (A_hi,W_lo), (A_lo,W_hi)
-                        const int ws = (pr == 1) ? 1 : 0;
+                        for (int tile = 0; tile < TILES; ++tile) {
+                            const uint32_t acc0 = tm + buf * ACC_COLS + tile * NSPLIT * C;   // D0 | D1 are adjacent: 2 x 64 columns
 #pragma unroll
-                        for (int k = 0; k < C / 16; ++k) {
-                            const uint32_t a_addr = a_base[as] + row0 * ROWB + k * 32;
-                            const uint32_t b_addr = w_base + (s * NSPLIT + ws) * WTAP_BYTES + k * 32;
-                            // accumulator 0: hi*hi; accumulator 1 (scaled by 2^11): hi*lo + lo*hi
-                            const uint32_t acc = tm + (tile * NSPLIT + (pr ? 1 : 0)) * C;
-                            const uint32_t first = (pr <= 1) ? (uint32_t)(tap | k) : 1u;
-                            tc::umma_bf16(acc, tc::umma_desc_sw128(a_addr, 1024, 0),
-                                          tc::umma_desc_sw128(b_addr, 1024, 0), idesc, first != 0 ? 1u : 0u);
+                            for (int k = 0; k < C / 16; ++k) {
+                                const uint32_t first = (ky | kx | k) ? 1u : 0u;
+                                const uint64_t a_hi = adesc[0][tile][k] + a_off;
+                                const uint64_t b_hi = b_st + (uint64_t)(k * 2);
+                                if (NSPLIT == 2) {
+                                    // one N=128 MMA against [W_hi ; W_lo] (the two weight tiles are adjacent in the stage):
+                                    // D0 += A_hi W_hi and D1 += A_hi W_lo share a single read of A_hi; then D1 += A_lo W_hi.
+                                    // 14 KB of shared-memory operand traffic per k-step instead of 18 KB for three N=64 MMAs.
+                                    tc::umma_bf16(acc0, a_hi, b_hi, idesc2, first);
+                                    tc::umma_bf16(acc0 + C, adesc[1][tile][k] + a_off, b_hi, idesc, 1u);
+                                } else {
+                                    tc::umma_bf16(acc0, a_hi, b_hi, idesc, first);
+                                }
+                            }
                         }
+                        tc::umma_commit(&bar_wempty[s]);       // frees the weight stage once these MMAs retire
                     }
                 }
-                tc::umma_commit(&bar_wempty[s]);           // frees the weight stage once these MMAs retire
+                tc::umma_commit(&bar_aempty);              // the activation region may be overwritten
+                tc::umma_commit(&bar_accfull[buf]);        // the accumulators of this item are complete
             }
-            tc::umma_commit(&bar_acc);
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
-        tc::mbar_wait(&bar_acc, 0);
-        tc::tc_fence_after();
         const int HW = p.H * p.W;
+        int i = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int img = it / p.items_per_img;
+            const int item = it - img * p.items_per_img;
+            const int p0 = 2 * p.Wp + item * NPOS;
+            const long long img_base = (long long)img * p.Hp * p.Wp;
+            tc::mbar_wait(&bar_accfull[buf], (i >> 1) & 1);
+            __syncwarp();
+            tc::tc_fence_after();
 #pragma unroll 1
-        for (int tile = 0; tile < TILES; ++tile) {
-            const int r = quad * 32 + lane;
-            const int pp = p0 + tile * TILE_M + r;          // padded-linear position inside the image
-            const int yp = pp / p.Wp, xp = pp - yp * p.Wp;
-            const bool row_ok = yp < p.H + 2;               // rows >= 2 by construction
-            const bool interior = row_ok && xp >= 2 && xp < p.W + 2;
-            float v[64];
-            const uint32_t tbase = tm + ((uint32_t)(quad * 32) << 16) + tile * NSPLIT * C;
-            tc::tmem_ld_32x32(tbase, v);
-            tc::tmem_ld_32x32(tbase + 32, v + 32);
-            if (NSPLIT == 2) {
-                float u[32];
+            for (int tile = 0; tile < TILES; ++tile) {
+                const int r = quad * 32 + lane;
+                const int pp = p0 + tile * TILE_M + r;          // padded-linear position inside the image
+                const int yp = pp / p.Wp, xp = pp - yp * p.Wp;
+                const bool row_ok = yp < p.H + 2;               // rows >= 2 by construction
+                const bool interior = row_ok && xp >= 2 && xp < p.W + 2;
+                float v[64];
+                const uint32_t tbase = tm + ((uint32_t)(quad * 32) << 16) + buf * ACC_COLS + tile * NSPLIT * C;
+                tc::tmem_ld_32x32(tbase, v);
+                tc::tmem_ld_32x32(tbase + 32, v + 32);
+                if (NSPLIT == 2) {
+                    float u[32];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    tc::tmem_ld_32x32(tbase + C + h * 32, u);
+                    for (int h = 0; h < 2; ++h) {
+                        tc::tmem_ld_32x32(tbase + C + h * 32, u);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[h * 32 + c] = fmaf(u[c], 1.0f / LO_SCALE, v[h * 32 + c]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                float t = fmaf(v[c], p.out_scale, s_bias[c]);
-                if (p.relu) t = fmaxf(t, 0.f);
-                v[c] = interior ? t : 0.f;
-            }
-            if (p.mask_hi && interior) {                    // ReLU data gradient: pass where the saved activation was positive
-                const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + ((size_t)img_base + pp) * C);
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const uint4 m4 = __ldg(mk + g);
-                    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if ((mw[j] & 0x7FFFu) == 0u || (mw[j] & 0x8000u)) v[g * 8 + 2 * j] = 0.f;
-                        if ((mw[j] & 0x7FFF0000u) == 0u || (mw[j] & 0x80000000u)) v[g * 8 + 2 * j + 1] = 0.f;
+                        for (int c = 0; c < 32; ++c) v[h * 32 + c] = fmaf(u[c], 1.0f / LO_SCALE, v[h * 32 + c]);
                     }
                 }
-            }
-            if (p.out_mode == 0) {
-                if (row_ok) {
-                    const size_t o = ((size_t)img_base + pp) * C;
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        split_store8(v + g * 8, p.out_hi + o + g * 8, p.out_lo ? p.out_lo + o + g * 8 : nullptr, p.bf16 != 0);
+                if (tile == TILES - 1) {
+                    // every accumulator column of this buffer is in registers: hand the buffer back to the MMA warp
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&bar_accempty[buf]);
                 }
-            } else if (interior) {
-                const int y = yp - 2, x = xp - 2;
-                if (p.out_mode == 1) {
-                    float* dst = p.out_f32 + (size_t)img * C * HW + (size_t)y * p.W + x;
 #pragma unroll
-                    for (int c = 0; c < 64; ++c) dst[(size_t)c * HW] = v[c];
-                } else {
-                    const size_t pix = (size_t)y * p.W + x;
-                    float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((size_t)img * HW + pix) * C);
-                    const float4* ad = p.addend ? reinterpret_cast<const float4*>(p.addend + pix * C) : nullptr;
+                for (int c = 0; c < 64; ++c) {
+                    float t = fmaf(v[c], p.out_scale, s_bias[c]);
+                    if (p.relu) t = fmaxf(t, 0.f);
+                    v[c] = interior ? t : 0.f;
+                }
+                if (p.mask_hi && interior) {                    // ReLU data gradient: pass where the saved activation was positive
+                    const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + ((size_t)img_base + pp) * C);
 #pragma unroll
-                    for (int g = 0; g < 16; ++g) {
-                        float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-                        if (ad) { const float4 a = ad[g]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-                        dst[g] = o;
+                    for (int g = 0; g < 8; ++g) {
+                        const uint4 m4 = __ldg(mk + g);
+                        const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if ((mw[j] & 0x7FFFu) == 0u || (mw[j] & 0x8000u)) v[g * 8 + 2 * j] = 0.f;
+                            if ((mw[j] & 0x7FFF0000u) == 0u || (mw[j] & 0x80000000u)) v[g * 8 + 2 * j + 1] = 0.f;
+                        }
+                    }
+                }
+                if (p.out_mode == 0) {
+                    if (row_ok) {
+                        const size_t o = ((size_t)img_base + pp) * C;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            split_store8(v + g * 8, p.out_hi + o + g * 8, p.out_lo ? p.out_lo + o + g * 8 : nullptr, p.bf16 != 0);
+                    }
+                } else if (interior) {
+                    const int y = yp - 2, x = xp - 2;
+                    if (p.out_mode == 1) {
+                        float* dst = p.out_f32 + (size_t)img * C * HW + (size_t)y * p.W + x;
+#pragma unroll
+                        for (int c = 0; c < 64; ++c) dst[(size_t)c * HW] = v[c];
+                    } else {
+                        const size_t pix = (size_t)y * p.W + x;
+                        float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((size_t)img * HW + pix) * C);
+                        const float4* ad = p.addend ? reinterpret_cast<const float4*>(p.addend + pix * C) : nullptr;
+#pragma unroll
+                        for (int g = 0; g < 16; ++g) {
+                            float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                            if (ad) { const float4 a = ad[g]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                            dst[g] = o;
+                        }
                     }
                 }
             }
@@ -240,7 +290,7 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tm, 64 * TILES * NSPLIT);
+    if (warp == 1) tc::tmem_dealloc(tm, 2 * ACC_COLS);
 }
 
 template <int TILES, int NSPLIT>
@@ -253,7 +303,8 @@ int launch_conv_tc(const CUtensorMap& mA_hi, const CUtensorMap& mA_lo, const CUt
         PS_CUDA(cudaFuncSetAttribute(conv5x5_tc_kernel<TILES, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    conv5x5_tc_kernel<TILES, NSPLIT><<<p.n_img * p.items_per_img, 192, smem, st>>>(mA_hi, mA_lo, mW, p);
+    const int n_items = p.n_img * p.items_per_img;
+    conv5x5_tc_kernel<TILES, NSPLIT><<<n_items < p.n_ctas ? n_items : p.n_ctas, 192, smem, st>>>(mA_hi, mA_lo, mW, p);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;
@@ -301,6 +352,11 @@ static int conv5x5_tc_run(const void* act_in, const void* w_tc, const float* bia
     p.items_per_img = (H * Wp + TILE_M * tiles - 1) / (TILE_M * tiles);
     p.halo = halo; p.a_rows = a_rows_for(tiles); p.stages = stages_for(tiles);
     p.relu = relu; p.out_mode = out_mode;
+    {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        p.n_ctas = sms;
+    }
     const uint16_t* in_hi = reinterpret_cast<const uint16_t*>(act_in);
     CUtensorMap mA_hi, mA_lo, mW;
     int r = tc::make_tmap_2d_bf16_sw128(&mA_hi, in_hi, (uint64_t)P, C, ABOX, C);

@@ -19,7 +19,6 @@
 #include "tc_common.cuh"
 #include "../../include/playslot_b200.h"
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 namespace {
 
@@ -40,7 +39,6 @@ struct SaTcParams {
     float* masks;         // [B][S][N] or null
     int B, N, S, CH, tpc;
     float ln_eps, attn_eps;
-    int debug;            // timing experiments only (results invalid when non-zero)
 };
 
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
@@ -177,7 +175,7 @@ __global__ void __launch_bounds__(288, 2) sa_main_tc_kernel(const SaTcParams p) 
         for (int t = 0; t < ntiles; ++t) {
             // ---------------------------------------------------------------- load, normalise, split, store
             load_pair(vb, t, 1);
-            if (t > 0 && !p.debug) tc::mbar_wait(&bar_v, (t - 1) & 1);         // previous tile fully consumed
+            if (t > 0) tc::mbar_wait(&bar_v, (t - 1) & 1);         // previous tile fully consumed
             store_pair(va, 0);
             load_pair(va, t + 1, 0);                                           // zeros past the last tile
             store_pair(vb, 1);
@@ -186,7 +184,7 @@ __global__ void __launch_bounds__(288, 2) sa_main_tc_kernel(const SaTcParams p) 
             if (lane == 0) tc::mbar_arrive(&bar_cfull);
 
             // ---------------------------------------------------------------- softmax over slots (warps 0-3)
-            if (warp < 4 && !p.debug) {
+            if (warp < 4) {
                 tc::mbar_wait(&bar_l, t & 1);
                 __syncwarp();
                 tc::tc_fence_after();
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__(288, 2) sa_main_tc_kernel(const SaTcParams p) 
         }
 
         // -------------------------------------------------------------------- epilogue: partial sums of this CTA
-        if (warp < 4 && !p.debug) {
+        if (warp < 4) {
             tc::mbar_wait(&bar_v, (ntiles - 1) & 1);
             __syncwarp();
             tc::tc_fence_after();
@@ -264,7 +262,7 @@ __global__ void __launch_bounds__(288, 2) sa_main_tc_kernel(const SaTcParams p) 
         }
     } else {
         // ------------------------------------------------------------------------ MMA issuer (warp 8)
-        if (!p.debug && tc::elect_one()) {
+        if (tc::elect_one()) {
             const uint32_t idesc1 = tc::umma_idesc_f16_major(128, N1, 0, 0);
             const uint32_t idesc2 = tc::umma_idesc_f16_major(128, N1, 1, 1);
             const uint32_t chi = tc::smem_u32(c_hi), clo = tc::smem_u32(c_lo);
@@ -329,7 +327,6 @@ extern "C" int ps_sa_main_tc(const float* x, const float* A, const float* a0, fl
     p.x = x; p.A = A; p.a0 = a0; p.partial = partial; p.masks = masks;
     p.B = B; p.N = N; p.S = S; p.CH = n_chunks; p.tpc = (N + n_chunks - 1) / n_chunks;
     p.ln_eps = ln_eps; p.attn_eps = attn_eps;
-    { const char* e = getenv("PLAYSLOT_SA_DEBUG"); p.debug = e ? atoi(e) : 0; }
     PS_REQUIRE((size_t)(n_chunks - 1) * p.tpc < (size_t)N, "ps_sa_main_tc: n_chunks=%d leaves empty chunks for N=%d", n_chunks, N);
     cudaStream_t st = (cudaStream_t)stream;
     if (S <= 8) return launch_sa_main_tc<8>(p, st);
