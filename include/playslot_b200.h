@@ -95,6 +95,17 @@ int ps_sa_main(const float* x, const float* A, const float* a0, const float* a1,
 int ps_sa_main_tc(const float* x, const float* A, const float* a0, float* partial, float* masks /* may be NULL */,
                   int B, int N, int S, int dim, int n_chunks, float ln_eps, float attn_eps, void* stream);
 
+/* Pre-normalised feature planes: c = (x - mean) * rstd of norm_input (no affine part) as two fp16 planes
+ * [hi | lo][n_tokens][128] (lo scaled by 2048; 512 bytes per token, like the fp32 input).  Computed once per frame;
+ * every SlotAttention iteration then streams the planes with TMA (ps_sa_main_tc2) and does no CUDA-core work on the
+ * features: TMA -> tcgen05 (logits) -> per-token softmax out of TMEM -> tcgen05 (weighted sums).  Persistent over
+ * (frame, chunk) items, 3-stage TMA ring, double-buffered logits / weights / accumulators in TMEM.
+ * lo_offset_tokens: distance (in tokens) from the first hi row of this batch to its first lo row (>= B*N), so that a
+ * batch may be a slice of planes prepared for many frames at once. */
+int ps_sa_prepare(const float* x, void* planes, long long n_tokens, int dim, float ln_eps, void* stream);
+int ps_sa_main_tc2(const void* planes, long long lo_offset_tokens, const float* A, const float* a0, float* partial,
+                   float* masks /* may be NULL */, int B, int N, int S, int dim, int n_chunks, float attn_eps, void* stream);
+
 /* Per-slot update: reduce the partials, renormalise over locations (:109), to_v (:94), nn.GRUCell (:112-115),
  * residual MLP (:117), then (do_prep) the folded queries of the next iteration.  With do_update = 0 it only
  * prepares A/a0/a1 from slots_in.  Weight matrices suffixed T are transposed to [in][out]. */

@@ -37,8 +37,10 @@ class SlotAttention(nn.Module):
     """
 
     TOKENS_PER_CTA = int(os.environ.get("PLAYSLOT_SA_TOKENS", "256"))
-    # "tc": both contractions on tcgen05 (fp16 hi/lo split operands, fp32-grade); "fp32": exact FFMA kernel
-    MODES = ("tc", "fp32")
+    # "tc":   pre-normalised fp16 hi/lo feature planes (one pass per frame) streamed by TMA into tcgen05 contractions
+    # "tc1":  the same contractions with the normalisation / split done inside every streaming pass
+    # "fp32": exact FFMA kernel
+    MODES = ("tc", "tc1", "fp32")
 
     def __init__(self, dim_feats, dim_slots, num_slots, num_iters_first=2, num_iters=2,
                  mlp_hidden=128, epsilon=1e-8):
@@ -99,19 +101,42 @@ class SlotAttention(nn.Module):
             }
         return self._cache.get(src, build)
 
+    def prepare(self, feats):
+        """ fp32 features (..., N, dim) -> pre-normalised planes for `forward(inputs=("planes", planes, first_token, B, N))`;
+        SAVi.forward prepares all frames of a clip in one launch """
+        return ops.sa_prepare(f32c(feats), self.norm_input.eps)
+
     def forward(self, inputs, slots, step=0, **kwargs):
-        require_cuda(inputs, "SlotAttention")
-        no_grad_only("SlotAttention", inputs, slots, self.to_q.weight)
-        x, slots = f32c(inputs), f32c(slots)
-        B, N, _ = x.shape
+        planes = None
+        if isinstance(inputs, tuple) and inputs[0] == "planes":
+            _, planes, first_token, B, N = inputs
+            require_cuda(planes, "SlotAttention")
+            x = None
+        else:
+            require_cuda(inputs, "SlotAttention")
+            x = f32c(inputs)
+            B, N, _ = x.shape
+        no_grad_only("SlotAttention", slots, self.to_q.weight, *([] if x is None else [x]))
+        slots = f32c(slots)
         S = slots.shape[1]
         self.attention_masks = None
         num_iters = self.num_iters_first if step == 0 else self.num_iters
         if num_iters <= 0:
             return slots
+        mode = self.mode
+        if planes is not None and mode != "tc":
+            raise ValueError("pre-normalised feature planes are only consumed by SlotAttention.mode == 'tc'")
         w = self._weights()
-        dev = x.device
-        n_chunks = max(1, (N + self.TOKENS_PER_CTA - 1) // self.TOKENS_PER_CTA)
+        dev = slots.device
+        if mode == "tc" and planes is None:
+            planes, first_token = ops.sa_prepare(x, self.norm_input.eps), 0
+        tokens = self.TOKENS_PER_CTA
+        if mode == "tc" and "PLAYSLOT_SA_TOKENS" not in os.environ:
+            # persistent kernel: the largest work item (fewest partials, fewest item switches) that still gives every SM one
+            tokens = 2048
+            while tokens > 256 and B * ((N + tokens - 1) // tokens) < 148:
+                tokens //= 2
+        n_chunks = max(1, (N + tokens - 1) // tokens)
         partial = torch.empty(B, n_chunks, ops.sa_partial_floats(S), device=dev, dtype=torch.float32)
         A = torch.empty(B, S, self.dim_slots, device=dev, dtype=torch.float32)
         a0 = torch.empty(B, S, device=dev, dtype=torch.float32)
@@ -132,10 +157,13 @@ class SlotAttention(nn.Module):
         update(None, cur, None, False, True)
         for it in range(num_iters):
             last = it == num_iters - 1
-            if self.mode == "tc":
-                ops.sa_main_tc(x, A, a0, partial, masks if last else None, n_chunks, eps_ln, self.epsilon)
+            mk = masks if last else None
+            if mode == "tc":
+                ops.sa_main_tc2(planes, first_token, B, N, A, a0, partial, mk, n_chunks, self.epsilon)
+            elif mode == "tc1":
+                ops.sa_main_tc(x, A, a0, partial, mk, n_chunks, eps_ln, self.epsilon)
             else:
-                ops.sa_main(x, A, a0, a1, partial, masks if last else None, n_chunks, eps_ln, self.epsilon)
+                ops.sa_main(x, A, a0, a1, partial, mk, n_chunks, eps_ln, self.epsilon)
             update(partial, cur, out, True, not last)
             cur = out
         self.attention_masks = masks

@@ -128,8 +128,17 @@ class SAVi(nn.Module):
 
         slot_history, recons_h, objs_h, masks_h = [], [], [], []
         feats_all = self._encode_clip(x, num_imgs)            # list of (t0, (t1-t0, B, N, D)) chunks
+        use_planes = self.slot_attention.mode == "tc"
+        if use_planes:
+            # norm_input statistics + fp16 hi/lo split of every frame in one launch per chunk; the per-frame
+            # SlotAttention passes then stream these planes by TMA
+            feats_all = [(t0, f.shape, self.slot_attention.prepare(f)) for t0, f in feats_all]
         for t in range(num_imgs):
-            feats = self._feats_at(feats_all, t)
+            if use_planes:
+                t0, shp, planes = next(c for c in feats_all if c[0] <= t < c[0] + c[1][0])
+                feats = ("planes", planes, (t - t0) * shp[1] * shp[2], shp[1], shp[2])
+            else:
+                feats = self._feats_at(feats_all, t)
             slots = self.slot_attention(inputs=feats, slots=predicted, step=t)
             if decode:
                 recon, (recons, masks) = self.decode(slots)

@@ -258,6 +258,32 @@ def sa_main_tc(x, A, a0, partial, masks, n_chunks, ln_eps, attn_eps):
     _lib.check(st, "ps_sa_main_tc")
 
 
+def sa_prepare(x, ln_eps=1e-5):
+    """ x (..., N, 128) fp32 features of one or several frame batches -> planes int16 (2 [hi, lo], n_tokens, 128): one pass
+    applying norm_input's statistics (no affine part) and the fp16 hi/lo split """
+    lib = _lib.load()
+    _req(x, "feats")
+    D = x.shape[-1]
+    n_tok = x.numel() // D
+    planes = torch.empty(2, n_tok, D, device=x.device, dtype=torch.int16)
+    with _timed("sa_prepare", (n_tok,)):
+        st = lib.ps_sa_prepare(_ptr(x), _ptr(planes), n_tok, D, float(ln_eps), _stream())
+    _lib.check(st, "ps_sa_prepare")
+    return planes
+
+
+def sa_main_tc2(planes, first_token, B, N, A, a0, partial, masks, n_chunks, attn_eps):
+    """ planes: (2, n_tokens, 128) int16 from sa_prepare; the batch covers tokens [first_token, first_token + B*N) """
+    lib = _lib.load()
+    S = A.shape[1]
+    n_tok = planes.shape[1]
+    base = planes.data_ptr() + first_token * 128 * 2
+    with _timed("sa_main_tc2", (B, N, S, 128, masks is not None)):
+        st = lib.ps_sa_main_tc2(base, n_tok, _ptr(A), _ptr(a0), _ptr(partial), _ptr(masks), B, N, S, 128, n_chunks,
+                                float(attn_eps), _stream())
+    _lib.check(st, "ps_sa_main_tc2")
+
+
 def sa_update(partial, n_chunks, slots_in, slots_out, w, A, a0, a1, mlp_hidden, scale, ln_eps, do_update, do_prep):
     """ w: dict of prepared SlotAttention weights (see models.BlocksUtils.attention.SlotAttention._weights) """
     lib = _lib.load()

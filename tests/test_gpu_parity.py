@@ -169,7 +169,7 @@ def _sa_module(S, sd, mlp_hidden=256, it_first=3, it=1):
     return m.to(DEV)
 
 
-SA_MODES = ["tc", "fp32"]
+SA_MODES = ["tc", "tc1", "fp32"]
 
 
 @pytest.mark.parametrize("sa_mode", SA_MODES)

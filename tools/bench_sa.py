@@ -13,8 +13,8 @@ for S in (8, 4):
     m = SlotAttention(128, 128, S, 3, 1, 256).eval().cuda()
     feats = torch.randn(64, 4096, 128, device="cuda")
     slots = torch.randn(64, S, 128, device="cuda")
-    for mode in ("tc", "fp32"):
-        for tokens in ((128, 256, 512, 1024) if mode == "tc" else (256,)):
+    for mode in ("tc", "tc1", "fp32"):
+        for tokens in ((128, 256, 512, 1024) if mode != "fp32" else (256,)):
             m.mode = mode
             SlotAttention.TOKENS_PER_CTA = tokens
             with torch.no_grad():
