@@ -170,14 +170,17 @@ struct MhaParams {
     float scale;
 };
 
+// One CTA per (sequence, head).  K and V are staged in shared memory; every warp processes FOUR query rows at a time so that
+// each shared-memory read of a key / value element feeds four FMAs (the kernel is LDS-bound otherwise): the four queries are
+// stored interleaved [d][4] and the four probability rows [j][4], both read as one broadcast LDS.128.
 __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
     extern __shared__ __align__(16) float sm[];
     const int seq = blockIdx.x, h = blockIdx.y;
     const int L = p.L, dh = p.dh, inner = p.H * dh;
     float* Ks = sm;                      // [L][dh+1]
     float* Vs = Ks + L * (dh + 1);       // [L][dh]
-    float* Ps = Vs + L * dh;             // [4][L]
-    float* Qs = Ps + 4 * L;              // [4][dh]
+    float* Ps = sm + ((L * (dh + 1) + L * dh + 3) & ~3);    // [4 warps][L][4], 16-byte aligned
+    float* Qs = Ps + 4 * L * 4;          // [4 warps][dh][4]
     const float* base = p.qkv + (size_t)seq * L * p.ld;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int idx = tid; idx < L * dh; idx += 128) {
@@ -186,36 +189,63 @@ __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
         Vs[j * dh + d] = base[(size_t)j * p.ld + 2 * inner + h * dh + d];
     }
     __syncthreads();
-    for (int i = w; i < L; i += 4) {
-        for (int d = lane; d < dh; d += 32) Qs[w * dh + d] = base[(size_t)i * p.ld + h * dh + d];
+    float* Pw = Ps + w * L * 4;
+    float* Qw = Qs + w * dh * 4;
+    for (int i0 = w * 4; i0 < L; i0 += 16) {
+        // the four query rows of this pass, interleaved; rows past the end are zero (their results are not stored)
+        for (int idx = lane; idx < dh * 4; idx += 32) {
+            const int d = idx >> 2, r = idx & 3;
+            Qw[idx] = (i0 + r < L) ? base[(size_t)(i0 + r) * p.ld + h * dh + d] : 0.f;
+        }
         __syncwarp();
-        float mx = -INFINITY;
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         for (int j = lane; j < L; j += 32) {
-            float dot = 0.f;
             const float* kr = Ks + j * (dh + 1);
-            const float* qr = Qs + w * dh;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-            for (int d = 0; d < dh; ++d) dot = fmaf(qr[d], kr[d], dot);
-            dot *= p.scale;
-            if (p.spf > 0 && (j / p.spf) > (i / p.spf)) dot = -1e9f;   // masked_fill(mask == 0, -1e9)
-            Ps[w * L + j] = dot;
-            mx = fmaxf(mx, dot);
+            for (int d = 0; d < dh; ++d) {
+                const float k = kr[d];
+                const float4 q = *reinterpret_cast<const float4*>(Qw + d * 4);
+                a0 = fmaf(q.x, k, a0); a1 = fmaf(q.y, k, a1); a2 = fmaf(q.z, k, a2); a3 = fmaf(q.w, k, a3);
+            }
+            float dot[4] = {a0 * p.scale, a1 * p.scale, a2 * p.scale, a3 * p.scale};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (p.spf > 0 && (j / p.spf) > ((i0 + r) / p.spf)) dot[r] = -1e9f;   // masked_fill(mask == 0, -1e9)
+                mx[r] = fmaxf(mx[r], dot[r]);
+            }
+            *reinterpret_cast<float4*>(Pw + j * 4) = make_float4(dot[0], dot[1], dot[2], dot[3]);
         }
-        mx = warp_max(mx);
-        float sum = 0.f;
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) mx[r] = warp_max(mx[r]);
         for (int j = lane; j < L; j += 32) {
-            const float e = expf(Ps[w * L + j] - mx);
-            Ps[w * L + j] = e;
-            sum += e;
+            float4 e = *reinterpret_cast<const float4*>(Pw + j * 4);
+            e.x = expf(e.x - mx[0]); e.y = expf(e.y - mx[1]); e.z = expf(e.z - mx[2]); e.w = expf(e.w - mx[3]);
+            sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
+            *reinterpret_cast<float4*>(Pw + j * 4) = e;
         }
-        sum = warp_sum(sum);
+        float inv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) inv[r] = 1.0f / warp_sum(sum[r]);
         __syncwarp();
-        const float inv = 1.0f / sum;
         for (int d = lane; d < dh; d += 32) {
-            float acc = 0.f;
-            for (int j = 0; j < L; ++j) acc = fmaf(Ps[w * L + j] * inv, Vs[j * dh + d], acc);
-            const size_t oi = ((size_t)seq * L + i) * p.ldo + h * dh + d;
-            p.out[oi] = p.res ? acc + p.res[oi] : acc;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < L; ++j) {
+                const float v = Vs[j * dh + d];
+                const float4 pr = *reinterpret_cast<const float4*>(Pw + j * 4);
+                a0 = fmaf(pr.x * inv[0], v, a0); a1 = fmaf(pr.y * inv[1], v, a1);
+                a2 = fmaf(pr.z * inv[2], v, a2); a3 = fmaf(pr.w * inv[3], v, a3);
+            }
+            const float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (i0 + r < L) {
+                    const size_t oi = ((size_t)seq * L + i0 + r) * p.ldo + h * dh + d;
+                    p.out[oi] = p.res ? acc[r] + p.res[oi] : acc[r];
+                }
+            }
         }
         __syncwarp();
     }
@@ -230,7 +260,7 @@ extern "C" int ps_mha(const float* qkv, int ld, const float* res, float* out, in
     MhaParams p;
     p.qkv = qkv; p.ld = ld; p.res = res; p.out = out; p.ldo = ldo; p.n_seq = n_seq; p.L = L; p.H = n_heads; p.dh = head_dim;
     p.spf = slots_per_frame; p.scale = 1.0f / sqrtf((float)head_dim);
-    size_t smem = (size_t)(L * (head_dim + 1) + L * head_dim + 4 * L + 4 * head_dim) * sizeof(float);
+    size_t smem = (size_t)(L * (head_dim + 1) + L * head_dim + 4 + 16 * L + 16 * head_dim) * sizeof(float);
     PS_REQUIRE(smem <= 200 * 1024, "ps_mha: sequence of %d tokens x head_dim %d does not fit in shared memory", L, head_dim);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {

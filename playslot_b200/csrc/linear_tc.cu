@@ -60,9 +60,8 @@ __device__ __forceinline__ void split_store4(const float4 v, uint8_t* hi, uint8_
     }
 }
 
-template <int BN, int NSPLIT>
-__global__ void __launch_bounds__(LT_THREADS, 2) linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const LinTcParams p) {
-    constexpr int NPROD = (NSPLIT == 2) ? 3 : 1;
+template <int BN, int NSPLIT, bool PIPE>
+__global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const LinTcParams p) {
     constexpr int W_TILE = BN * 128;
     constexpr int STAGE_BYTES = NSPLIT * (A_TILE + W_TILE);
     constexpr int TM_COLS = (NSPLIT * BN < 32) ? 32 : NSPLIT * BN;
@@ -153,7 +152,17 @@ __global__ void __launch_bounds__(LT_THREADS, 2) linear_tc_kernel(const __grid_c
             }
             __syncwarp();                          // the rows a warp normalises are the rows it measured
         }
-        for (int kb = 0; kb < p.nkb; ++kb) {
+        auto load_kb = [&](float4 (&v)[8], int kb) {
+            const int k = kb * KB + c4 * 4;
+            const bool k_ok = kb < p.nkb && k < p.K;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + i * 16 + r_sub;
+                v[i] = (m < p.M && k_ok) ? *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto store_kb = [&](const float4 (&v)[8], int kb) {
             const int s = kb % STAGES;
             uint8_t* a_hi = smem + s * STAGE_BYTES;
             uint8_t* a_lo = a_hi + A_TILE;
@@ -163,13 +172,6 @@ __global__ void __launch_bounds__(LT_THREADS, 2) linear_tc_kernel(const __grid_c
             if (ln && k_ok) {
                 g4 = *reinterpret_cast<const float4*>(p.ln_g + k);
                 b4 = *reinterpret_cast<const float4*>(p.ln_b + k);
-            }
-            float4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = m0 + i * 16 + r_sub;
-                v[i] = (m < p.M && k_ok) ? *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], ((kb / STAGES) - 1) & 1);
 #pragma unroll
@@ -188,6 +190,26 @@ __global__ void __launch_bounds__(LT_THREADS, 2) linear_tc_kernel(const __grid_c
             tc::fence_async_proxy();               // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar_afull[s]);
+        };
+        if (PIPE) {
+            // long K (small-M rollout GEMMs, one CTA per SM): the loads of the next K block are in flight while this one
+            // is normalised, split and stored
+            float4 va[8], vb[8];
+            load_kb(va, 0);
+            for (int kb = 0; kb < p.nkb; kb += 2) {
+                load_kb(vb, kb + 1);
+                store_kb(va, kb);
+                if (kb + 1 < p.nkb) {
+                    load_kb(va, kb + 2);
+                    store_kb(vb, kb + 1);
+                }
+            }
+        } else {
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                float4 v[8];
+                load_kb(v, kb);
+                store_kb(v, kb);
+            }
         }
         // ------------------------------------------------------------------ epilogue
         // warp w owns TMEM lanes (w % 4) * 32 .. +31 (rows) and the column half w / 4.  Each 32 x CW chunk is
@@ -238,6 +260,7 @@ __global__ void __launch_bounds__(LT_THREADS, 2) linear_tc_kernel(const __grid_c
         // ------------------------------------------------------------------ MMA issuer
         if (tc::elect_one()) {
             const uint32_t idesc = p.bf16 ? tc::umma_idesc_bf16(BM, BN) : tc::umma_idesc_f16(BM, BN);
+            const uint32_t idesc2 = tc::umma_idesc_f16(BM, 2 * BN <= 256 ? 2 * BN : BN);
             const uint32_t base = tc::smem_u32(smem);
             for (int kb = 0; kb < p.nkb; ++kb) {
                 const int s = kb % STAGES;
@@ -248,17 +271,21 @@ __global__ void __launch_bounds__(LT_THREADS, 2) linear_tc_kernel(const __grid_c
                 const uint32_t a_base = base + s * STAGE_BYTES;
                 const uint32_t w_base = a_base + NSPLIT * A_TILE;
 #pragma unroll
-                for (int pr = 0; pr < NPROD; ++pr) {
-                    const int as = (pr == 2) ? 1 : 0;           // (A_hi,W_hi), (A_hi,W_lo), (A_lo,W_hi)
-                    const int ws = (pr == 1) ? 1 : 0;
-#pragma unroll
-                    for (int k = 0; k < KB / 16; ++k) {
-                        const uint32_t a_addr = a_base + as * A_TILE + k * 32;
-                        const uint32_t b_addr = w_base + ws * W_TILE + k * 32;
-                        const uint32_t acc = tm + (pr ? BN : 0);
-                        const uint32_t accumulate = (pr <= 1) ? (uint32_t)(kb | k) : 1u;
-                        tc::umma_bf16(acc, tc::umma_desc_sw128(a_addr, 1024, 0), tc::umma_desc_sw128(b_addr, 1024, 0), idesc,
-                                      accumulate != 0 ? 1u : 0u);
+                for (int k = 0; k < KB / 16; ++k) {
+                    const uint32_t first = (uint32_t)(kb | k) ? 1u : 0u;
+                    const uint64_t a_hi = tc::umma_desc_sw128(a_base + k * 32, 1024, 0);
+                    const uint64_t b_hi = tc::umma_desc_sw128(w_base + k * 32, 1024, 0);
+                    if (NSPLIT == 2 && 2 * BN <= 256) {
+                        // A_hi x [W_hi ; W_lo] in one N = 2*BN MMA (the two weight tiles are adjacent in the stage, D0 | D1
+                        // adjacent in TMEM), then D1 += A_lo x W_hi
+                        tc::umma_bf16(tm, a_hi, b_hi, idesc2, first);
+                        tc::umma_bf16(tm + BN, tc::umma_desc_sw128(a_base + A_TILE + k * 32, 1024, 0), b_hi, idesc, 1u);
+                    } else if (NSPLIT == 2) {                      // BN = 256: an MMA cannot be wider, three N = BN products
+                        tc::umma_bf16(tm, a_hi, b_hi, idesc, first);
+                        tc::umma_bf16(tm + BN, a_hi, tc::umma_desc_sw128(w_base + W_TILE + k * 32, 1024, 0), idesc, first);
+                        tc::umma_bf16(tm + BN, tc::umma_desc_sw128(a_base + A_TILE + k * 32, 1024, 0), b_hi, idesc, 1u);
+                    } else {
+                        tc::umma_bf16(tm, a_hi, b_hi, idesc, first);
                     }
                 }
                 tc::umma_commit(&bar_empty[s]);
@@ -284,22 +311,30 @@ __global__ void __launch_bounds__(LT_THREADS, 2) linear_tc_kernel(const __grid_c
     if (warp == 8) tc::tmem_dealloc(tm, TM_COLS);
 }
 
-template <int BN, int NSPLIT>
-int launch_linear_tc(const CUtensorMap& mW, const LinTcParams& p, cudaStream_t st) {
+template <int BN, int NSPLIT, bool PIPE>
+int launch_linear_tc_impl(const CUtensorMap& mW, const LinTcParams& p, cudaStream_t st) {
     constexpr int STAGE_BYTES = NSPLIT * (A_TILE + BN * 128);
     size_t smem = (size_t)p.stages * STAGE_BYTES;
     if (smem < 8 * 32 * 33 * sizeof(float)) smem = 8 * 32 * 33 * sizeof(float);      // epilogue transpose scratch
     smem += 1024;
     static size_t configured = 0;
     if (smem > configured) {
-        PS_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PS_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, NSPLIT, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-    linear_tc_kernel<BN, NSPLIT><<<grid, LT_THREADS, smem, st>>>(mW, p);
+    linear_tc_kernel<BN, NSPLIT, PIPE><<<grid, LT_THREADS, smem, st>>>(mW, p);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;
+}
+
+template <int BN, int NSPLIT>
+int launch_linear_tc(const CUtensorMap& mW, const LinTcParams& p, cudaStream_t st) {
+    // software-pipelined producers when K is long and the grid leaves at most one CTA per SM anyway
+    const long long ctas = (long long)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    if (p.nkb >= 3 && ctas <= 2 * 148) return launch_linear_tc_impl<BN, NSPLIT, true>(mW, p, st);
+    return launch_linear_tc_impl<BN, NSPLIT, false>(mW, p, st);
 }
 
 }  // namespace
@@ -325,12 +360,16 @@ extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_s
     p.res = res; p.ldres = ldres; p.res_div = res_div > 0 ? res_div : 1; p.res_mod = res_mod > 0 ? res_mod : M;
     p.Y = Y; p.ldy = ldy; p.M = M; p.N = N; p.K = K; p.nkb = Kp / KB; p.npad = Npad;
     p.act = act; p.bf16 = precision == 1 ? 1 : 0; p.out_scale = 1.0f / w_scale;
-    // column tile: the widest that still gives the grid about two CTAs per SM
+    // Column tile.  Every CTA normalises / splits its own copy of the 128-row activation tile, so narrow tiles multiply that
+    // CUDA-core work: take the widest tile (<= 256) that still leaves about one CTA per two SMs.
     const long long mt = (M + BM - 1) / BM;
-    int bn = 128;
-    while (bn > 32 && (mt * ((N + bn - 1) / bn) < 2 * 148 || bn / 2 >= ((N + 31) / 32) * 32)) bn >>= 1;
+    const int n32 = ((N + 31) / 32) * 32;
+    int bn = 256;
+    while (bn > 32 && (bn / 2 >= n32 || mt * ((N + bn - 1) / bn) < 74)) bn >>= 1;
+    if (bn == 256 && nsplit == 1) bn = 128;            // (the single-product instantiation of the widest tile is not built)
     const int stage_bytes = nsplit * (A_TILE + bn * 128);
     int stages = (100 * 1024) / stage_bytes;         // at most ~100 KB per CTA: two CTAs per SM overlap each other's phases
+    if (bn == 256) stages = 2;                       // 96 KB stages, one CTA per SM (its 512 TMEM columns fill the SM anyway)
     if (stages < 1) stages = 1;
     if (stages > LT_MAX_STAGES) stages = LT_MAX_STAGES;
     if (stages > p.nkb) stages = p.nkb;
@@ -339,6 +378,7 @@ extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_s
     const int r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 2ull * Npad, (uint64_t)Kp, (uint32_t)bn, KB);
     PS_REQUIRE(r == 0, "ps_linear_tc: cuTensorMapEncodeTiled(W) failed (%d)", r);
     cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 256) return launch_linear_tc<256, 2>(mW, p, st);
     if (bn == 128) return nsplit == 2 ? launch_linear_tc<128, 2>(mW, p, st) : launch_linear_tc<128, 1>(mW, p, st);
     if (bn == 64) return nsplit == 2 ? launch_linear_tc<64, 2>(mW, p, st) : launch_linear_tc<64, 1>(mW, p, st);
     return nsplit == 2 ? launch_linear_tc<32, 2>(mW, p, st) : launch_linear_tc<32, 1>(mW, p, st);
