@@ -172,6 +172,13 @@ int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* bias, float
                   float* out_f32, const float* addend, int n_img, int H, int W, int relu, int out_mode, int precision,
                   void* stream);
 
+/* ps_dec_composite on the tensor cores: the 3x3 convolution as a 9-tap implicit GEMM over padded NHWC split planes
+ * (act_in: the last 5x5 block's output for M*S slot images, precision 3), all S slots of a 128-position tile accumulated
+ * side by side in TMEM, slot softmax and compositing in the epilogue.  w_tc: 16-bit [9 taps][16 rows: 4 hi, 4 zero, 4 lo,
+ * 4 zero][64 cin] holding w * w_scale. */
+int ps_dec_composite_tc(const void* act_in, const void* w_tc, float w_scale, const float* bias, float* recon, float* recons,
+                        float* masks, int M, int S, int H, int W, void* stream);
+
 /* ps_dec_expand writing the padded NHWC split format (P_hwc: [H*W][64] = conv1(position embedding) + bias). */
 int ps_dec_expand_split(const float* G, const float* P_hwc, void* act_out, int n_img, int H, int W, int ksize,
                         int precision, void* stream);

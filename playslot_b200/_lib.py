@@ -45,6 +45,7 @@ SIGNATURES = {
     "ps_dec_final_dgrad": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_conv5x5_tc_dgrad": (c_i, [c_f, c_f, c_fl, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_dec_expand_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
+    "ps_dec_composite_tc": (c_i, [c_f, c_f, c_fl, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_nchw_to_split": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
 }
 

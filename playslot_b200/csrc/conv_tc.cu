@@ -481,3 +481,227 @@ extern "C" int ps_nchw_to_split(const float* x, void* act_out, int n_img, int H,
     PS_LAUNCH_CHECK();
     return PS_OK;
 }
+
+// ================================================================================================
+// Final decoder stage on the tensor cores: Conv2d(64, 4, 3, padding=1) of every slot image + softmax of the alpha channel
+// over the slot axis + compositing (src/models/SAVi.py:226-234, EncodersDecoders/decoders.py:103-111).
+// Same padded-linear implicit GEMM as above with 9 taps; the 4 output channels are padded to 8, [w_hi | w_lo] form one
+// N = 16 operand, so slot s owns 16 TMEM columns (D0 | D1).  One work item = 128 positions of one frame: the S slot
+// images stream through a double-buffered activation region, their accumulators sit side by side in TMEM, and the
+// epilogue thread of a position sees all S slots: bias, slot softmax, recons / masks / recon written once.
+// ================================================================================================
+namespace {
+
+struct CompTcParams {
+    const float* bias;       // [4]
+    float* recon;            // [M][3][H][W]
+    float* recons;           // [M][S][3][H][W]
+    float* masks;            // [M][S][1][H][W]
+    int M, S, H, W, Wp, Hp;
+    int tiles_per_img, halo, a_rows, nbuf, n_ctas;
+    float out_scale;
+};
+
+constexpr int CT_WBYTES = 9 * 16 * ROWB;     // 9 taps x (8 hi + 8 lo rows) x 64 cin fp16
+
+template <int SPAD>      // slots padded to 8 or 16 (TMEM columns = 16 per slot)
+__global__ void __launch_bounds__(192, 1)
+dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                        const __grid_constant__ CUtensorMap mapW, const CompTcParams p) {
+    constexpr uint32_t ACC_COLS = 16 * SPAD;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = p.a_rows * ROWB;
+    uint8_t* sW = smem;                                    // 18 KB
+    uint8_t* sA0 = smem + ((CT_WBYTES + 1023) & ~1023);    // nbuf x [hi | lo] regions
+    __shared__ uint64_t bar_w, bar_afull[2], bar_aempty[2], bar_accfull[2], bar_accempty[2];
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_items = p.M * p.tiles_per_img;
+    const int S = p.S, NBUF = p.nbuf;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_w, 1);
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&bar_afull[b], 1); tc::mbar_init(&bar_aempty[b], 1);
+            tc::mbar_init(&bar_accfull[b], 1); tc::mbar_init(&bar_accempty[b], 4);
+        }
+        tc::fence_mbar_init();
+    }
+    if (warp == 1) tc::tmem_alloc(&tmem_base, 2 * ACC_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tm = tmem_base;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            tc::tma_prefetch_desc(&mapA_hi);
+            tc::mbar_expect_tx(&bar_w, CT_WBYTES);
+            tc::tma_load_2d(sW, &mapW, &bar_w, 0, 0);
+            int q = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int m = it / p.tiles_per_img, tile = it - m * p.tiles_per_img;
+                const int p0 = 2 * p.Wp + tile * TILE_M;
+                for (int s = 0; s < S; ++s, ++q) {
+                    const int buf = q % NBUF;
+                    if (q >= NBUF) tc::mbar_wait(&bar_aempty[buf], ((q / NBUF) - 1) & 1);
+                    const int g0 = (int)((long long)(m * S + s) * p.Hp * p.Wp + p0 - p.halo);
+                    uint8_t* a = sA0 + buf * 2 * a_bytes;
+                    tc::mbar_expect_tx(&bar_afull[buf], (uint32_t)(2 * a_bytes));
+                    for (int r = 0; r < p.a_rows; r += ABOX) {
+                        tc::tma_load_2d(a + r * ROWB, &mapA_hi, &bar_afull[buf], 0, g0 + r);
+                        tc::tma_load_2d(a + a_bytes + r * ROWB, &mapA_lo, &bar_afull[buf], 0, g0 + r);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            const uint32_t idesc16 = tc::umma_idesc_f16(TILE_M, 16), idesc8 = tc::umma_idesc_f16(TILE_M, 8);
+            const uint64_t dW = tc::umma_desc_sw128(tc::smem_u32(sW), 1024, 0);
+            const uint64_t dA = tc::umma_desc_sw128(tc::smem_u32(sA0), 1024, 0);
+            tc::mbar_wait(&bar_w, 0);
+            int q = 0, i = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+                const int ab = i & 1;
+                if (i >= 2) tc::mbar_wait(&bar_accempty[ab], ((i >> 1) - 1) & 1);
+                for (int s = 0; s < S; ++s, ++q) {
+                    const int buf = q % NBUF;
+                    tc::mbar_wait(&bar_afull[buf], (q / NBUF) & 1);
+                    tc::tc_fence_after();
+                    const uint64_t a_hi = dA + (uint64_t)((buf * 2 * a_bytes) / 16);
+                    const uint64_t a_lo = a_hi + (uint64_t)(a_bytes / 16);
+                    const uint32_t acc = tm + ab * ACC_COLS + s * 16;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const uint64_t row = (uint64_t)((p.halo + (ky - 1) * p.Wp + (kx - 1)) * (ROWB / 16));
+#pragma unroll
+                        for (int k = 0; k < C / 16; ++k) {
+                            const uint64_t bd = dW + (uint64_t)((tap * 16 * ROWB + k * 32) / 16);
+                            tc::umma_bf16(acc, a_hi + row + (uint64_t)(k * 2), bd, idesc16, (tap | k) ? 1u : 0u);   // D0 | D1 += A_hi [w_hi | w_lo]
+                            tc::umma_bf16(acc + 8, a_lo + row + (uint64_t)(k * 2), bd, idesc8, 1u);               // D1 += A_lo w_hi
+                        }
+                    }
+                    tc::umma_commit(&bar_aempty[buf]);
+                }
+                tc::umma_commit(&bar_accfull[ab]);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int HW = p.H * p.W;
+        const float b0 = p.bias[0], b1 = p.bias[1], b2 = p.bias[2], b3 = p.bias[3];
+        int i = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+            const int ab = i & 1;
+            const int m = it / p.tiles_per_img, tile = it - m * p.tiles_per_img;
+            const int pp = 2 * p.Wp + tile * TILE_M + quad * 32 + lane;
+            const int yp = pp / p.Wp, xp = pp - yp * p.Wp;
+            const bool interior = yp < p.H + 2 && xp >= 2 && xp < p.W + 2;
+            tc::mbar_wait(&bar_accfull[ab], (i >> 1) & 1);
+            __syncwarp();
+            tc::tc_fence_after();
+            float o[SPAD][4];
+            const uint32_t tb = tm + ((uint32_t)(quad * 32) << 16) + ab * ACC_COLS;
+#pragma unroll
+            for (int s = 0; s < SPAD; ++s) {
+                if (s < S) {
+                    float v[16];
+                    tc::tmem_ld_32x16(tb + s * 16, v);
+                    o[s][0] = fmaf(fmaf(v[8], 1.0f / LO_SCALE, v[0]), p.out_scale, b0);
+                    o[s][1] = fmaf(fmaf(v[9], 1.0f / LO_SCALE, v[1]), p.out_scale, b1);
+                    o[s][2] = fmaf(fmaf(v[10], 1.0f / LO_SCALE, v[2]), p.out_scale, b2);
+                    o[s][3] = fmaf(fmaf(v[11], 1.0f / LO_SCALE, v[3]), p.out_scale, b3);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_accempty[ab]);
+            if (!interior) continue;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < SPAD; ++s)
+                if (s < S) mx = fmaxf(mx, o[s][3]);
+            float den = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int s = 0; s < SPAD; ++s)
+                if (s < S) { const float e = expf(o[s][3] - mx); o[s][3] = e; den += e; }
+            const float inv = 1.0f / den;
+            const size_t pix = (size_t)(yp - 2) * p.W + (xp - 2);
+#pragma unroll
+            for (int s = 0; s < SPAD; ++s) {
+                if (s < S) {
+                    const float mk = o[s][3] * inv;
+                    const size_t ms = (size_t)m * S + s;
+                    p.recons[(ms * 3 + 0) * HW + pix] = o[s][0];
+                    p.recons[(ms * 3 + 1) * HW + pix] = o[s][1];
+                    p.recons[(ms * 3 + 2) * HW + pix] = o[s][2];
+                    p.masks[ms * HW + pix] = mk;
+                    r0 = fmaf(o[s][0], mk, r0); r1 = fmaf(o[s][1], mk, r1); r2 = fmaf(o[s][2], mk, r2);
+                }
+            }
+            p.recon[((size_t)m * 3 + 0) * HW + pix] = r0;
+            p.recon[((size_t)m * 3 + 1) * HW + pix] = r1;
+            p.recon[((size_t)m * 3 + 2) * HW + pix] = r2;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tm, 2 * ACC_COLS);
+}
+
+template <int SPAD>
+int launch_comp_tc(const CUtensorMap& mA_hi, const CUtensorMap& mA_lo, const CUtensorMap& mW, const CompTcParams& p, cudaStream_t st) {
+    const size_t smem = ((CT_WBYTES + 1023) & ~1023) + (size_t)p.nbuf * 2 * p.a_rows * ROWB + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PS_CUDA(cudaFuncSetAttribute(dec_composite_tc_kernel<SPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int n_items = p.M * p.tiles_per_img;
+    dec_composite_tc_kernel<SPAD><<<n_items < p.n_ctas ? n_items : p.n_ctas, 192, smem, st>>>(mA_hi, mA_lo, mW, p);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
+}
+
+}  // namespace
+
+extern "C" int ps_dec_composite_tc(const void* act_in, const void* w_tc, float w_scale, const float* bias, float* recon,
+                                   float* recons, float* masks, int M, int S, int H, int W, void* stream) {
+    PS_REQUIRE(act_in && w_tc && bias && recon && recons && masks, "ps_dec_composite_tc: null pointer");
+    PS_REQUIRE(S >= 1 && S <= 16, "ps_dec_composite_tc: 1 <= num_slots <= 16 (got %d)", S);
+    PS_REQUIRE(H >= 8 && W >= 8 && W <= 252, "ps_dec_composite_tc: unsupported image size %dx%d", H, W);
+    PS_REQUIRE(w_scale > 0.f, "ps_dec_composite_tc: w_scale must be positive");
+    if (M == 0) return PS_OK;
+    const int Wp = W + 4, Hp = H + 4;
+    const long long P = (long long)M * S * Hp * Wp;
+    PS_REQUIRE(P < (1ll << 31) - 4096, "ps_dec_composite_tc: too many positions for 32-bit TMA coordinates");
+    CompTcParams p;
+    p.bias = bias; p.recon = recon; p.recons = recons; p.masks = masks;
+    p.M = M; p.S = S; p.H = H; p.W = W; p.Wp = Wp; p.Hp = Hp;
+    p.tiles_per_img = (H * Wp + TILE_M - 1) / TILE_M;
+    p.halo = Wp + 1;
+    p.a_rows = ((TILE_M + 2 * p.halo) + 63) / 64 * 64;
+    const long long room = 227ll * 1024 - 1024 - ((CT_WBYTES + 1023) & ~1023);
+    p.nbuf = (2ll * 2 * p.a_rows * ROWB <= room) ? 2 : 1;
+    PS_REQUIRE(2ll * p.a_rows * ROWB <= room, "ps_dec_composite_tc: image width %d does not fit the shared-memory staging", W);
+    p.out_scale = 1.0f / w_scale;
+    {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        p.n_ctas = sms;
+    }
+    const uint16_t* in_hi = reinterpret_cast<const uint16_t*>(act_in);
+    CUtensorMap mA_hi, mA_lo, mW;
+    int r = tc::make_tmap_2d_bf16_sw128(&mA_hi, in_hi, (uint64_t)P, C, ABOX, C);
+    PS_REQUIRE(r == 0, "ps_dec_composite_tc: cuTensorMapEncodeTiled(A_hi) failed (%d)", r);
+    r = tc::make_tmap_2d_bf16_sw128(&mA_lo, in_hi + P * C, (uint64_t)P, C, ABOX, C);
+    PS_REQUIRE(r == 0, "ps_dec_composite_tc: cuTensorMapEncodeTiled(A_lo) failed (%d)", r);
+    r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 9ull * 16, C, 9 * 16, C);
+    PS_REQUIRE(r == 0, "ps_dec_composite_tc: cuTensorMapEncodeTiled(W) failed (%d)", r);
+    cudaStream_t st = (cudaStream_t)stream;
+    return S <= 8 ? launch_comp_tc<8>(mA_hi, mA_lo, mW, p, st) : launch_comp_tc<16>(mA_hi, mA_lo, mW, p, st);
+}

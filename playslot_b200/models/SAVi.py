@@ -321,6 +321,15 @@ class SAVi(nn.Module):
                 ops.dec_expand_split(G, P_hwc, acts[0], n_img, H, W, k, prec)
                 for i, blk in enumerate(blocks[1:-1]):
                     ops.conv5x5_tc(acts[i], self._tc_weight(blk), blk.conv.bias, n_img, H, W, blk._relu, prec, act_out=acts[i + 1])
+                if not keep and prec == 3 and S <= 16:
+                    # inference: the last block stays in the split format and the 3x3 conv + slot softmax + compositing
+                    # run on the tensor cores too (no fp32 NCHW round trip of the 64-channel activation)
+                    last_in = acts[len(blocks) - 2]
+                    last_out = b if last_in is a else a                        # ping-pong workspaces
+                    ops.conv5x5_tc(acts[len(blocks) - 2], self._tc_weight(blocks[-1]), blocks[-1].conv.bias, n_img, H, W, blocks[-1]._relu, prec, act_out=last_out)
+                    r, rs, ms = ops.dec_composite_tc(last_out, self._final_packed_tc(final), final.bias, m1 - m0, S, H, W)
+                    recon_l.append(r); recons_l.append(rs); masks_l.append(ms)
+                    continue
                 h = torch.empty(n_img, 64, H, W, device=slots.device, dtype=torch.float32)
                 ops.conv5x5_tc(acts[len(blocks) - 2], self._tc_weight(blocks[-1]), blocks[-1].conv.bias, n_img, H, W, blocks[-1]._relu, prec, out_nchw=h)
             else:
@@ -377,6 +386,11 @@ class SAVi(nn.Module):
         if not hasattr(self, "_fin_cache"):
             self._fin_cache = DerivedWeights()
         return self._fin_cache.get([conv.weight], lambda: ops.pack_conv_weight(conv.weight))
+
+    def _final_packed_tc(self, conv):
+        if not hasattr(self, "_fin_tc_cache"):
+            self._fin_tc_cache = DerivedWeights()
+        return self._fin_tc_cache.get([conv.weight], lambda: ops.pack_final_conv_tc(conv.weight))
 
     def broadcast(self, slots):
         """ (B, S, D) -> (B*S, D, H, W): slot broadcast + position embedding (SAVi.py:237-248).  The decode

@@ -344,6 +344,38 @@ def dec_composite(h, w_packed, bias, M, S):
     return recon, recons, masks
 
 
+def pack_final_conv_tc(w):
+    """ final decoder conv weight (4, 64, 3, 3) -> (int16 (9 taps, 16 rows [4 hi | 4 zero | 4 lo | 4 zero], 64 cin), w_scale) """
+    Cout, Cin, K, _ = w.shape
+    assert (Cout, Cin, K) == (4, 64, 3), "the tensor-core compositing kernel covers the 64 -> 4 channel 3x3 convolution"
+    wt = w.detach().float().permute(2, 3, 0, 1).reshape(9, 4, 64)
+    amax = float(wt.abs().max())
+    scale = 1.0 if amax == 0.0 else 2.0 ** (-round(math.log2(amax)))
+    wt = wt * scale
+    h = wt.to(torch.float16)
+    lo = ((wt - h.float()) * TC_LO_SCALE).to(torch.float16)
+    out = torch.zeros(9, 16, 64, device=w.device, dtype=torch.float16)
+    out[:, 0:4] = h
+    out[:, 8:12] = lo
+    return out.view(torch.int16).contiguous(), scale
+
+
+def dec_composite_tc(act, w_packed, bias, M, S, H, W):
+    """ act: padded split planes of the last 5x5 block's output for M*S slot images -> (recon, recons, masks) """
+    lib = _lib.load()
+    w_tc, w_scale = w_packed
+    _req(bias, "bias")
+    dev = act.device
+    recon = torch.empty(M, 3, H, W, device=dev, dtype=torch.float32)
+    recons = torch.empty(M, S, 3, H, W, device=dev, dtype=torch.float32)
+    masks = torch.empty(M, S, 1, H, W, device=dev, dtype=torch.float32)
+    with _timed("dec_composite_tc"):
+        st = lib.ps_dec_composite_tc(_ptr(act), _ptr(w_tc), float(w_scale), _ptr(bias), _ptr(recon), _ptr(recons), _ptr(masks),
+                                     M, S, H, W, _stream())
+    _lib.check(st, "ps_dec_composite_tc")
+    return recon, recons, masks
+
+
 # ------------------------------------------------------------------------------------------------ InvDyn tail
 
 def invdyn_tail(mv, noise, codebook, per_slot, eps=1e-6):

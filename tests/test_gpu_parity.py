@@ -446,3 +446,37 @@ def test_graphed_seed_rollout_equals_eager():
     with FixedRandn(noise):
         eager2 = seed_rollout(savi, pred, v2, ns, npred)
     assert torch.equal(g(v2, noise=noise)["pred_imgs"], eager2["pred_imgs"])
+
+
+def test_config5_highres_many_slots_vs_oracle():
+    """ BASELINE.json configs[4] shapes: Sketchy hyper-parameters at 128x128, 16 slots, context 10 (N = 16384 feature tokens,
+    160 predictor tokens): a short clip through encode -> SlotAttention -> InvDyn -> rollout -> decode against the CPU oracle """
+    from playslot_b200 import configs
+    cfg = configs.experiment("Sketchy", num_slots=16, resolution=(128, 128))
+    scfg, pcfg = cfg["model"]["model_params"], cfg["predictor"]["predictor_params"]
+    savi_cpu, pred_cpu = configs.build_models(cfg, "cpu")
+    sman = {k: list(v.shape) for k, v in savi_cpu.state_dict().items()}
+    pman = {k: list(v.shape) for k, v in pred_cpu.state_dict().items()}
+    ssd, psd = synth_state_dict(sman, 31), synth_state_dict(pman, 131)
+    psd["dynamics_model.pos_emb.pe"] = pred_cpu.state_dict()["dynamics_model.pos_emb.pe"].clone()
+    savi = make_savi(scfg, ssd, DEV)
+    pred = make_predictor(cfg["predictor"]["predictor_name"], pcfg, psd, DEV)
+    B, ns, npred = 1, 3, 2
+    T = ns + npred
+    video = g(B, T, 3, 128, 128, seed=3).abs().clamp(max=1.0)
+    noise = g(B, T - 1, pcfg["action_dim"], seed=4)
+    with torch.no_grad():
+        out = savi(video.to(DEV), num_imgs=T, decode=False)
+        r_sh = O.savi_encode_video(ssd, scfg, video, T)
+        check("slot_history", out["slot_history"], r_sh)
+        sh_ref = r_sh.to(DEV)
+        with FixedRandn(noise):
+            ps, _ = pred.forward_multiple_samples(sh_ref, 1, ns, npred, use_posterior=True)
+        r_ps, r_act = O.posterior_rollout(psd, pcfg, r_sh, ns, npred, noise)
+        check("pred_slots", ps[:, 0], r_ps)
+        recon, (recons, masks) = savi.decode(r_ps[:, -1].to(DEV))
+        r_recon, r_recons, r_masks = O.decode(ssd, scfg, r_ps[:, -1])
+    assert recon.shape == (B, 3, 128, 128) and masks.shape == (B, 16, 1, 128, 128)
+    check("recon", recon, r_recon)
+    check("masks", masks, r_masks)
+    check("recons", recons, r_recons)
