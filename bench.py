@@ -182,6 +182,15 @@ def workload_config(batch_per_gpu, n_gpus):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 
+def ncu_traffic(kernel):
+    """ dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full capture
+    (profiles/r01_traffic.json), or None """
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
 def conv_flops(meta):
     n, cin, cout, H, W, k = meta
     return 2.0 * n * H * W * cin * cout * k * k
@@ -357,14 +366,22 @@ def run_ours(args):
                     "launches": dom[1]["calls"], "avg_launch_ms": dom[1]["ms"] / dom[1]["calls"]}
         if dom[0].startswith("conv5x5_tc_p3"):
             roofline["issued_tensor_TFLOPs"] = 3 * ach * (68.0 / 64.0)
+        tr = ncu_traffic(dom[0])
+        if tr:
+            n_imgs = sum(m[0] for m in dom[1]["meta"]) / max(dom[1]["calls"], 1)
+            roofline["traffic"] = tr["dram_bytes_per_launch"] / tr["images"] * n_imgs
+            roofline["traffic_note"] = (f"DRAM read+write of a {tr['images']}-image launch under ncu ({tr['dram_bytes_per_launch'] / 1e9:.2f} GB vs "
+                                        f"{tr['algorithmic_bytes'] / 1e9:.2f} GB algorithmic: one read + one write of the split planes), scaled to the "
+                                        f"average {n_imgs:.0f} images per launch of the timed region")
     sa_name = next((n for n in ("sa_main_tc2", "sa_main_tc", "sa_main") if n in prof), "sa_main")
     sa = prof.get(sa_name)
     roofline_sa = None
     if sa:
         by = sum(sa_main_bytes(m) for m in sa["meta"])
         ach = by / (sa["ms"] * 1e-3) / 1e9
+        tr_sa = ncu_traffic(sa_name)
         roofline_sa = {"kernel": sa_name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                       "frac": ach / pk["hbm_gbs"], "traffic": None, "launches": sa["calls"],
+                       "frac": ach / pk["hbm_gbs"], "traffic": tr_sa["dram_bytes_per_launch"] if tr_sa else None, "launches": sa["calls"],
                        "avg_launch_us": 1e3 * sa["ms"] / sa["calls"], "share_of_step": shares.get(sa_name),
                        "note": "one streaming pass of a SlotAttention iteration over 64 frames x 4096 tokens x 512 bytes (pre-normalised fp16 hi/lo "
                                "planes, read once) + masks; per-launch CUDA-event pairs inside the step add ~5 us to each ~30 us launch: "
