@@ -38,7 +38,7 @@ struct LinTcParams {
     const float* res; int ldres; int res_div; int res_mod;
     float* Y; int ldy;
     int M, N, K, nkb, npad;
-    int act, stages, bf16;
+    int act, stages, bf16, vec_out;
     float out_scale;
 };
 
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
         const int r_sub = tid >> 4;               // 0..15
         const int c4 = tid & 15;                  // float4 index inside the 64-wide K block
         const bool ln = p.ln_g != nullptr;
-        if (ln) {
+        const bool ln_fused = ln && p.K <= 128 && !PIPE;     // K <= 128: one load round serves statistics AND both K blocks
+        if (ln && !ln_fused) {
             // two-pass LayerNorm statistics, 16 lanes per row, 2 rows per round.  K <= 256: the row slice stays in
             // registers between the passes; larger K re-reads (L1-resident).
             const int nk = (p.K + 63) >> 6;
@@ -191,18 +192,86 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar_afull[s]);
         };
-        if (PIPE) {
+        if (ln_fused) {
+            // LayerNorm over K <= 128 (every transformer / encoder LayerNorm of the shipped configs): the 8 rows x 2 K-blocks
+            // a thread owns are loaded once, reduced over the 16 lanes of a row (two passes, in registers), normalised,
+            // split and stored -- no statistics pre-pass, no second read
+            float4 v[8][2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + i * 16 + r_sub;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int k = c * 64 + c4 * 4;
+                    v[i][c] = (m < p.M && k < p.K) ? *reinterpret_cast<const float4*>(p.X + (size_t)m * p.ldx + k)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            float mean[8], rstd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float sm_ = ((v[i][0].x + v[i][0].y) + (v[i][0].z + v[i][0].w)) + ((v[i][1].x + v[i][1].y) + (v[i][1].z + v[i][1].w));
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) sm_ += __shfl_xor_sync(0xffffffffu, sm_, o);
+                mean[i] = sm_ / (float)p.K;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float ss = 0.f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c * 64 + c4 * 4 < p.K) {
+                        const float a = v[i][c].x - mean[i], b = v[i][c].y - mean[i], cc = v[i][c].z - mean[i], d = v[i][c].w - mean[i];
+                        ss += (a * a + b * b) + (cc * cc + d * d);
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                rstd[i] = 1.0f / sqrtf(ss / (float)p.K + p.ln_eps);
+            }
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+                if (kb >= p.nkb) break;
+                const int s = kb % STAGES;
+                uint8_t* a_hi = smem + s * STAGE_BYTES;
+                uint8_t* a_lo = a_hi + A_TILE;
+                const int k = kb * KB + c4 * 4;
+                const bool k_ok = k < p.K;
+                float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k_ok) {
+                    g4 = *reinterpret_cast<const float4*>(p.ln_g + k);
+                    b4 = *reinterpret_cast<const float4*>(p.ln_b + k);
+                }
+                if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], ((kb / STAGES) - 1) & 1);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 16 + r_sub;
+                    float4 x = v[i][kb];
+                    x.x = (x.x - mean[i]) * rstd[i] * g4.x + b4.x; x.y = (x.y - mean[i]) * rstd[i] * g4.y + b4.y;
+                    x.z = (x.z - mean[i]) * rstd[i] * g4.z + b4.z; x.w = (x.w - mean[i]) * rstd[i] * g4.w + b4.w;
+                    if (!(m0 + row < p.M && k_ok)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int off = row * 128 + ((((c4 >> 1) ^ (row & 7))) << 4) + ((c4 & 1) << 3);
+                    split_store4<NSPLIT>(x, a_hi + off, a_lo + off, p.bf16 != 0);
+                }
+                tc::fence_async_proxy();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_afull[s]);
+            }
+        } else if (PIPE) {
             // long K (small-M rollout GEMMs, one CTA per SM): the loads of the next K block are in flight while this one
             // is normalised, split and stored
-            float4 va[8], vb[8];
-            load_kb(va, 0);
-            for (int kb = 0; kb < p.nkb; kb += 2) {
-                load_kb(vb, kb + 1);
-                store_kb(va, kb);
-                if (kb + 1 < p.nkb) {
-                    load_kb(va, kb + 2);
-                    store_kb(vb, kb + 1);
-                }
+            // (register ring of four K blocks: three loads are always in flight behind the block being converted)
+            float4 v0[8], v1[8], v2[8], v3[8];
+            load_kb(v0, 0); load_kb(v1, 1); load_kb(v2, 2);
+            for (int kb = 0; kb < p.nkb; kb += 4) {
+                load_kb(v3, kb + 3);
+                store_kb(v0, kb);
+                load_kb(v0, kb + 4);
+                if (kb + 1 < p.nkb) store_kb(v1, kb + 1);
+                load_kb(v1, kb + 5);
+                if (kb + 2 < p.nkb) store_kb(v2, kb + 2);
+                load_kb(v2, kb + 6);
+                if (kb + 3 < p.nkb) store_kb(v3, kb + 3);
             }
         } else {
             for (int kb = 0; kb < p.nkb; ++kb) {
@@ -235,6 +304,35 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
 #pragma unroll
             for (int j = 0; j < CW; ++j) scratch[lane * 33 + j] = v[j] * p.out_scale;
             __syncwarp();
+            if (CW == 32 && p.vec_out && n0 + col0 + 32 <= p.N) {
+                // lanes walk along rows in float4 pieces: one store instruction writes 4 rows x 128 bytes
+                const int rsub4 = lane >> 3, c4o = (lane & 7) * 4;
+                const int n = n0 + col0 + c4o;
+                float4 bv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) bv4 = *reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll 2
+                for (int r = 0; r < 32; r += 4) {
+                    const int row = q * 32 + r + rsub4;
+                    const int m = m0 + row;
+                    const float* sp = scratch + (r + rsub4) * 33 + c4o;
+                    float t[4] = {sp[0] + bv4.x, sp[1] + bv4.y, sp[2] + bv4.z, sp[3] + bv4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (p.act == 1) t[j] = fmaxf(t[j], 0.f);
+                        else if (p.act == 2) t[j] = gelu_erf(t[j]);
+                        else if (p.act == 3) t[j] = fabsf(t[j]);
+                    }
+                    if (m < p.M) {
+                        if (p.res) {
+                            const float4 rv = *reinterpret_cast<const float4*>(p.res + (size_t)((m / p.res_div) % p.res_mod) * p.ldres + n);
+                            t[0] += rv.x; t[1] += rv.y; t[2] += rv.z; t[3] += rv.w;
+                        }
+                        *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             // lanes now walk along a row: lane = column (two rows per instruction when CW == 16)
             constexpr int RPI = 32 / CW;                             // rows per instruction
             const int jj = lane % CW, rsub = lane / CW;
@@ -360,6 +458,7 @@ extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_s
     p.res = res; p.ldres = ldres; p.res_div = res_div > 0 ? res_div : 1; p.res_mod = res_mod > 0 ? res_mod : M;
     p.Y = Y; p.ldy = ldy; p.M = M; p.N = N; p.K = K; p.nkb = Kp / KB; p.npad = Npad;
     p.act = act; p.bf16 = precision == 1 ? 1 : 0; p.out_scale = 1.0f / w_scale;
+    p.vec_out = (ldy % 4 == 0 && ps_aligned16(Y) && (!bias || ps_aligned16(bias)) && (!res || (ldres % 4 == 0 && ps_aligned16(res)))) ? 1 : 0;
     // Column tile.  Every CTA normalises / splits its own copy of the 128-row activation tile, so narrow tiles multiply that
     // CUDA-core work: take the widest tile (<= 256) that still leaves about one CTA per two SMs.
     const long long mt = (M + BM - 1) / BM;
@@ -370,6 +469,11 @@ extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_s
     const int stage_bytes = nsplit * (A_TILE + bn * 128);
     int stages = (100 * 1024) / stage_bytes;         // at most ~100 KB per CTA: two CTAs per SM overlap each other's phases
     if (bn == 256) stages = 2;                       // 96 KB stages, one CTA per SM (its 512 TMEM columns fill the SM anyway)
+    if (mt * ((N + bn - 1) / bn) <= 148) {           // one CTA per SM anyway: use the shared memory for a deeper ring
+        stages = (200 * 1024) / stage_bytes;
+        if (stages < 1) stages = 1;
+        if (stages > LT_MAX_STAGES) stages = LT_MAX_STAGES;
+    }
     if (stages < 1) stages = 1;
     if (stages > LT_MAX_STAGES) stages = LT_MAX_STAGES;
     if (stages > p.nkb) stages = p.nkb;
