@@ -75,6 +75,10 @@ int ps_mha(const float* qkv, int ld, const float* res /* optional residual, laid
 int ps_conv2d(const float* x, const float* w_packed, const float* bias, const float* addend_nhwc, float* y,
               int n_img, int Cin, int Cout, int H, int W, int ksize, int relu, int out_nhwc, void* stream);
 
+/* ps_conv2d with Cout == 64 writing the padded NHWC split planes of ps_conv5x5_tc directly (first encoder convolution). */
+int ps_conv2d_split(const float* x, const float* w_packed, const float* bias, void* act_out, int n_img, int Cin, int H, int W,
+                    int ksize, int relu, int precision, void* stream);
+
 /* ---- SlotAttention (src/models/BlocksUtils/attention.py:76-119) ---------------------------------------- */
 
 /* floats per (frame, chunk) of the partial buffer used between ps_sa_main and ps_sa_update */

@@ -20,6 +20,7 @@ SIGNATURES = {
     "ps_linear_tc": (c_i, [c_f, c_i, c_f, c_fl, c_i, c_i, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_mha": (c_i, [c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_conv2d": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_conv2d_split": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_sa_partial_floats": (c_i, [c_i]),
     "ps_sa_main": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),
     "ps_sa_main_tc": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),

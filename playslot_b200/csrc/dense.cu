@@ -6,6 +6,8 @@
 // These are the exact-fp32 reference kernels of the library; the tcgen05 kernels are checked against them.
 #include "common.cuh"
 #include "../../include/playslot_b200.h"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 // ------------------------------------------------------------------------------------------------
 // linear
@@ -285,6 +287,9 @@ struct ConvParams {
     float* y;              // [n][Cout][H][W] or [n][H][W][Cout]
     int n, Cin, Cout, H, W;
     int relu, out_nhwc;
+    uint16_t* split_hi;    // out_nhwc == 2: zero-bordered NHWC 16-bit planes of the tensor-core convolutions (Cout == 64)
+    uint16_t* split_lo;    // null in the single-product modes
+    int split_bf16;
 };
 
 #define CV_T 16        // output tile is CV_T x CV_T pixels
@@ -370,7 +375,31 @@ __global__ __launch_bounds__(256) void conv2d_kernel(ConvParams p) {
             acc[i][j] = v;
         }
     }
-    if (!p.out_nhwc) {
+    if (p.out_nhwc == 2) {
+        if constexpr (COUT_T == 8) {
+            const int Wp = p.W + 4, Hp = p.H + 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const size_t o = (((size_t)img * Hp + oy + 2) * Wp + ox + i + 2) * 64 + cg * 8;
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = acc[i][2 * j], b = acc[i][2 * j + 1];
+                    if (p.split_bf16) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                        hw[j] = *reinterpret_cast<const uint32_t*>(&h2); lw[j] = 0;
+                    } else {
+                        const __half2 h2 = __floats2half2_rn(a, b);
+                        const float2 f = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn((a - f.x) * 2048.0f, (b - f.y) * 2048.0f);
+                        hw[j] = *reinterpret_cast<const uint32_t*>(&h2); lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                }
+                *reinterpret_cast<uint4*>(p.split_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                if (p.split_lo) *reinterpret_cast<uint4*>(p.split_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+        }
+    } else if (!p.out_nhwc) {
 #pragma unroll
         for (int j = 0; j < COUT_T; ++j) {
             const int co = cg * COUT_T + j;
@@ -425,12 +454,38 @@ extern "C" int ps_conv2d(const float* x, const float* w_packed, const float* bia
     PS_REQUIRE(!addend_nhwc || out_nhwc, "ps_conv2d: the addend is only supported with NHWC output");
     ConvParams p;
     p.x = x; p.wp = w_packed; p.bias = bias; p.addend = addend_nhwc; p.y = y;
-    p.n = n_img; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu; p.out_nhwc = out_nhwc;
+    p.n = n_img; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu; p.out_nhwc = out_nhwc ? 1 : 0;
+    p.split_hi = nullptr; p.split_lo = nullptr; p.split_bf16 = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (ksize == 5 && Cout == 64) return launch_conv<5, 8>(p, st);
     if (ksize == 5 && Cout == 32) return launch_conv<5, 4>(p, st);
     if (ksize == 3 && Cout == 64) return launch_conv<3, 8>(p, st);
     if (ksize == 3 && Cout == 32) return launch_conv<3, 4>(p, st);
     ps_set_error("ps_conv2d: unsupported ksize=%d Cout=%d (supported: ksize 3|5, Cout 32|64)", ksize, Cout);
+    return PS_EUNSUPPORTED;
+}
+
+// ps_conv2d writing the zero-bordered NHWC split planes consumed by ps_conv5x5_tc (Cout == 64): the first encoder
+// convolution feeds the tensor-core layers without an fp32 NCHW round trip.
+extern "C" int ps_conv2d_split(const float* x, const float* w_packed, const float* bias, void* act_out, int n_img, int Cin,
+                               int H, int W, int ksize, int relu, int precision, void* stream) {
+    PS_REQUIRE(x && w_packed && act_out, "ps_conv2d_split: null pointer");
+    PS_REQUIRE(precision >= 1 && precision <= 3, "ps_conv2d_split: precision must be 1, 2 or 3");
+    PS_REQUIRE(n_img >= 0 && Cin > 0, "ps_conv2d_split: bad shape");
+    if (n_img == 0) return PS_OK;
+    PS_REQUIRE(H % CV_T == 0 && W % CV_T == 0, "ps_conv2d_split: H and W must be multiples of %d (got %dx%d)", CV_T, H, W);
+    PS_REQUIRE(n_img <= 65535, "ps_conv2d_split: at most 65535 images per launch (got %d)", n_img);
+    PS_REQUIRE(ps_aligned16(x) && ps_aligned16(w_packed) && ps_aligned16(act_out), "ps_conv2d_split: pointers must be 16-byte aligned");
+    ConvParams p;
+    p.x = x; p.wp = w_packed; p.bias = bias; p.addend = nullptr; p.y = nullptr;
+    p.n = n_img; p.Cin = Cin; p.Cout = 64; p.H = H; p.W = W; p.relu = relu; p.out_nhwc = 2;
+    const long long P = (long long)n_img * (H + 4) * (W + 4);
+    p.split_hi = reinterpret_cast<uint16_t*>(act_out);
+    p.split_lo = precision == 3 ? p.split_hi + P * 64 : nullptr;
+    p.split_bf16 = precision == 1 ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ksize == 5) return launch_conv<5, 8>(p, st);
+    if (ksize == 3) return launch_conv<3, 8>(p, st);
+    ps_set_error("ps_conv2d_split: unsupported ksize=%d (supported: 3, 5)", ksize);
     return PS_EUNSUPPORTED;
 }

@@ -225,11 +225,16 @@ class SAVi(nn.Module):
         prec = ops.TC_PRECISION[self.conv_mode]
         blocks = list(self.encoder.encoder)
         M, _, H, W = x.shape
-        h = blocks[0].run(x)                                          # fp32 NCHW (M, 64, H, W)
         a = self._tc_workspace("enc_a", M, H, W, x.device)
         b = self._tc_workspace("enc_b", M, H, W, x.device)
-        ops.nchw_to_split(h, a, prec)
-        del h
+        c0 = blocks[0].conv
+        if M <= 65535 and H % 16 == 0 and W % 16 == 0:
+            # first conv (3 -> 64, FFMA) writes the split planes of the tensor-core layers directly
+            ops.conv2d_split(x, blocks[0].packed_weight(), c0.bias, c0.kernel_size[0], blocks[0]._relu, a, prec)
+        else:
+            h = blocks[0].run(x)                                      # fp32 NCHW (M, 64, H, W)
+            ops.nchw_to_split(h, a, prec)
+            del h
         for blk in blocks[1:-1]:
             ops.conv5x5_tc(a, self._tc_weight(blk), blk.conv.bias, M, H, W, blk._relu, prec, act_out=b)
             a, b = b, a

@@ -230,6 +230,18 @@ def conv2d(x, w_packed, bias, ksize, relu, out_nhwc=False, addend=None):
     return y
 
 
+def conv2d_split(x, w_packed, bias, ksize, relu, act_out, precision):
+    """ x (n, Cin, H, W) -> padded NHWC split planes (Cout == 64) in `act_out` """
+    lib = _lib.load()
+    _req(x, "x"); _req(w_packed, "w_packed")
+    n, Cin, H, W = x.shape
+    assert w_packed.shape[-1] == 64 and n <= 65535
+    with _timed("conv2d_%dx%d_%dto64_split" % (ksize, ksize, Cin), (n, Cin, 64, H, W, ksize)):
+        st = lib.ps_conv2d_split(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(act_out), n, Cin, H, W, ksize, int(relu), int(precision), _stream())
+    _lib.check(st, "ps_conv2d_split")
+    return act_out
+
+
 # ------------------------------------------------------------------------------------------------ SlotAttention
 
 def sa_partial_floats(S):
