@@ -185,7 +185,7 @@ class SAVi(nn.Module):
         x = f32c(x)
         M, _, H, W = x.shape
         posemb = self.encoder_pos_embedding.table(channels_last=True)
-        if self._tc_applicable(self.encoder.encoder, skip_first=True):
+        if self._tc_applicable(self.encoder.encoder, skip_first=True, channels=self.enc_tc_channels):
             tokens = self._encode_convs_tc(x, posemb)
         else:
             tokens = self.encoder.run(x, last_nhwc_addend=posemb)
@@ -195,16 +195,22 @@ class SAVi(nn.Module):
         return ops.linear(h, fc2.weight, fc2.bias)
 
     # --------------------------------------------------------------------------------------------- tensor-core convs
-    def _tc_applicable(self, blocks, skip_first):
-        """ the tcgen05 kernel covers plain 5x5, 64 -> 64 channel ConvBlocks """
+    enc_tc_channels = (32, 64)      # encoder widths routed to the tcgen05 convolution (32 is zero-padded to 64)
+
+    def _tc_applicable(self, blocks, skip_first, channels=(64,)):
+        """ the tcgen05 kernel covers plain 5x5, 64 -> 64 channel ConvBlocks; 32-channel encoder stacks run on it with
+        their weights zero-padded to 64 channels (4x the useful MMA work is still ~4x faster than the FFMA kernel) """
         if self.conv_mode not in ops.TC_PRECISION:
             return False
         blocks = list(blocks)[1:] if skip_first else list(blocks)
         if not blocks:
             return False
+        ch = blocks[0].conv.in_channels if getattr(blocks[0], "conv", None) is not None else None
+        if ch not in channels:
+            return False
         for b in blocks:
             c = getattr(b, "conv", None)
-            if c is None or not b._plain or c.kernel_size != (5, 5) or c.in_channels != 64 or c.out_channels != 64:
+            if c is None or not b._plain or c.kernel_size != (5, 5) or c.in_channels != ch or c.out_channels != ch:
                 return False
         return True
 
@@ -214,34 +220,81 @@ class SAVi(nn.Module):
             self._tc_ws[key] = ops.conv_tc_workspace(n_img, H, W, device)
         return self._tc_ws[key]
 
+    @staticmethod
+    def _pad64(w):
+        """ zero-pad a (Cout, Cin, k, k) weight to 64 x 64 channels """
+        if w.shape[0] == 64 and w.shape[1] == 64:
+            return w
+        out = torch.zeros(64, 64, *w.shape[2:], device=w.device, dtype=w.dtype)
+        out[:w.shape[0], :w.shape[1]] = w
+        return out
+
     def _tc_weight(self, block):
         prec = ops.TC_PRECISION[self.conv_mode]
         cache = self._tc_w.setdefault((id(block), prec), DerivedWeights())
         w = block.conv.weight
-        return cache.get([w], lambda: ops.pack_conv_weight_tc(w, prec))
+        return cache.get([w], lambda: ops.pack_conv_weight_tc(self._pad64(w.detach()), prec))
+
+    def _tc_first_conv(self, block):
+        """ (packed weight, bias) of the first encoder conv with its output channels zero-padded to 64 """
+        cache = self._tc_w.setdefault((id(block), "first"), DerivedWeights())
+        c = block.conv
+
+        def build():
+            w = c.weight.detach()
+            if w.shape[0] == 64:
+                return block.packed_weight(), c.bias.detach()
+            wp = torch.zeros(64, *w.shape[1:], device=w.device, dtype=w.dtype)
+            wp[:w.shape[0]] = w
+            bp = torch.zeros(64, device=w.device, dtype=w.dtype)
+            bp[:w.shape[0]] = c.bias.detach()
+            return ops.pack_conv_weight(wp), bp
+        return cache.get([c.weight, c.bias], build)
+
+    def _tc_bias64(self, block):
+        cache = self._tc_w.setdefault((id(block), "bias64"), DerivedWeights())
+        b = block.conv.bias
+
+        def build():
+            if b.shape[0] == 64:
+                return b.detach()
+            out = torch.zeros(64, device=b.device, dtype=b.dtype)
+            out[:b.shape[0]] = b.detach()
+            return out
+        return cache.get([b], build)
 
     def _encode_convs_tc(self, x, posemb):
-        """ first conv (3 -> 64) on the CUDA cores, the 64 -> 64 layers on tcgen05; tokens + posemb out """
+        """ first conv (3 -> C) on the CUDA cores writing the split planes, the C -> C layers on tcgen05; tokens + posemb out.
+        C = 32 stacks are zero-padded to 64 channels. """
         prec = ops.TC_PRECISION[self.conv_mode]
         blocks = list(self.encoder.encoder)
         M, _, H, W = x.shape
+        C = blocks[0].conv.out_channels
         a = self._tc_workspace("enc_a", M, H, W, x.device)
         b = self._tc_workspace("enc_b", M, H, W, x.device)
         c0 = blocks[0].conv
         if M <= 65535 and H % 16 == 0 and W % 16 == 0:
-            # first conv (3 -> 64, FFMA) writes the split planes of the tensor-core layers directly
-            ops.conv2d_split(x, blocks[0].packed_weight(), c0.bias, c0.kernel_size[0], blocks[0]._relu, a, prec)
+            # first conv (FFMA) writes the split planes of the tensor-core layers directly
+            w0, b0 = self._tc_first_conv(blocks[0])
+            ops.conv2d_split(x, w0, b0, c0.kernel_size[0], blocks[0]._relu, a, prec)
         else:
+            if C != 64:
+                raise NotImplementedError("32-channel encoders on the tensor-core path need H, W multiples of 16 and <= 65535 images per pass")
             h = blocks[0].run(x)                                      # fp32 NCHW (M, 64, H, W)
             ops.nchw_to_split(h, a, prec)
             del h
         for blk in blocks[1:-1]:
-            ops.conv5x5_tc(a, self._tc_weight(blk), blk.conv.bias, M, H, W, blk._relu, prec, act_out=b)
+            ops.conv5x5_tc(a, self._tc_weight(blk), self._tc_bias64(blk), M, H, W, blk._relu, prec, act_out=b)
             a, b = b, a
         last = blocks[-1]
+        if C != 64:
+            if not hasattr(self, "_posemb64"):
+                self._posemb64 = DerivedWeights()
+            pe = self.encoder_pos_embedding.projection
+            posemb = self._posemb64.get([pe.weight, pe.bias], lambda: torch.nn.functional.pad(posemb, (0, 64 - C)).contiguous())
         tokens = torch.empty(M, H * W, 64, device=x.device, dtype=torch.float32)
-        ops.conv5x5_tc(a, self._tc_weight(last), last.conv.bias, M, H, W, last._relu, prec, out_tokens=tokens, addend=posemb)
-        return tokens
+        ops.conv5x5_tc(a, self._tc_weight(last), self._tc_bias64(last), M, H, W, last._relu, prec, out_tokens=tokens, addend=posemb)
+        return tokens if C == 64 else tokens[..., :C].contiguous()
 
     # --------------------------------------------------------------------------------------------- decode
     def _decoder_constants(self):

@@ -334,7 +334,17 @@ def test_pipeline_matches_reference_golden(case, conv_mode, linear_mode_guard):
             out = savi(video.to(DEV), num_imgs=ns + npred, decode=False)
         sh = out["slot_history"]
         check("slot_history", sh, fx["slot_history"])
-        check("sa masks (last frame)", savi.slot_attention.get_attention_masks(), fx["sa_masks_last"])
+        sa_masks = savi.slot_attention.get_attention_masks()
+        if case.endswith("_sharp"):
+            # sharpened softmaxes: the reference's own fp32 masks sit 2.5e-5 (blockpush_sharp) away from the fp64
+            # evaluation; judge the CUDA path against that truth, relative to the reference's own rounding noise
+            sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in ssd.items()}
+            _, m64 = O.savi_encode_video(sd64, scfg, video.double(), ns + npred,
+                                         None if init_noise is None else init_noise.double(), return_masks=True)
+            check_conditioned("sa masks (last frame)", sa_masks, fx["sa_masks_last"], m64, factor=8.0)
+            check("sa masks (last frame)", sa_masks, fx["sa_masks_last"], 3e-4)
+        else:
+            check("sa masks (last frame)", sa_masks, fx["sa_masks_last"])
         # feed the reference's slots to the predictor so that stage errors do not compound in this check
         sh_ref = fx["slot_history"].to(DEV)
         with FixedRandn(noise):
