@@ -96,7 +96,8 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     __shared__ uint32_t tmem_base;
     __shared__ float s_bias[C];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay on the uniform datapath
     const int n_items = p.n_img * p.items_per_img;
 
     if (tid == 0) {
@@ -118,6 +119,8 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&mapA_hi);
             tc::tma_prefetch_desc(&mapW);
+            int ws = 0;                    // weight ring slot and the parity of its "empty" barrier, advanced per tap
+            uint32_t wph = 1;              // (a fresh barrier passes a wait on parity 1: the first STAGES loads do not block)
             int i = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
                 const int img = it / p.items_per_img;
@@ -125,11 +128,10 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 const int p0 = 2 * p.Wp + item * NPOS;
                 const int g0 = (int)((long long)img * p.Hp * p.Wp + p0 - p.halo);
                 auto load_w = [&](int tap) {
-                    const int g = i * 25 + tap;
-                    const int s = g % STAGES;
-                    if (g >= STAGES) tc::mbar_wait(&bar_wempty[s], ((g / STAGES) - 1) & 1);
-                    tc::mbar_expect_tx(&bar_wfull[s], NSPLIT * WTAP_BYTES);
-                    tc::tma_load_2d(sW + s * NSPLIT * WTAP_BYTES, &mapW, &bar_wfull[s], 0, tap * 128);
+                    tc::mbar_wait(&bar_wempty[ws], wph);
+                    tc::mbar_expect_tx(&bar_wfull[ws], NSPLIT * WTAP_BYTES);
+                    tc::tma_load_2d(sW + ws * NSPLIT * WTAP_BYTES, &mapW, &bar_wfull[ws], 0, tap * 128);
+                    if (++ws == STAGES) { ws = 0; wph ^= 1u; }
                 };
                 // the first weight taps of this item stream in while the previous item's last MMAs still run
                 for (int tap = 0; tap < STAGES; ++tap) load_w(tap);
@@ -144,61 +146,73 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (tc::elect_one()) {
+        // The whole warp walks the loop (uniform control flow and uniform-register address arithmetic); one elected lane
+        // issues the MMAs and the commits.
+        const bool leader = tc::elect_one();
+        {
             const uint32_t idesc = p.bf16 ? tc::umma_idesc_bf16(TILE_M, C) : tc::umma_idesc_f16(TILE_M, C);
             const uint32_t idesc2 = tc::umma_idesc_f16(TILE_M, 2 * C);
-            // Descriptors are built once: per MMA only the 14-bit start-address field changes, so the issue loop adds a
-            // (16-byte unit) offset to the low word -- the single issuing thread must not become the bottleneck.
-            const uint32_t a_base[2] = {tc::smem_u32(sA[0]), tc::smem_u32(sA[1])};
-            const uint32_t w_base = tc::smem_u32(sW);
-            uint64_t adesc[2][TILES][C / 16];
-#pragma unroll
-            for (int pl = 0; pl < 2; ++pl)
-#pragma unroll
-                for (int tile = 0; tile < TILES; ++tile)
-#pragma unroll
-                    for (int k = 0; k < C / 16; ++k)
-                        adesc[pl][tile][k] = tc::umma_desc_sw128(a_base[pl] + (uint32_t)(p.halo + tile * TILE_M) * ROWB + k * 32, 1024, 0);
-            const uint64_t bdesc0 = tc::umma_desc_sw128(w_base, 1024, 0);
+            // The single issuing thread must not become the bottleneck (the MMA queue is shallow: scalar work between two
+            // MMAs that takes longer than the queued MMAs idles the tensor pipe).  So: descriptors are built once and per
+            // MMA only a compile-time constant is added to the 14-bit start-address field (16-byte units); ring slots,
+            // parities and tap shifts are advanced incrementally (no division by the run-time stage count); and the wait
+            // for the NEXT tap's weights is issued in the middle of the current tap's MMAs.
+            const uint64_t a_hi0 = tc::umma_desc_sw128(tc::smem_u32(sA[0]) + (uint32_t)p.halo * ROWB, 1024, 0);
+            const uint64_t a_lo0 = tc::umma_desc_sw128(tc::smem_u32(sA[1]) + (uint32_t)p.halo * ROWB, 1024, 0);
+            const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(sW), 1024, 0);
+            constexpr uint64_t TILE_UNITS = (uint64_t)TILE_M * ROWB / 16;             // descriptor units between the tiles
+            constexpr uint64_t STAGE_UNITS = (uint64_t)NSPLIT * WTAP_BYTES / 16;
+            const int row_step = (p.Wp - 5) * (ROWB / 16);                            // ky -> ky+1 after five kx steps
+            int ws = 0;
+            uint32_t wph = 0;
             int i = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
                 const int buf = i & 1;
                 if (i >= 2) tc::mbar_wait(&bar_accempty[buf], ((i >> 1) - 1) & 1);   // epilogue drained this accumulator buffer
                 tc::mbar_wait(&bar_afull, i & 1);
+                tc::mbar_wait(&bar_wfull[ws], wph);                                  // weights of tap 0
                 tc::tc_fence_after();
-                int g = i * 25;
+                int a_off = (-2 * p.Wp - 2) * (ROWB / 16);                           // tap (0, 0) shift, 16-byte units
+                const uint32_t acc_buf = tm + buf * ACC_COLS;
+#pragma unroll 1
                 for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
-                    for (int kx = 0; kx < 5; ++kx, ++g) {
-                        const int s = g % STAGES;
-                        tc::mbar_wait(&bar_wfull[s], (g / STAGES) & 1);
-                        tc::tc_fence_after();
-                        const int64_t a_off = (int64_t)(((ky - 2) * p.Wp + (kx - 2)) * (ROWB / 16));     // tap shift, 16-byte units
-                        const uint64_t b_st = bdesc0 + (uint64_t)(s * NSPLIT * (WTAP_BYTES / 16));
+                    for (int kx = 0; kx < 5; ++kx) {
+                        const uint64_t a_hi = a_hi0 + (uint64_t)(int64_t)a_off;
+                        const uint64_t a_lo = a_lo0 + (uint64_t)(int64_t)a_off;
+                        const uint64_t b_st = bdesc0 + (uint64_t)ws * STAGE_UNITS;
+                        uint64_t* const done_bar = &bar_wempty[ws];
+                        if (++ws == STAGES) { ws = 0; wph ^= 1u; }
 #pragma unroll
                         for (int tile = 0; tile < TILES; ++tile) {
-                            const uint32_t acc0 = tm + buf * ACC_COLS + tile * NSPLIT * C;   // D0 | D1 are adjacent: 2 x 64 columns
+                            const uint32_t acc0 = acc_buf + tile * NSPLIT * C;        // D0 | D1 are adjacent: 2 x 64 columns
 #pragma unroll
                             for (int k = 0; k < C / 16; ++k) {
                                 const uint32_t first = (ky | kx | k) ? 1u : 0u;
-                                const uint64_t a_hi = adesc[0][tile][k] + a_off;
-                                const uint64_t b_hi = b_st + (uint64_t)(k * 2);
                                 if (NSPLIT == 2) {
                                     // one N=128 MMA against [W_hi ; W_lo] (the two weight tiles are adjacent in the stage):
                                     // D0 += A_hi W_hi and D1 += A_hi W_lo share a single read of A_hi; then D1 += A_lo W_hi.
                                     // 14 KB of shared-memory operand traffic per k-step instead of 18 KB for three N=64 MMAs.
-                                    tc::umma_bf16(acc0, a_hi, b_hi, idesc2, first);
-                                    tc::umma_bf16(acc0 + C, adesc[1][tile][k] + a_off, b_hi, idesc, 1u);
+                                    if (leader) tc::umma_bf16(acc0, a_hi + (tile * TILE_UNITS + k * 2), b_st + k * 2, idesc2, first);
+                                    if (leader) tc::umma_bf16(acc0 + C, a_lo + (tile * TILE_UNITS + k * 2), b_st + k * 2, idesc, 1u);
                                 } else {
-                                    tc::umma_bf16(acc0, a_hi, b_hi, idesc, first);
+                                    if (leader) tc::umma_bf16(acc0, a_hi + (tile * TILE_UNITS + k * 2), b_st + k * 2, idesc, first);
                                 }
                             }
+                            if (tile == 0 && !(ky == 4 && kx == 4)) {
+                                // the next tap's weights: normally long there (ring of STAGES taps); checked here, with
+                                // this tap's MMAs still queued, so that the check costs no tensor-pipe time
+                                tc::mbar_wait(&bar_wfull[ws], wph);
+                                tc::tc_fence_after();
+                            }
                         }
-                        tc::umma_commit(&bar_wempty[s]);       // frees the weight stage once these MMAs retire
+                        if (leader) tc::umma_commit(done_bar);             // frees the weight stage once these MMAs retire
+                        a_off += ROWB / 16;
                     }
+                    a_off += row_step;
                 }
-                tc::umma_commit(&bar_aempty);              // the activation region may be overwritten
-                tc::umma_commit(&bar_accfull[buf]);        // the accumulators of this item are complete
+                if (leader) tc::umma_commit(&bar_aempty);              // the activation region may be overwritten
+                if (leader) tc::umma_commit(&bar_accfull[buf]);        // the accumulators of this item are complete
             }
         }
     } else {

@@ -23,4 +23,16 @@ if what in ("all", "sa"):
         for _ in range(2):
             m(feats, slots, step=0)
     torch.cuda.synchronize()
+if what in ("conv", "dec"):
+    # decoder-sized launches: 4092 slot images 64x64 through the tensor-core convolution and the compositing kernel
+    n, H, W = 4092, 64, 64
+    a0 = ops.conv_tc_workspace(n, H, W, "cuda"); a1 = ops.conv_tc_workspace(n, H, W, "cuda")
+    x = torch.randn(n, 64, H, W, device="cuda")
+    ops.nchw_to_split(x, a0, 3)
+    del x
+    w = torch.randn(64, 64, 5, 5, device="cuda") * 0.03; b = torch.randn(64, device="cuda") * 0.1
+    wp = ops.pack_conv_weight_tc(w, 3)
+    for _ in range(3):
+        ops.conv5x5_tc(a0, wp, b, n, H, W, True, 3, act_out=a1)
+    torch.cuda.synchronize()
 print("done")
