@@ -69,7 +69,10 @@ struct ConvTcParams {
     float* out_f32;          // mode 1 (NCHW) / mode 2 (NHWC)
     int n_img, H, W, Wp, Hp;
     int items_per_img;       // work items (NPOS positions each) per image
-    int halo, a_rows;        // halo rows on each side, staged A rows (multiple of ABOX)
+    int halo, a_rows;        // halo rows on each side, rows reserved per staged plane (multiple of 64: 1024-byte aligned regions)
+    int chunk_b[6];          // the staged region is (re)filled in five row chunks [chunk_b[c], chunk_b[c+1]): chunk c < 4 is dead once
+                             // the taps of filter row ky = c have been issued, chunk 4 at the end of the item
+    int n_early;             // chunks the first filter row needs (4, or 5 when the image is too narrow to split)
     int stages;              // weight ring depth (2..MAX_STAGES)
     int n_ctas;              // persistent grid size (one CTA per SM)
     int relu, out_mode;
@@ -83,6 +86,7 @@ struct ConvTcParams {
 template <int TILES, int NSPLIT>
 __global__ void __launch_bounds__(192, 1)
 conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                  const __grid_constant__ CUtensorMap mapA_hi8, const __grid_constant__ CUtensorMap mapA_lo8,
                   const __grid_constant__ CUtensorMap mapW, const ConvTcParams p) {
     constexpr int NPOS = TILE_M * TILES;
     constexpr uint32_t ACC_COLS = 64 * TILES * NSPLIT;      // TMEM columns of one accumulator buffer
@@ -91,7 +95,7 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     const int a_bytes = p.a_rows * ROWB;
     uint8_t* sA[2] = {smem, smem + a_bytes};
     uint8_t* sW = smem + NSPLIT * a_bytes;                 // stages x NSPLIT x 8 KB
-    __shared__ uint64_t bar_afull, bar_aempty, bar_wfull[MAX_STAGES], bar_wempty[MAX_STAGES], bar_accfull[2], bar_accempty[2];
+    __shared__ uint64_t bar_afull[2], bar_aempty[5], bar_wfull[MAX_STAGES], bar_wempty[MAX_STAGES], bar_accfull[2], bar_accempty[2];
     const int STAGES = p.stages;
     __shared__ uint32_t tmem_base;
     __shared__ float s_bias[C];
@@ -101,8 +105,8 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     const int n_items = p.n_img * p.items_per_img;
 
     if (tid == 0) {
-        tc::mbar_init(&bar_afull, 1);
-        tc::mbar_init(&bar_aempty, 1);
+        for (int b = 0; b < 2; ++b) tc::mbar_init(&bar_afull[b], 1);
+        for (int c = 0; c < 5; ++c) tc::mbar_init(&bar_aempty[c], 1);
         for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_accfull[b], 1); tc::mbar_init(&bar_accempty[b], 4); }
         for (int s = 0; s < MAX_STAGES; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
         tc::fence_mbar_init();
@@ -121,27 +125,58 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
             tc::tma_prefetch_desc(&mapW);
             int ws = 0;                    // weight ring slot and the parity of its "empty" barrier, advanced per tap
             uint32_t wph = 1;              // (a fresh barrier passes a wait on parity 1: the first STAGES loads do not block)
-            int i = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+            auto region_row0 = [&](int it) {                        // first global row of the staged region of work item `it`
                 const int img = it / p.items_per_img;
                 const int item = it - img * p.items_per_img;
-                const int p0 = 2 * p.Wp + item * NPOS;
-                const int g0 = (int)((long long)img * p.Hp * p.Wp + p0 - p.halo);
-                auto load_w = [&](int tap) {
+                return (int)((long long)img * p.Hp * p.Wp + 2 * p.Wp + item * NPOS - p.halo);
+            };
+            // chunk c of the region of an item: 32-row boxes, then 8-row boxes up to the chunk end (both multiples of 8 rows)
+            auto load_chunk = [&](int g0, int c) {
+                const int fb = c < p.n_early ? 0 : 1;
+                if (c == 0 || c == p.n_early) {
+                    const int rows = c == 0 ? p.chunk_b[p.n_early] : p.chunk_b[5] - p.chunk_b[p.n_early];
+                    tc::mbar_expect_tx(&bar_afull[fb], (uint32_t)(NSPLIT * rows * ROWB));
+                }
+                int r = p.chunk_b[c];
+                const int r1 = p.chunk_b[c + 1];
+                for (; r + ABOX <= r1; r += ABOX) {
+                    tc::tma_load_2d(sA[0] + r * ROWB, &mapA_hi, &bar_afull[fb], 0, g0 + r);
+                    if (NSPLIT == 2) tc::tma_load_2d(sA[1] + r * ROWB, &mapA_lo, &bar_afull[fb], 0, g0 + r);
+                }
+                for (; r < r1; r += 8) {
+                    tc::tma_load_2d(sA[0] + r * ROWB, &mapA_hi8, &bar_afull[fb], 0, g0 + r);
+                    if (NSPLIT == 2) tc::tma_load_2d(sA[1] + r * ROWB, &mapA_lo8, &bar_afull[fb], 0, g0 + r);
+                }
+            };
+            int i = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+                const int g0 = region_row0(it);
+                const bool has_next = it + (int)gridDim.x < n_items;
+                const int g0_next = has_next ? region_row0(it + gridDim.x) : 0;
+                if (i == 0)
+                    for (int c = 0; c < 5; ++c) load_chunk(g0, c);
+                for (int tap = 0; tap < 25; ++tap) {
                     tc::mbar_wait(&bar_wempty[ws], wph);
                     tc::mbar_expect_tx(&bar_wfull[ws], NSPLIT * WTAP_BYTES);
                     tc::tma_load_2d(sW + ws * NSPLIT * WTAP_BYTES, &mapW, &bar_wfull[ws], 0, tap * 128);
                     if (++ws == STAGES) { ws = 0; wph ^= 1u; }
-                };
-                // the first weight taps of this item stream in while the previous item's last MMAs still run
-                for (int tap = 0; tap < STAGES; ++tap) load_w(tap);
-                if (i > 0) tc::mbar_wait(&bar_aempty, (i - 1) & 1);            // MMAs of the previous item have read the region
-                tc::mbar_expect_tx(&bar_afull, (uint32_t)(NSPLIT * a_bytes));
-                for (int r = 0; r < p.a_rows; r += ABOX) {
-                    tc::tma_load_2d(sA[0] + r * ROWB, &mapA_hi, &bar_afull, 0, g0 + r);
-                    if (NSPLIT == 2) tc::tma_load_2d(sA[1] + r * ROWB, &mapA_lo, &bar_afull, 0, g0 + r);
+                    // Region refill, interleaved with the weight stream at the points where the MMA warp is known to be past the
+                    // rows in question (it has consumed tap - STAGES when the wait above returns), so these waits do not stall
+                    // the weight ring: chunk 4 of THIS item once the previous item is finished, chunks 0..3 of the NEXT item as
+                    // the filter rows of this item retire.  The next item's first filter row only reads chunks 0..3.
+                    if (i > 0 && tap == STAGES - 1) {
+                        tc::mbar_wait(&bar_aempty[4], (i - 1) & 1);
+                        load_chunk(g0, 4);
+                    }
+                    if (has_next) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (tap == 5 * c + 4 + STAGES) {                     // <= 23: STAGES <= MAX_STAGES = 4
+                                tc::mbar_wait(&bar_aempty[c], i & 1);
+                                load_chunk(g0_next, c);
+                            }
+                    }
                 }
-                for (int tap = STAGES; tap < 25; ++tap) load_w(tap);
             }
         }
     } else if (warp == 1) {
@@ -169,7 +204,7 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
                 const int buf = i & 1;
                 if (i >= 2) tc::mbar_wait(&bar_accempty[buf], ((i >> 1) - 1) & 1);   // epilogue drained this accumulator buffer
-                tc::mbar_wait(&bar_afull, i & 1);
+                tc::mbar_wait(&bar_afull[0], i & 1);                                 // the rows the first filter row reads
                 tc::mbar_wait(&bar_wfull[ws], wph);                                  // weights of tap 0
                 tc::tc_fence_after();
                 int a_off = (-2 * p.Wp - 2) * (ROWB / 16);                           // tap (0, 0) shift, 16-byte units
@@ -210,8 +245,12 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                         a_off += ROWB / 16;
                     }
                     a_off += row_step;
+                    if (leader) tc::umma_commit(&bar_aempty[ky]);      // region chunk ky is dead (chunk 4: the rest of the region)
+                    if (ky == 0 && p.n_early < 5) {
+                        tc::mbar_wait(&bar_afull[1], i & 1);           // the remaining rows (loaded while filter row 0 was issued)
+                        tc::tc_fence_after();
+                    }
                 }
-                if (leader) tc::umma_commit(&bar_aempty);              // the activation region may be overwritten
                 if (leader) tc::umma_commit(&bar_accfull[buf]);        // the accumulators of this item are complete
             }
         }
@@ -308,8 +347,8 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
 }
 
 template <int TILES, int NSPLIT>
-int launch_conv_tc(const CUtensorMap& mA_hi, const CUtensorMap& mA_lo, const CUtensorMap& mW, const ConvTcParams& p,
-                   cudaStream_t st) {
+int launch_conv_tc(const CUtensorMap& mA_hi, const CUtensorMap& mA_lo, const CUtensorMap& mA_hi8, const CUtensorMap& mA_lo8,
+                   const CUtensorMap& mW, const ConvTcParams& p, cudaStream_t st) {
     const size_t smem = (size_t)NSPLIT * p.a_rows * ROWB + (size_t)p.stages * NSPLIT * WTAP_BYTES + 1024;
     PS_REQUIRE(smem <= 227 * 1024, "ps_conv5x5_tc: image width %d needs %zu bytes of shared memory", p.W, smem);
     static size_t configured = 0;
@@ -318,7 +357,7 @@ int launch_conv_tc(const CUtensorMap& mA_hi, const CUtensorMap& mA_lo, const CUt
         configured = smem;
     }
     const int n_items = p.n_img * p.items_per_img;
-    conv5x5_tc_kernel<TILES, NSPLIT><<<n_items < p.n_ctas ? n_items : p.n_ctas, 192, smem, st>>>(mA_hi, mA_lo, mW, p);
+    conv5x5_tc_kernel<TILES, NSPLIT><<<n_items < p.n_ctas ? n_items : p.n_ctas, 192, smem, st>>>(mA_hi, mA_lo, mA_hi8, mA_lo8, mW, p);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;
@@ -365,6 +404,11 @@ static int conv5x5_tc_run(const void* act_in, const void* w_tc, const float* bia
     p.n_img = n_img; p.H = H; p.W = W; p.Wp = Wp; p.Hp = Hp;
     p.items_per_img = (H * Wp + TILE_M * tiles - 1) / (TILE_M * tiles);
     p.halo = halo; p.a_rows = a_rows_for(tiles); p.stages = stages_for(tiles);
+    // refill chunks: rows below Wp * (c + 1) are dead after filter row c (rounded down to the 8-row swizzle atom)
+    p.chunk_b[0] = 0;
+    for (int c = 0; c < 4; ++c) p.chunk_b[c + 1] = Wp * (c + 1) / 8 * 8;
+    p.chunk_b[5] = (TILE_M * tiles + 2 * halo + 7) / 8 * 8;
+    p.n_early = (TILE_M * tiles + 4 <= p.chunk_b[4]) ? 4 : 5;
     p.relu = relu; p.out_mode = out_mode;
     {
         int dev = 0, sms = 148;
@@ -372,17 +416,22 @@ static int conv5x5_tc_run(const void* act_in, const void* w_tc, const float* bia
         p.n_ctas = sms;
     }
     const uint16_t* in_hi = reinterpret_cast<const uint16_t*>(act_in);
-    CUtensorMap mA_hi, mA_lo, mW;
+    CUtensorMap mA_hi, mA_lo, mA_hi8, mA_lo8, mW;
+    const uint16_t* in_lo = precision == 3 ? in_hi + P * C : in_hi;
     int r = tc::make_tmap_2d_bf16_sw128(&mA_hi, in_hi, (uint64_t)P, C, ABOX, C);
     PS_REQUIRE(r == 0, "ps_conv5x5_tc: cuTensorMapEncodeTiled(A_hi) failed (%d)", r);
-    r = tc::make_tmap_2d_bf16_sw128(&mA_lo, precision == 3 ? in_hi + P * C : in_hi, (uint64_t)P, C, ABOX, C);
+    r = tc::make_tmap_2d_bf16_sw128(&mA_lo, in_lo, (uint64_t)P, C, ABOX, C);
     PS_REQUIRE(r == 0, "ps_conv5x5_tc: cuTensorMapEncodeTiled(A_lo) failed (%d)", r);
+    r = tc::make_tmap_2d_bf16_sw128(&mA_hi8, in_hi, (uint64_t)P, C, 8, C);
+    PS_REQUIRE(r == 0, "ps_conv5x5_tc: cuTensorMapEncodeTiled(A_hi, 8 rows) failed (%d)", r);
+    r = tc::make_tmap_2d_bf16_sw128(&mA_lo8, in_lo, (uint64_t)P, C, 8, C);
+    PS_REQUIRE(r == 0, "ps_conv5x5_tc: cuTensorMapEncodeTiled(A_lo, 8 rows) failed (%d)", r);
     // weights: [25 taps][2 (hi, lo)][64 cout][64 cin]; the single-product modes load the hi half of each tap only
     r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 25ull * 2 * 64, C, 64 * nsplit, C);
     PS_REQUIRE(r == 0, "ps_conv5x5_tc: cuTensorMapEncodeTiled(W) failed (%d)", r);
     cudaStream_t st = (cudaStream_t)stream;
-    if (tiles == 2) return nsplit == 2 ? launch_conv_tc<2, 2>(mA_hi, mA_lo, mW, p, st) : launch_conv_tc<2, 1>(mA_hi, mA_lo, mW, p, st);
-    return nsplit == 2 ? launch_conv_tc<1, 2>(mA_hi, mA_lo, mW, p, st) : launch_conv_tc<1, 1>(mA_hi, mA_lo, mW, p, st);
+    if (tiles == 2) return nsplit == 2 ? launch_conv_tc<2, 2>(mA_hi, mA_lo, mA_hi8, mA_lo8, mW, p, st) : launch_conv_tc<2, 1>(mA_hi, mA_lo, mA_hi8, mA_lo8, mW, p, st);
+    return nsplit == 2 ? launch_conv_tc<1, 2>(mA_hi, mA_lo, mA_hi8, mA_lo8, mW, p, st) : launch_conv_tc<1, 1>(mA_hi, mA_lo, mA_hi8, mA_lo8, mW, p, st);
 }
 
 extern "C" int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* bias, float w_scale, void* act_out,
