@@ -253,6 +253,157 @@ __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
     }
 }
 
+// Register-tiled variant for head_dim % 4 == 0 (every shipped config): one CTA per (sequence, head), 128 threads.
+//   S = scale * Q K^T : thread tile 3 query rows x 6 keys, operands read as LDS.128 along the head dimension (9 loads per 72 FMAs);
+//                       rows / keys of a thread are strided (i = ty + nTy*r, j = tx + nTx*c) so that the 128-bit loads of a warp
+//                       fall into distinct banks with the (dh + 4)-float row pitch
+//   P = softmax(S)    : one warp per row, written transposed (Pt[j][i]) for the next stage
+//   O = P V           : thread tile 6 consecutive rows x 4 consecutive head columns (3 LDS.64 + 1 LDS.128 per 24 FMAs)
+// For the cOCVP shape (L = 48, dh = 64) both stages use all 128 threads exactly once.
+#define MHA_RT 3
+#define MHA_CT 6
+__global__ __launch_bounds__(128) void mha_tiled_kernel(MhaParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int seq = blockIdx.x, h = blockIdx.y;
+    const int L = p.L, dh = p.dh, inner = p.H * dh;
+    const int L6 = (L + 5) / 6 * 6;            // padded row count of Q / K (zero rows) and of the transposed probabilities
+    const int pitch = dh + 4;
+    const int Lt = (L6 + 3) & ~3;              // pitch of Pt rows (16-byte aligned)
+    float* Qs = sm;                            // [L6][pitch]; reused as Pt [L][Lt] after the first stage
+    float* Ks = Qs + max(L6 * pitch, L * Lt);  // [L6][pitch]
+    float* Vs = Ks + L6 * pitch;               // [L][dh]
+    float* Ss = Vs + L * dh;                   // [L][L + 1]
+    int* frame = reinterpret_cast<int*>(Ss + L * (L + 1));     // [L6]: frame index of a token (block-causal mask), 0 when unmasked
+    const float* base = p.qkv + (size_t)seq * L * p.ld + h * dh;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int dq = dh >> 2;
+    for (int j = tid; j < L6; j += 128) frame[j] = p.spf > 0 ? j / p.spf : 0;
+    for (int idx0 = tid; idx0 < L6 * dq; idx0 += 128 * 4) {
+        float4 q[4], k[4], v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                          // 12 independent 16-byte loads in flight per thread
+            const int idx = idx0 + u * 128;
+            const int j = idx / dq, d4 = (idx - j * dq) * 4;
+            q[u] = k[u] = v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < L6 * dq && j < L) {
+                const float* row = base + (size_t)j * p.ld + d4;
+                q[u] = __ldg(reinterpret_cast<const float4*>(row));
+                k[u] = __ldg(reinterpret_cast<const float4*>(row + inner));
+                v[u] = __ldg(reinterpret_cast<const float4*>(row + 2 * inner));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * 128;
+            const int j = idx / dq, d4 = (idx - j * dq) * 4;
+            if (idx < L6 * dq) {
+                *reinterpret_cast<float4*>(Qs + j * pitch + d4) = q[u];
+                *reinterpret_cast<float4*>(Ks + j * pitch + d4) = k[u];
+                if (j < L) *reinterpret_cast<float4*>(Vs + j * dh + d4) = v[u];
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int nTy = L6 / MHA_RT, nTx = L6 / MHA_CT;
+        for (int t = tid; t < nTy * nTx; t += 128) {
+            const int ty = t / nTx, tx = t - ty * nTx;
+            float acc[MHA_RT][MHA_CT];
+#pragma unroll
+            for (int r = 0; r < MHA_RT; ++r)
+#pragma unroll
+                for (int c = 0; c < MHA_CT; ++c) acc[r][c] = 0.f;
+            const float* qr = Qs + ty * pitch;
+            const float* kr = Ks + tx * pitch;
+            const int qstep = nTy * pitch, kstep = nTx * pitch;
+#pragma unroll 2
+            for (int d = 0; d < dh; d += 4) {
+                float4 q[MHA_RT], k[MHA_CT];
+#pragma unroll
+                for (int r = 0; r < MHA_RT; ++r) q[r] = *reinterpret_cast<const float4*>(qr + r * qstep + d);
+#pragma unroll
+                for (int c = 0; c < MHA_CT; ++c) k[c] = *reinterpret_cast<const float4*>(kr + c * kstep + d);
+#pragma unroll
+                for (int r = 0; r < MHA_RT; ++r)
+#pragma unroll
+                    for (int c = 0; c < MHA_CT; ++c) {
+                        acc[r][c] = fmaf(q[r].x, k[c].x, acc[r][c]);
+                        acc[r][c] = fmaf(q[r].y, k[c].y, acc[r][c]);
+                        acc[r][c] = fmaf(q[r].z, k[c].z, acc[r][c]);
+                        acc[r][c] = fmaf(q[r].w, k[c].w, acc[r][c]);
+                    }
+            }
+#pragma unroll
+            for (int r = 0; r < MHA_RT; ++r) {
+                const int i = ty + nTy * r;
+                const int fi = frame[i];
+#pragma unroll
+                for (int c = 0; c < MHA_CT; ++c) {
+                    const int j = tx + nTx * c;
+                    if (i < L && j < L)
+                        Ss[i * (L + 1) + j] = frame[j] > fi ? -1e9f : acc[r][c] * p.scale;   // masked_fill(mask == 0, -1e9)
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float* Pt = Qs;                            // [L][Lt]: Pt[j][i], columns i >= L zero
+    for (int i = w; i < Lt; i += 4) {
+        if (i >= L) {
+            for (int j = lane; j < L; j += 32) Pt[j * Lt + i] = 0.f;
+            continue;
+        }
+        float mx = -INFINITY;
+        for (int j = lane; j < L; j += 32) mx = fmaxf(mx, Ss[i * (L + 1) + j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < L; j += 32) {
+            const float e = expf(Ss[i * (L + 1) + j] - mx);
+            Ss[i * (L + 1) + j] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / warp_sum(sum);
+        for (int j = lane; j < L; j += 32) Pt[j * Lt + i] = Ss[i * (L + 1) + j] * inv;
+    }
+    __syncthreads();
+    {
+        const int nTy = L6 / 6;
+        for (int t = tid; t < nTy * dq; t += 128) {
+            const int ty = t / dq, tx = t - ty * dq;
+            float acc[6][4];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+            const float* pr = Pt + ty * 6;
+            const float* vr = Vs + tx * 4;
+#pragma unroll 4
+            for (int j = 0; j < L; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(vr + j * dh);
+                const float2 p0 = *reinterpret_cast<const float2*>(pr + j * Lt);
+                const float2 p1 = *reinterpret_cast<const float2*>(pr + j * Lt + 2);
+                const float2 p2 = *reinterpret_cast<const float2*>(pr + j * Lt + 4);
+                const float pv[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    acc[r][0] = fmaf(pv[r], v.x, acc[r][0]); acc[r][1] = fmaf(pv[r], v.y, acc[r][1]);
+                    acc[r][2] = fmaf(pv[r], v.z, acc[r][2]); acc[r][3] = fmaf(pv[r], v.w, acc[r][3]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const int i = ty * 6 + r;
+                if (i < L) {
+                    const size_t oi = ((size_t)seq * L + i) * p.ldo + h * dh + tx * 4;
+                    float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                    if (p.res) { const float4 a = *reinterpret_cast<const float4*>(p.res + oi); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                    *reinterpret_cast<float4*>(p.out + oi) = o;
+                }
+            }
+        }
+    }
+}
+
 extern "C" int ps_mha(const float* qkv, int ld, const float* res, float* out, int ldo, int n_seq, int L, int n_heads,
                       int head_dim, int slots_per_frame, void* stream) {
     PS_REQUIRE(qkv && out, "ps_mha: null pointer");
@@ -262,15 +413,31 @@ extern "C" int ps_mha(const float* qkv, int ld, const float* res, float* out, in
     MhaParams p;
     p.qkv = qkv; p.ld = ld; p.res = res; p.out = out; p.ldo = ldo; p.n_seq = n_seq; p.L = L; p.H = n_heads; p.dh = head_dim;
     p.spf = slots_per_frame; p.scale = 1.0f / sqrtf((float)head_dim);
-    size_t smem = (size_t)(L * (head_dim + 1) + L * head_dim + 4 + 16 * L + 16 * head_dim) * sizeof(float);
-    PS_REQUIRE(smem <= 200 * 1024, "ps_mha: sequence of %d tokens x head_dim %d does not fit in shared memory", L, head_dim);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        PS_CUDA(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
     PS_REQUIRE(n_heads <= 65535, "ps_mha: too many heads");
-    mha_kernel<<<dim3(n_seq, n_heads), 128, smem, (cudaStream_t)stream>>>(p);
+    const bool vec = head_dim % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && ps_aligned16(qkv) && ps_aligned16(out) &&
+                     (res == nullptr || ps_aligned16(res));
+    const int L6 = (L + 5) / 6 * 6, Lt = (L6 + 3) & ~3, pitch = head_dim + 4;
+    const int qreg = L6 * pitch > L * Lt ? L6 * pitch : L * Lt;
+    const size_t smem_tiled = (size_t)(qreg + L6 * pitch + L * head_dim + L * (L + 1) + L6) * sizeof(float);
+    // long sequences (the L x L score tile does not fit) and very short ones (a handful of tiles) take the row-streaming kernel
+    if (vec && L >= 12 && smem_tiled <= 200 * 1024) {
+        const size_t smem = smem_tiled;
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            PS_CUDA(cudaFuncSetAttribute(mha_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = 200 * 1024;
+        }
+        mha_tiled_kernel<<<dim3(n_seq, n_heads), 128, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        size_t smem = (size_t)(L * (head_dim + 1) + L * head_dim + 4 + 16 * L + 16 * head_dim) * sizeof(float);
+        PS_REQUIRE(smem <= 200 * 1024, "ps_mha: sequence of %d tokens x head_dim %d does not fit in shared memory", L, head_dim);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            PS_CUDA(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = 200 * 1024;
+        }
+        mha_kernel<<<dim3(n_seq, n_heads), 128, smem, (cudaStream_t)stream>>>(p);
+    }
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;

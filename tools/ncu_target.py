@@ -35,4 +35,9 @@ if what in ("conv", "dec"):
     for _ in range(3):
         ops.conv5x5_tc(a0, wp, b, n, H, W, True, 3, act_out=a1)
     torch.cuda.synchronize()
+if what in ("mha",):
+    qkv = torch.randn(3072, 1536, device="cuda")
+    for _ in range(3):
+        ops.mha(qkv, 64, 48, 8, 64, 6)
+    torch.cuda.synchronize()
 print("done")
