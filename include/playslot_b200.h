@@ -110,6 +110,17 @@ int ps_sa_prepare(const float* x, void* planes, long long n_tokens, int dim, flo
 int ps_sa_main_tc2(const void* planes, long long lo_offset_tokens, const float* A, const float* a0, float* partial,
                    float* masks /* may be NULL */, int B, int N, int S, int dim, int n_chunks, float attn_eps, void* stream);
 
+/* Fused SAVi encoder MLP + norm_input for the tensor-core SlotAttention pass (src/models/SAVi.py:111-116,214-216 and
+ * the statistics part of BlocksUtils/attention.py:57,88):
+ *     h = relu(LayerNorm(x; ln_g, ln_b, ln_eps) W1^T + b1);  y = h W2^T + b2;  planes = split((y - mean y) * rstd(y; out_eps))
+ * One persistent tcgen05 kernel: tokens [n_tokens][ldx] fp32 (K1 <= 64 features used) are read once, the planes
+ * [hi | lo][n_tokens][128] (same format as ps_sa_prepare) are written once; hidden and output activations never touch HBM.
+ * w1_packed / w2_packed: fp16 hi/lo copies [2][128][64] / [2][128][128] of W1 (128 x K1, K zero-padded) and W2 (128 x 128),
+ * each multiplied by the power of two w*_scale (the layout ps_linear_tc takes). */
+int ps_enc_mlp_planes(const float* x, int ldx, int K1, const float* ln_g, const float* ln_b, float ln_eps,
+                      const void* w1_packed, float w1_scale, const float* b1, const void* w2_packed, float w2_scale,
+                      const float* b2, float out_eps, void* planes, long long n_tokens, void* stream);
+
 /* Per-slot update: reduce the partials, renormalise over locations (:109), to_v (:94), nn.GRUCell (:112-115),
  * residual MLP (:117), then (do_prep) the folded queries of the next iteration.  With do_update = 0 it only
  * prepares A/a0/a1 from slots_in.  Weight matrices suffixed T are transposed to [in][out]. */

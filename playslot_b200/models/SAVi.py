@@ -127,18 +127,16 @@ class SAVi(nn.Module):
         predicted = f32c(predicted.detach())
 
         slot_history, recons_h, objs_h, masks_h = [], [], [], []
-        feats_all = self._encode_clip(x, num_imgs)            # list of (t0, (t1-t0, B, N, D)) chunks
         use_planes = self.slot_attention.mode == "tc"
-        if use_planes:
-            # norm_input statistics + fp16 hi/lo split of every frame in one launch per chunk; the per-frame
-            # SlotAttention passes then stream these planes by TMA
-            feats_all = [(t0, f.shape, self.slot_attention.prepare(f)) for t0, f in feats_all]
+        # use_planes: norm_input statistics + fp16 hi/lo split of every frame once per chunk (fused into the encoder MLP
+        # kernel when that applies); the per-frame SlotAttention passes then stream these planes by TMA
+        feats_all = self._encode_clip(x, num_imgs, planes=use_planes)     # list of (t0, shape (t1-t0, B, N, D), data) chunks
         for t in range(num_imgs):
             if use_planes:
                 t0, shp, planes = next(c for c in feats_all if c[0] <= t < c[0] + c[1][0])
                 feats = ("planes", planes, (t - t0) * shp[1] * shp[2], shp[1], shp[2])
             else:
-                feats = self._feats_at(feats_all, t)
+                feats = next(f[t - t0] for t0, _, f in feats_all if t0 <= t < t0 + f.shape[0])
             slots = self.slot_attention(inputs=feats, slots=predicted, step=t)
             if decode:
                 recon, (recons, masks) = self.decode(slots)
@@ -156,8 +154,9 @@ class SAVi(nn.Module):
             "slot_history": torch.stack(slot_history, dim=1),
         }
 
-    def _encode_clip(self, x, num_imgs):
-        """ batched, time-major encode of frames [0, num_imgs) in chunks bounded by ENCODE_CHUNK_BYTES """
+    def _encode_clip(self, x, num_imgs, planes=False):
+        """ batched, time-major encode of frames [0, num_imgs) in chunks bounded by ENCODE_CHUNK_BYTES; each chunk is
+        (t0, (frames, B, N, D), fp32 features) or, with planes=True, (t0, shape, pre-normalised fp16 hi/lo planes) """
         B, _, C, H, W = x.shape
         N = H * W
         per_frame = B * N * self.mlp_encoder_dim * 4
@@ -166,33 +165,40 @@ class SAVi(nn.Module):
         for t0 in range(0, num_imgs, step):
             t1 = min(num_imgs, t0 + step)
             frames = x[:, t0:t1].transpose(0, 1).reshape((t1 - t0) * B, C, H, W)
-            feats = self.encode(frames).view(t1 - t0, B, N, self.mlp_encoder_dim)
-            chunks.append((t0, feats))
+            shape = (t1 - t0, B, N, self.mlp_encoder_dim)
+            if planes:
+                chunks.append((t0, shape, self.encode(frames, planes=True)))
+            else:
+                chunks.append((t0, shape, self.encode(frames).view(shape)))
         return chunks
 
-    @staticmethod
-    def _feats_at(chunks, t):
-        for t0, feats in chunks:
-            if t0 <= t < t0 + feats.shape[0]:
-                return feats[t - t0]
-        raise IndexError(t)
-
     # --------------------------------------------------------------------------------------------- encode
-    def encode(self, x):
-        """ images (M, C, H, W) -> feature tokens (M, H*W, mlp_encoder_dim)   (SAVi.py:207-217) """
+    def encode(self, x, planes=False):
+        """ images (M, C, H, W) -> feature tokens (M, H*W, mlp_encoder_dim)   (SAVi.py:207-217).
+        planes=True (internal): the norm_input-normalised features as fp16 hi/lo planes (2, M*H*W, 128) for
+        SlotAttention's "tc" mode instead """
         require_cuda(x, "SAVi.encode")
         no_grad_only("SAVi.encode", x, self.encoder_mlp[1].weight)
         x = f32c(x)
         M, _, H, W = x.shape
         posemb = self.encoder_pos_embedding.table(channels_last=True)
-        if self._tc_applicable(self.encoder.encoder, skip_first=True, channels=self.enc_tc_channels):
-            tokens = self._encode_convs_tc(x, posemb)
+        ln, fc1, fc2 = self.encoder_mlp[0], self.encoder_mlp[1], self.encoder_mlp[3]
+        C = fc1.in_features
+        tc_convs = self._tc_applicable(self.encoder.encoder, skip_first=True, channels=self.enc_tc_channels)
+        fused = (planes and ops.linear_mode() == "fp16x3" and self.mlp_encoder_dim == 128 and fc1.out_features == 128
+                 and C <= 64 and C % 16 == 0 and M * H * W >= ops.LINEAR_TC_MIN_ROWS)
+        if tc_convs:
+            tokens = self._encode_convs_tc(x, posemb, keep_padded=fused)          # (M, H*W, 64 if fused else C)
         else:
             tokens = self.encoder.run(x, last_nhwc_addend=posemb)
+        if fused:
+            # LayerNorm -> Linear -> ReLU -> Linear -> norm_input statistics -> split, one kernel, activations stay on chip
+            return ops.enc_mlp_planes(tokens.view(M * H * W, -1), C, (ln.weight, ln.bias, ln.eps), (fc1.weight, fc1.bias),
+                                      (fc2.weight, fc2.bias), self.slot_attention.norm_input.eps)
         tokens = tokens.view(M, H * W, -1)
-        ln, fc1, fc2 = self.encoder_mlp[0], self.encoder_mlp[1], self.encoder_mlp[3]
         h = ops.linear(tokens, fc1.weight, fc1.bias, ln=(ln.weight, ln.bias, ln.eps), act=ops.ACT_RELU)
-        return ops.linear(h, fc2.weight, fc2.bias)
+        feats = ops.linear(h, fc2.weight, fc2.bias)
+        return self.slot_attention.prepare(feats) if planes else feats
 
     # --------------------------------------------------------------------------------------------- tensor-core convs
     enc_tc_channels = (32, 64)      # encoder widths routed to the tcgen05 convolution (32 is zero-padded to 64)
@@ -263,7 +269,7 @@ class SAVi(nn.Module):
             return out
         return cache.get([b], build)
 
-    def _encode_convs_tc(self, x, posemb):
+    def _encode_convs_tc(self, x, posemb, keep_padded=False):
         """ first conv (3 -> C) on the CUDA cores writing the split planes, the C -> C layers on tcgen05; tokens + posemb out.
         C = 32 stacks are zero-padded to 64 channels. """
         prec = ops.TC_PRECISION[self.conv_mode]
@@ -294,7 +300,7 @@ class SAVi(nn.Module):
             posemb = self._posemb64.get([pe.weight, pe.bias], lambda: torch.nn.functional.pad(posemb, (0, 64 - C)).contiguous())
         tokens = torch.empty(M, H * W, 64, device=x.device, dtype=torch.float32)
         ops.conv5x5_tc(a, self._tc_weight(last), self._tc_bias64(last), M, H, W, last._relu, prec, out_tokens=tokens, addend=posemb)
-        return tokens if C == 64 else tokens[..., :C].contiguous()
+        return tokens if (C == 64 or keep_padded) else tokens[..., :C].contiguous()
 
     # --------------------------------------------------------------------------------------------- decode
     def _decoder_constants(self):

@@ -284,6 +284,24 @@ def sa_prepare(x, ln_eps=1e-5):
     return planes
 
 
+def enc_mlp_planes(tokens, K1, ln, fc1, fc2, out_eps):
+    """ tokens (n_tok, ldx) fp32 (first K1 columns used), ln = (gamma, beta, eps) over K1, fc1 = (W1 (128,K1), b1),
+    fc2 = (W2 (128,128), b2) -> planes int16 (2 [hi, lo], n_tok, 128) of norm_input-normalised encoder features: the
+    encoder MLP and sa_prepare in one tensor-core kernel """
+    lib = _lib.load()
+    _req(tokens, "tokens")
+    n_tok, ldx = tokens.shape
+    w1, s1, kp1, np1 = _packed_linear_weight(fc1[0], 3)
+    w2, s2, kp2, np2 = _packed_linear_weight(fc2[0], 3)
+    assert (kp1, np1, kp2, np2) == (64, 128, 128, 128), "enc_mlp_planes: Linear(K1<=64, 128) -> Linear(128, 128) only"
+    planes = torch.empty(2, n_tok, 128, device=tokens.device, dtype=torch.int16)
+    with _timed("enc_mlp_planes", (n_tok, K1)):
+        st = lib.ps_enc_mlp_planes(_ptr(tokens), ldx, K1, _ptr(ln[0]), _ptr(ln[1]), float(ln[2]), _ptr(w1), float(s1), _ptr(fc1[1]),
+                                   _ptr(w2), float(s2), _ptr(fc2[1]), float(out_eps), _ptr(planes), n_tok, _stream())
+    _lib.check(st, "ps_enc_mlp_planes")
+    return planes
+
+
 def sa_main_tc2(planes, first_token, B, N, A, a0, partial, masks, n_chunks, attn_eps):
     """ planes: (2, n_tokens, 128) int16 from sa_prepare; the batch covers tokens [first_token, first_token + B*N) """
     lib = _lib.load()

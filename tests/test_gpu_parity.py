@@ -160,6 +160,31 @@ def test_conv5x5_tensor_core(n, H, W, precision, tol):
     check("tc vs fp32 kernel", _unpack_split(a1, n, H, W, precision), y, tol)
 
 
+@pytest.mark.parametrize("n_tok,K1,ldx", [(128 * 300 + 77, 64, 64), (4096, 32, 64), (1000, 32, 32), (131, 64, 64)])
+def test_enc_mlp_planes(n_tok, K1, ldx, linear_mode_guard):
+    """ fused encoder MLP + norm_input planes (one tcgen05 kernel) vs fp64: LayerNorm -> Linear -> ReLU -> Linear -> LayerNorm
+    statistics, and vs the unfused chain of this library (ps_linear_tc x2 + ps_sa_prepare) """
+    from playslot_b200 import ops
+    linear_mode_guard.set_linear_mode("fp16x3")
+    x = g(n_tok, ldx, seed=1, scale=2.0) + 0.3
+    gam, bet = 1.0 + 0.2 * g(K1, seed=2), 0.1 * g(K1, seed=3)
+    w1, b1 = g(128, K1, seed=4, scale=K1 ** -0.5), 0.1 * g(128, seed=5)
+    w2, b2 = g(128, 128, seed=6, scale=128 ** -0.5), 0.1 * g(128, seed=7)
+    xd = x[:, :K1].double()
+    h = F.relu(F.linear(F.layer_norm(xd, (K1,), gam.double(), bet.double(), 1e-5), w1.double(), b1.double()))
+    y = F.linear(h, w2.double(), b2.double())
+    ref = F.layer_norm(y, (128,), None, None, 1e-5).float()
+    dev = [t.to(DEV) for t in (x, gam, bet, w1, b1, w2, b2)]
+    planes = ops.enc_mlp_planes(dev[0], K1, (dev[1], dev[2], 1e-5), (dev[3], dev[4]), (dev[5], dev[6]), 1e-5)
+    assert planes.shape == (2, n_tok, 128)
+    got = planes.view(torch.float16).float()
+    got = got[0] + got[1] / 2048.0
+    check("fused encoder MLP planes vs fp64", got, ref, 2e-5)
+    h2 = ops.linear(dev[0][:, :K1].contiguous(), dev[3], dev[4], ln=(dev[1], dev[2], 1e-5), act=ops.ACT_RELU)
+    un = ops.sa_prepare(ops.linear(h2, dev[5], dev[6]), 1e-5).view(torch.float16).float()
+    check("fused vs unfused chain", got, un[0] + un[1] / 2048.0, 5e-6)
+
+
 # ----------------------------------------------------------------------------------------------- SlotAttention
 
 def _sa_module(S, sd, mlp_hidden=256, it_first=3, it=1):

@@ -35,6 +35,15 @@ if what in ("conv", "dec"):
     for _ in range(3):
         ops.conv5x5_tc(a0, wp, b, n, H, W, True, 3, act_out=a1)
     torch.cuda.synchronize()
+if what in ("encmlp",):
+    n_tok = 1 << 20
+    x = torch.randn(n_tok, 64, device="cuda")
+    gam, bet = torch.ones(64, device="cuda"), torch.zeros(64, device="cuda")
+    w1, b1 = torch.randn(128, 64, device="cuda") * 0.125, torch.zeros(128, device="cuda")
+    w2, b2 = torch.randn(128, 128, device="cuda") * 0.09, torch.zeros(128, device="cuda")
+    for _ in range(3):
+        ops.enc_mlp_planes(x, 64, (gam, bet, 1e-5), (w1, b1), (w2, b2), 1e-5)
+    torch.cuda.synchronize()
 if what in ("mha",):
     qkv = torch.randn(3072, 1536, device="cuda")
     for _ in range(3):
