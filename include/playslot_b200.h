@@ -56,6 +56,16 @@ int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_scale, int K
                  const float* res, int ldres, int res_div, int res_mod,
                  float* Y, int ldy, int M, int N, int K, int act, int precision, void* stream);
 
+/* ps_linear_tc (fp16x3) with fp16 [hi | lo] plane operands on either side, for chains of tensor-core linears (MLP fc1 ->
+ * fc2, attention -> output projection): x_planes [2][x_plane_rows][ldx] (lo scaled by 2048) replaces X and is loaded by TMA
+ * straight into the operand tiles (no conversion work in the kernel, no LayerNorm prologue); y_planes
+ * [2][y_plane_rows][ldy] replaces Y (the epilogue writes the split of the fp32 result; N multiple of 32).  Exactly one of
+ * X / x_planes and one of Y / y_planes is non-NULL.  The values are those ps_linear_tc would produce. */
+int ps_linear_tc_planes(const float* X, int ldx, const void* x_planes, long long x_plane_rows, const void* w_tc, float w_scale,
+                        int Kp, int Npad, const float* bias, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                        const float* res, int ldres, int res_div, int res_mod, float* Y, void* y_planes, long long y_plane_rows,
+                        int ldy, int M, int N, int K, int act, void* stream);
+
 /* Multi-head self attention over n_seq independent sequences of L tokens.
  * qkv: [n_seq*L, ld] rows holding q | k | v (each n_heads*head_dim wide, head-major); out: [n_seq*L, ldo].
  * slots_per_frame > 0 applies the block-causal (time x slot staircase) mask: token j is visible to token i
@@ -65,6 +75,9 @@ int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_scale, int K
  * (BlocksUtils/model_utils.py:115-124). */
 int ps_mha(const float* qkv, int ld, const float* res /* optional residual, laid out like out */, float* out,
            int ldo, int n_seq, int L, int n_heads, int head_dim, int slots_per_frame, void* stream);
+/* same, result as fp16 [hi | lo] planes [2][plane_rows][ldo] for ps_linear_tc_planes (head_dim % 4 == 0, L >= 12) */
+int ps_mha_planes(const float* qkv, int ld, const float* res, void* out_planes, long long plane_rows, int ldo, int n_seq,
+                  int L, int n_heads, int head_dim, int slots_per_frame, void* stream);
 
 /* KxK stride-1 zero-padded ("same") convolution + bias (+ReLU).  x: [n,Cin,H,W]; w_packed: [Cin][K*K][Cout]
  * (a repack of nn.Conv2d's [Cout,Cin,K,K]); y: [n,Cout,H,W], or with out_nhwc [n,H,W,Cout] (+ addend_nhwc

@@ -18,6 +18,9 @@ SIGNATURES = {
     "ps_device_info": (c_i, [ctypes.POINTER(c_i)] * 3),
     "ps_linear": (c_i, [c_f, c_i, c_f, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_linear_tc": (c_i, [c_f, c_i, c_f, c_fl, c_i, c_i, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_linear_tc_planes": (c_i, [c_f, c_i, c_f, ctypes.c_longlong, c_f, c_fl, c_i, c_i, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_f,
+                                   ctypes.c_longlong, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_mha_planes": (c_i, [c_f, c_i, c_f, c_f, ctypes.c_longlong, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_mha": (c_i, [c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_conv2d": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_conv2d_split": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),

@@ -17,6 +17,10 @@ def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+def needs_grad(*tensors):
+    return _needs_grad(*tensors)
+
+
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 

@@ -60,6 +60,28 @@ __device__ __forceinline__ void split_store8(const float* v, uint16_t* hi, uint1
     if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
+// 16 consecutive channels -> one 32-byte (256-bit) store per plane: the rows a warp writes are 128 bytes apart, so 16-byte
+// stores would touch every 32-byte sector twice
+__device__ __forceinline__ void split_store16(const float* v, uint16_t* hi, uint16_t* lo, bool bf16) {
+    uint32_t hw[8], lw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float a = v[2 * j], b = v[2 * j + 1];
+        if (bf16) {
+            hw[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+            lw[j] = 0;
+        } else {
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 f = __half22float2(h);
+            const __half2 l = __floats2half2_rn((a - f.x) * LO_SCALE, (b - f.y) * LO_SCALE);
+            hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+    }
+    tc::st_global_v8(hi, hw[0], hw[1], hw[2], hw[3], hw[4], hw[5], hw[6], hw[7]);
+    if (lo) tc::st_global_v8(lo, lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
+}
+
 struct ConvTcParams {
     const float* bias;
     const float* addend;     // mode 2: [H*W][64]
@@ -317,8 +339,8 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                     if (row_ok) {
                         const size_t o = ((size_t)img_base + pp) * C;
 #pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            split_store8(v + g * 8, p.out_hi + o + g * 8, p.out_lo ? p.out_lo + o + g * 8 : nullptr, p.bf16 != 0);
+                        for (int g = 0; g < 4; ++g)          // 16 channels = one full 32-byte sector per plane and store
+                            split_store16(v + g * 16, p.out_hi + o + g * 16, p.out_lo ? p.out_lo + o + g * 16 : nullptr, p.bf16 != 0);
                     }
                 } else if (interior) {
                     const int y = yp - 2, x = xp - 2;
@@ -328,13 +350,19 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                         for (int c = 0; c < 64; ++c) dst[(size_t)c * HW] = v[c];
                     } else {
                         const size_t pix = (size_t)y * p.W + x;
-                        float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((size_t)img * HW + pix) * C);
+                        float* dst = p.out_f32 + ((size_t)img * HW + pix) * C;
                         const float4* ad = p.addend ? reinterpret_cast<const float4*>(p.addend + pix * C) : nullptr;
 #pragma unroll
-                        for (int g = 0; g < 16; ++g) {
-                            float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-                            if (ad) { const float4 a = ad[g]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-                            dst[g] = o;
+                        for (int g = 0; g < 8; ++g) {
+                            float4 o0 = make_float4(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3]);
+                            float4 o1 = make_float4(v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]);
+                            if (ad) {
+                                const float4 a = __ldg(ad + 2 * g), b = __ldg(ad + 2 * g + 1);
+                                o0.x += a.x; o0.y += a.y; o0.z += a.z; o0.w += a.w;
+                                o1.x += b.x; o1.y += b.y; o1.z += b.z; o1.w += b.w;
+                            }
+                            tc::st_global_v8(dst + 8 * g, __float_as_uint(o0.x), __float_as_uint(o0.y), __float_as_uint(o0.z), __float_as_uint(o0.w),
+                                             __float_as_uint(o1.x), __float_as_uint(o1.y), __float_as_uint(o1.z), __float_as_uint(o1.w));
                         }
                     }
                 }

@@ -168,6 +168,8 @@ struct MhaParams {
     const float* qkv; int ld;
     const float* res;      // optional residual added to the output, same layout as out
     float* out; int ldo;
+    uint16_t* out_hi;      // tiled kernel only: write the result as fp16 [hi | lo] planes (operand of a tensor-core linear)
+    uint16_t* out_lo;      // instead of fp32 `out`
     int n_seq, L, H, dh, spf;
     float scale;
 };
@@ -278,6 +280,8 @@ __global__ __launch_bounds__(128) void mha_tiled_kernel(MhaParams p) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int dq = dh >> 2;
     for (int j = tid; j < L6; j += 128) frame[j] = p.spf > 0 ? j / p.spf : 0;
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");     // PDL (see tc_common.cuh): the next kernel's prologue may start
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");                  // qkv comes from the previous kernel
     for (int idx0 = tid; idx0 < L6 * dq; idx0 += 128 * 4) {
         float4 q[4], k[4], v[4];
 #pragma unroll
@@ -397,6 +401,14 @@ __global__ __launch_bounds__(128) void mha_tiled_kernel(MhaParams p) {
                     const size_t oi = ((size_t)seq * L + i) * p.ldo + h * dh + tx * 4;
                     float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                     if (p.res) { const float4 a = *reinterpret_cast<const float4*>(p.res + oi); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                    if (p.out_hi) {
+                        const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                        const __half2 l0 = __floats2half2_rn((o.x - f0.x) * 2048.0f, (o.y - f0.y) * 2048.0f);
+                        const __half2 l1 = __floats2half2_rn((o.z - f1.x) * 2048.0f, (o.w - f1.y) * 2048.0f);
+                        *reinterpret_cast<uint2*>(p.out_hi + oi) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                        *reinterpret_cast<uint2*>(p.out_lo + oi) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+                    } else
                     *reinterpret_cast<float4*>(p.out + oi) = o;
                 }
             }
@@ -404,22 +416,26 @@ __global__ __launch_bounds__(128) void mha_tiled_kernel(MhaParams p) {
     }
 }
 
-extern "C" int ps_mha(const float* qkv, int ld, const float* res, float* out, int ldo, int n_seq, int L, int n_heads,
-                      int head_dim, int slots_per_frame, void* stream) {
-    PS_REQUIRE(qkv && out, "ps_mha: null pointer");
+static int mha_run(const float* qkv, int ld, const float* res, float* out, void* out_planes, long long plane_rows, int ldo,
+                   int n_seq, int L, int n_heads, int head_dim, int slots_per_frame, void* stream) {
+    PS_REQUIRE(qkv && (out || out_planes), "ps_mha: null pointer");
     PS_REQUIRE(n_seq >= 0 && L > 0 && n_heads > 0 && head_dim > 0, "ps_mha: bad shape");
     if (n_seq == 0) return PS_OK;
     PS_REQUIRE(ld >= 3 * n_heads * head_dim && ldo >= n_heads * head_dim, "ps_mha: leading dimensions too small");
     MhaParams p;
-    p.qkv = qkv; p.ld = ld; p.res = res; p.out = out; p.ldo = ldo; p.n_seq = n_seq; p.L = L; p.H = n_heads; p.dh = head_dim;
+    p.qkv = qkv; p.ld = ld; p.res = res; p.out = out; p.ldo = ldo;
+    p.out_hi = reinterpret_cast<uint16_t*>(out_planes);
+    p.out_lo = p.out_hi ? p.out_hi + (size_t)plane_rows * ldo : nullptr; p.n_seq = n_seq; p.L = L; p.H = n_heads; p.dh = head_dim;
     p.spf = slots_per_frame; p.scale = 1.0f / sqrtf((float)head_dim);
     PS_REQUIRE(n_heads <= 65535, "ps_mha: too many heads");
-    const bool vec = head_dim % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && ps_aligned16(qkv) && ps_aligned16(out) &&
+    const bool vec = head_dim % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && ps_aligned16(qkv) && (out_planes ? ps_aligned16(out_planes) : ps_aligned16(out)) &&
                      (res == nullptr || ps_aligned16(res));
     const int L6 = (L + 5) / 6 * 6, Lt = (L6 + 3) & ~3, pitch = head_dim + 4;
     const int qreg = L6 * pitch > L * Lt ? L6 * pitch : L * Lt;
     const size_t smem_tiled = (size_t)(qreg + L6 * pitch + L * head_dim + L * (L + 1) + L6) * sizeof(float);
     // long sequences (the L x L score tile does not fit) and very short ones (a handful of tiles) take the row-streaming kernel
+    PS_REQUIRE(!out_planes || (vec && L >= 12 && smem_tiled <= 200 * 1024 && plane_rows >= (long long)n_seq * L),
+               "ps_mha_planes: plane output needs head_dim %% 4 == 0, 12 <= L and a sequence that fits the tiled kernel");
     if (vec && L >= 12 && smem_tiled <= 200 * 1024) {
         const size_t smem = smem_tiled;
         static size_t configured = 0;
@@ -427,7 +443,13 @@ extern "C" int ps_mha(const float* qkv, int ld, const float* res, float* out, in
             PS_CUDA(cudaFuncSetAttribute(mha_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             configured = 200 * 1024;
         }
-        mha_tiled_kernel<<<dim3(n_seq, n_heads), 128, smem, (cudaStream_t)stream>>>(p);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_seq, n_heads); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PS_CUDA(cudaLaunchKernelEx(&cfg, mha_tiled_kernel, p));
     } else {
         size_t smem = (size_t)(L * (head_dim + 1) + L * head_dim + 4 + 16 * L + 16 * head_dim) * sizeof(float);
         PS_REQUIRE(smem <= 200 * 1024, "ps_mha: sequence of %d tokens x head_dim %d does not fit in shared memory", L, head_dim);
@@ -441,6 +463,20 @@ extern "C" int ps_mha(const float* qkv, int ld, const float* res, float* out, in
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;
+}
+
+extern "C" int ps_mha(const float* qkv, int ld, const float* res, float* out, int ldo, int n_seq, int L, int n_heads,
+                      int head_dim, int slots_per_frame, void* stream) {
+    PS_REQUIRE(out, "ps_mha: null pointer");
+    return mha_run(qkv, ld, res, out, nullptr, 0, ldo, n_seq, L, n_heads, head_dim, slots_per_frame, stream);
+}
+
+// Same attention, result written as fp16 [hi | lo] planes [2][plane_rows][ldo] (lo scaled by 2048): the operand format
+// ps_linear_tc_planes loads by TMA, so the output projection does no conversion work.
+extern "C" int ps_mha_planes(const float* qkv, int ld, const float* res, void* out_planes, long long plane_rows, int ldo, int n_seq,
+                             int L, int n_heads, int head_dim, int slots_per_frame, void* stream) {
+    PS_REQUIRE(out_planes, "ps_mha_planes: null pointer");
+    return mha_run(qkv, ld, res, nullptr, out_planes, plane_rows, ldo, n_seq, L, n_heads, head_dim, slots_per_frame, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

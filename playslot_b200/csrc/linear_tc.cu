@@ -40,6 +40,10 @@ struct LinTcParams {
     int M, N, K, nkb, npad;
     int act, stages, bf16, vec_out;
     float out_scale;
+    int a_planes;            // 1: the activations arrive as fp16 [hi | lo] planes and are loaded by TMA (no conversion work)
+    int a_lo_row0;           // first row of the lo plane inside the plane tensor map
+    uint16_t* y_hi;          // planes output instead of Y (fp16 [hi | lo][M][ldy], lo scaled by 2048), else null
+    uint16_t* y_lo;
 };
 
 // 4 consecutive K elements -> 8 bytes of the hi tile (and of the lo tile)
@@ -61,7 +65,7 @@ __device__ __forceinline__ void split_store4(const float4 v, uint8_t* hi, uint8_
 }
 
 template <int BN, int NSPLIT, bool PIPE>
-__global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const LinTcParams p) {
+__global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapA, const LinTcParams p) {
     constexpr int W_TILE = BN * 128;
     constexpr int STAGE_BYTES = NSPLIT * (A_TILE + W_TILE);
     constexpr int TM_COLS = (NSPLIT * BN < 32) ? 32 : NSPLIT * BN;
@@ -89,9 +93,14 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tm = tmem_base;
+    // PDL: the prologue above and the weight TMA loads (parameters, never written inside a step) overlap the tail of the
+    // previous kernel; everything that reads activations or writes Y waits for it here.
+    tc::pdl_trigger();
 
     if (warp < 8) {
         // ------------------------------------------------------------------ A producers
+        tc::pdl_wait();
+        if (!p.a_planes) {
         const int r_sub = tid >> 4;               // 0..15
         const int c4 = tid & 15;                  // float4 index inside the 64-wide K block
         const bool ln = p.ln_g != nullptr;
@@ -280,6 +289,7 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
                 store_kb(v, kb);
             }
         }
+        }   // !a_planes
         // ------------------------------------------------------------------ epilogue
         // warp w owns TMEM lanes (w % 4) * 32 .. +31 (rows) and the column half w / 4.  Each 32 x CW chunk is
         // transposed through shared memory so that every global store instruction writes one contiguous row piece.
@@ -327,6 +337,11 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
                             const float4 rv = *reinterpret_cast<const float4*>(p.res + (size_t)((m / p.res_div) % p.res_mod) * p.ldres + n);
                             t[0] += rv.x; t[1] += rv.y; t[2] += rv.z; t[3] += rv.w;
                         }
+                        if (p.y_hi) {          // the consumer is another tensor-core linear: hand it the split operand directly
+                            const size_t o = (size_t)m * p.ldy + n;
+                            split_store4<2>(make_float4(t[0], t[1], t[2], t[3]), reinterpret_cast<uint8_t*>(p.y_hi + o),
+                                            reinterpret_cast<uint8_t*>(p.y_lo + o), false);
+                        } else
                         *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = make_float4(t[0], t[1], t[2], t[3]);
                     }
                 }
@@ -364,7 +379,7 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 tc::mbar_wait(&bar_wfull[s], ph);
-                tc::mbar_wait(&bar_afull[s], ph);
+                if (!p.a_planes) tc::mbar_wait(&bar_afull[s], ph);
                 tc::tc_fence_after();
                 const uint32_t a_base = base + s * STAGE_BYTES;
                 const uint32_t w_base = a_base + NSPLIT * A_TILE;
@@ -394,13 +409,21 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
         // ------------------------------------------------------------------ TMA producer of the weights
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&mapW);
+            if (p.a_planes) tc::tma_prefetch_desc(&mapA);
             for (int kb = 0; kb < p.nkb; ++kb) {
                 const int s = kb % STAGES;
                 if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], ((kb / STAGES) - 1) & 1);
-                uint8_t* w_hi = smem + s * STAGE_BYTES + NSPLIT * A_TILE;
-                tc::mbar_expect_tx(&bar_wfull[s], NSPLIT * W_TILE);
+                uint8_t* a_hi = smem + s * STAGE_BYTES;
+                uint8_t* w_hi = a_hi + NSPLIT * A_TILE;
+                tc::mbar_expect_tx(&bar_wfull[s], NSPLIT * W_TILE + (p.a_planes ? NSPLIT * A_TILE : 0));
                 tc::tma_load_2d(w_hi, &mapW, &bar_wfull[s], kb * KB, n0);
                 if (NSPLIT == 2) tc::tma_load_2d(w_hi + W_TILE, &mapW, &bar_wfull[s], kb * KB, p.npad + n0);
+                if (p.a_planes) {
+                    // activation planes written by the previous kernel: the weight loads above did not have to wait for it
+                    if (kb == 0) tc::pdl_wait();
+                    tc::tma_load_2d(a_hi, &mapA, &bar_wfull[s], kb * KB, m0);
+                    if (NSPLIT == 2) tc::tma_load_2d(a_hi + A_TILE, &mapA, &bar_wfull[s], kb * KB, p.a_lo_row0 + m0);
+                }
             }
         }
     }
@@ -410,7 +433,7 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
 }
 
 template <int BN, int NSPLIT, bool PIPE>
-int launch_linear_tc_impl(const CUtensorMap& mW, const LinTcParams& p, cudaStream_t st) {
+int launch_linear_tc_impl(const CUtensorMap& mW, const CUtensorMap& mA, const LinTcParams& p, cudaStream_t st) {
     constexpr int STAGE_BYTES = NSPLIT * (A_TILE + BN * 128);
     size_t smem = (size_t)p.stages * STAGE_BYTES;
     if (smem < 8 * 32 * 33 * sizeof(float)) smem = 8 * 32 * 33 * sizeof(float);      // epilogue transpose scratch
@@ -421,27 +444,37 @@ int launch_linear_tc_impl(const CUtensorMap& mW, const LinTcParams& p, cudaStrea
         configured = smem;
     }
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-    linear_tc_kernel<BN, NSPLIT, PIPE><<<grid, LT_THREADS, smem, st>>>(mW, p);
+    PS_CUDA(tc::launch_pdl(linear_tc_kernel<BN, NSPLIT, PIPE>, grid, dim3(LT_THREADS), smem, st, mW, mA, p));
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;
 }
 
 template <int BN, int NSPLIT>
-int launch_linear_tc(const CUtensorMap& mW, const LinTcParams& p, cudaStream_t st) {
+int launch_linear_tc(const CUtensorMap& mW, const CUtensorMap& mA, const LinTcParams& p, cudaStream_t st) {
     // software-pipelined producers when K is long and the grid leaves at most one CTA per SM anyway
     const long long ctas = (long long)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-    if (p.nkb >= 3 && ctas <= 2 * 148) return launch_linear_tc_impl<BN, NSPLIT, true>(mW, p, st);
-    return launch_linear_tc_impl<BN, NSPLIT, false>(mW, p, st);
+    if (!p.a_planes && p.nkb >= 3 && ctas <= 2 * 148) return launch_linear_tc_impl<BN, NSPLIT, true>(mW, mA, p, st);
+    return launch_linear_tc_impl<BN, NSPLIT, false>(mW, mA, p, st);
 }
 
 }  // namespace
 
-extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_scale, int Kp, int Npad, const float* bias,
-                            const float* ln_gamma, const float* ln_beta, float ln_eps,
-                            const float* res, int ldres, int res_div, int res_mod,
-                            float* Y, int ldy, int M, int N, int K, int act, int precision, void* stream) {
-    PS_REQUIRE(X && w_tc && Y, "ps_linear_tc: null pointer");
+static int linear_tc_run(const float* X, int ldx, const void* x_planes, long long x_plane_rows, const void* w_tc, float w_scale,
+                         int Kp, int Npad, const float* bias, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                         const float* res, int ldres, int res_div, int res_mod, float* Y, void* y_planes, long long y_plane_rows,
+                         int ldy, int M, int N, int K, int act, int precision, void* stream) {
+    PS_REQUIRE((X || x_planes) && w_tc && (Y || y_planes), "ps_linear_tc: null pointer");
+    if (x_planes) {
+        PS_REQUIRE(precision == 3 && !ln_gamma, "ps_linear_tc_planes: plane input needs the fp16x3 mode and no LayerNorm prologue");
+        PS_REQUIRE(ldx % 8 == 0 && ldx >= K && ps_aligned16(x_planes) && x_plane_rows >= M && 2 * x_plane_rows < (1ll << 31),
+                   "ps_linear_tc_planes: plane input needs a row pitch (%d) that is a multiple of 8 elements and 16-byte alignment", ldx);
+        X = reinterpret_cast<const float*>(x_planes);      // only for the alignment checks below
+    }
+    if (y_planes) {
+        PS_REQUIRE(precision == 3 && ldy % 4 == 0 && N % 32 == 0 && ps_aligned16(y_planes) && y_plane_rows >= M,
+                   "ps_linear_tc_planes: plane output needs the fp16x3 mode, N (%d) multiple of 32 and ldy (%d) multiple of 4", N, ldy);
+    }
     PS_REQUIRE(M >= 0 && N > 0 && K > 0, "ps_linear_tc: bad shape M=%d N=%d K=%d", M, N, K);
     if (M == 0) return PS_OK;
     PS_REQUIRE(precision >= 1 && precision <= 3, "ps_linear_tc: precision must be 1 (bf16), 2 (fp16) or 3 (fp16x3)");
@@ -458,7 +491,12 @@ extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_s
     p.res = res; p.ldres = ldres; p.res_div = res_div > 0 ? res_div : 1; p.res_mod = res_mod > 0 ? res_mod : M;
     p.Y = Y; p.ldy = ldy; p.M = M; p.N = N; p.K = K; p.nkb = Kp / KB; p.npad = Npad;
     p.act = act; p.bf16 = precision == 1 ? 1 : 0; p.out_scale = 1.0f / w_scale;
-    p.vec_out = (ldy % 4 == 0 && ps_aligned16(Y) && (!bias || ps_aligned16(bias)) && (!res || (ldres % 4 == 0 && ps_aligned16(res)))) ? 1 : 0;
+    p.vec_out = (ldy % 4 == 0 && (y_planes || ps_aligned16(Y)) && (!bias || ps_aligned16(bias)) && (!res || (ldres % 4 == 0 && ps_aligned16(res)))) ? 1 : 0;
+    p.a_planes = x_planes ? 1 : 0;
+    p.a_lo_row0 = (int)x_plane_rows;
+    p.y_hi = reinterpret_cast<uint16_t*>(y_planes);
+    p.y_lo = p.y_hi ? p.y_hi + (size_t)y_plane_rows * ldy : nullptr;
+    PS_REQUIRE(!y_planes || p.vec_out, "ps_linear_tc_planes: plane output needs 16-byte aligned bias / residual");
     // Column tile.  Every CTA normalises / splits its own copy of the 128-row activation tile, so narrow tiles multiply that
     // CUDA-core work: take the widest tile (<= 256) that still leaves about one CTA per two SMs.
     const long long mt = (M + BM - 1) / BM;
@@ -466,6 +504,7 @@ extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_s
     int bn = 256;
     while (bn > 32 && (bn / 2 >= n32 || mt * ((N + bn - 1) / bn) < 74)) bn >>= 1;
     if (bn == 256 && nsplit == 1) bn = 128;            // (the single-product instantiation of the widest tile is not built)
+    if (y_planes && bn < 64) bn = 64;                  // the plane epilogue is the 32-column float4 path
     const int stage_bytes = nsplit * (A_TILE + bn * 128);
     int stages = (100 * 1024) / stage_bytes;         // at most ~100 KB per CTA: two CTAs per SM overlap each other's phases
     if (bn == 256) stages = 2;                       // 96 KB stages, one CTA per SM (its 512 TMEM columns fill the SM anyway)
@@ -478,12 +517,40 @@ extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_s
     if (stages > LT_MAX_STAGES) stages = LT_MAX_STAGES;
     if (stages > p.nkb) stages = p.nkb;
     p.stages = stages;
-    CUtensorMap mW;
-    const int r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 2ull * Npad, (uint64_t)Kp, (uint32_t)bn, KB);
+    CUtensorMap mW, mA;
+    int r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 2ull * Npad, (uint64_t)Kp, (uint32_t)bn, KB);
     PS_REQUIRE(r == 0, "ps_linear_tc: cuTensorMapEncodeTiled(W) failed (%d)", r);
+    mA = mW;                                          // unused unless the activations arrive as planes
+    if (x_planes) {
+        // [hi rows 0..rows-1 | lo rows rows..2*rows-1] x ldx fp16; columns >= K of a box are weighted by zero-padded weight columns
+        r = tc::make_tmap_2d_bf16_sw128(&mA, x_planes, 2ull * (uint64_t)x_plane_rows, (uint64_t)ldx, BM, KB);
+        PS_REQUIRE(r == 0, "ps_linear_tc_planes: cuTensorMapEncodeTiled(A) failed (%d)", r);
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 256) return launch_linear_tc<256, 2>(mW, p, st);
-    if (bn == 128) return nsplit == 2 ? launch_linear_tc<128, 2>(mW, p, st) : launch_linear_tc<128, 1>(mW, p, st);
-    if (bn == 64) return nsplit == 2 ? launch_linear_tc<64, 2>(mW, p, st) : launch_linear_tc<64, 1>(mW, p, st);
-    return nsplit == 2 ? launch_linear_tc<32, 2>(mW, p, st) : launch_linear_tc<32, 1>(mW, p, st);
+    if (bn == 256) return launch_linear_tc<256, 2>(mW, mA, p, st);
+    if (bn == 128) return nsplit == 2 ? launch_linear_tc<128, 2>(mW, mA, p, st) : launch_linear_tc<128, 1>(mW, mA, p, st);
+    if (bn == 64) return nsplit == 2 ? launch_linear_tc<64, 2>(mW, mA, p, st) : launch_linear_tc<64, 1>(mW, mA, p, st);
+    return nsplit == 2 ? launch_linear_tc<32, 2>(mW, mA, p, st) : launch_linear_tc<32, 1>(mW, mA, p, st);
+}
+
+extern "C" int ps_linear_tc(const float* X, int ldx, const void* w_tc, float w_scale, int Kp, int Npad, const float* bias,
+                            const float* ln_gamma, const float* ln_beta, float ln_eps,
+                            const float* res, int ldres, int res_div, int res_mod,
+                            float* Y, int ldy, int M, int N, int K, int act, int precision, void* stream) {
+    PS_REQUIRE(X && Y, "ps_linear_tc: null pointer");
+    return linear_tc_run(X, ldx, nullptr, 0, w_tc, w_scale, Kp, Npad, bias, ln_gamma, ln_beta, ln_eps, res, ldres, res_div, res_mod,
+                         Y, nullptr, 0, ldy, M, N, K, act, precision, stream);
+}
+
+// The same linear layer with fp16 [hi | lo] plane operands on either side, for chains of tensor-core linears (MLP fc1 -> fc2,
+// attention -> out projection): x_planes [2][x_plane_rows][ldx] replaces X (loaded by TMA: no conversion work in the kernel),
+// y_planes [2][y_plane_rows][ldy] replaces Y (the epilogue writes the split of the fp32 result).  Either may be NULL.
+extern "C" int ps_linear_tc_planes(const float* X, int ldx, const void* x_planes, long long x_plane_rows, const void* w_tc,
+                                   float w_scale, int Kp, int Npad, const float* bias, const float* ln_gamma, const float* ln_beta,
+                                   float ln_eps, const float* res, int ldres, int res_div, int res_mod, float* Y, void* y_planes,
+                                   long long y_plane_rows, int ldy, int M, int N, int K, int act, void* stream) {
+    PS_REQUIRE((X != nullptr) != (x_planes != nullptr), "ps_linear_tc_planes: exactly one of X / x_planes");
+    PS_REQUIRE((Y != nullptr) != (y_planes != nullptr), "ps_linear_tc_planes: exactly one of Y / y_planes");
+    return linear_tc_run(X, ldx, x_planes, x_plane_rows, w_tc, w_scale, Kp, Npad, bias, ln_gamma, ln_beta, ln_eps, res, ldres, res_div,
+                         res_mod, Y, y_planes, y_plane_rows, ldy, M, N, K, act, 3, stream);
 }

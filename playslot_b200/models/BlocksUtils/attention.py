@@ -270,8 +270,13 @@ class MetaAttention(nn.Module):
         B, L, E = x.shape
         qkv = AG.linear(x, self.qkv_weight(), None, ln=ln)
         if self.has_out_proj():
-            att = AG.mha(qkv, B, L, self.num_heads, self.head_dim, slots_per_frame)
             lin = self.out_proj[0]
+            if (ops.planes_ok(B * L, self.num_heads * self.head_dim) and 12 <= L <= 96 and self.head_dim % 4 == 0
+                    and not AG.needs_grad(qkv, res, lin.weight, lin.bias)):
+                # inference on the tensor cores: the attention kernel writes the projection's operand as fp16 hi/lo planes
+                att = ops.mha(qkv, B, L, self.num_heads, self.head_dim, slots_per_frame, out_planes=True)
+                return ops.linear(att, lin.weight, lin.bias, res=res).view(B, L, -1)
+            att = AG.mha(qkv, B, L, self.num_heads, self.head_dim, slots_per_frame)
             return AG.linear(att.view(B, L, -1), lin.weight, lin.bias, res=res)
         att = AG.mha(qkv, B, L, self.num_heads, self.head_dim, slots_per_frame, res=res)
         return att.view(B, L, E)

@@ -196,8 +196,15 @@ class MLP(nn.Module):
 
     def run(self, x, ln=None, res=None):
         """ kernel path: optional fused pre-LayerNorm and residual """
-        h = AG.linear(x, self.mlp[0].weight, self.mlp[0].bias, ln=ln, act=self._act)
-        return AG.linear(h, self.mlp[2].weight, self.mlp[2].bias, res=res)
+        fc1, fc2 = self.mlp[0], self.mlp[2]
+        rows = x.numel() // x.shape[-1]
+        if ops.planes_ok(rows, fc1.out_features) and not AG.needs_grad(x, res, fc1.weight, fc1.bias, fc2.weight, fc2.bias,
+                                                                        *(ln[:2] if ln is not None else ())):
+            # inference on the tensor cores: fc1's epilogue hands fc2 its operand as fp16 hi/lo planes (loaded by TMA)
+            h = ops.linear(x, fc1.weight, fc1.bias, ln=ln, act=self._act, out_planes=True)
+            return ops.linear(h, fc2.weight, fc2.bias, res=res).view(*x.shape[:-1], fc2.out_features)
+        h = AG.linear(x, fc1.weight, fc1.bias, ln=ln, act=self._act)
+        return AG.linear(h, fc2.weight, fc2.bias, res=res)
 
     def forward(self, x):
         require_cuda(x, "MLP")

@@ -106,7 +106,26 @@ def reset_launch_count():
 
 # ------------------------------------------------------------------------------------------------ dense
 
-def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res_mod=None, out=None, mode=None):
+class Planes:
+    """ an activation matrix (M, N) stored as fp16 [hi | lo] planes (int16 tensor (2, M, N), lo scaled by 2048): the operand
+    format the tensor-core linear loads by TMA.  Produced by linear(..., out_planes=True) / mha(..., out_planes=True) and
+    consumed by linear(Planes, ...), so chained linears skip the fp32 round trip and the conversion work. """
+    __slots__ = ("data",)
+
+    def __init__(self, data):
+        self.data = data
+
+    @property
+    def shape(self):
+        return self.data.shape[1:]
+
+
+def planes_ok(rows, features=32):
+    """ can a (rows, features) activation be handed over as Planes?  (fp16x3 tensor-core linears only) """
+    return _LINEAR_MODE == "fp16x3" and rows >= LINEAR_TC_MIN_ROWS and features % 32 == 0
+
+
+def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res_mod=None, out=None, mode=None, out_planes=False):
     """
     y = act(LN(x) @ weight.T + bias) + res_rows.   x: (..., K) contiguous; weight (N, K).
     ln = (gamma, beta, eps) fuses a LayerNorm over K in front.  `res` is a 2-D (R, N) tensor; output
@@ -115,6 +134,8 @@ def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res
     every optimiser step, so a packed tensor-core copy would be rebuilt per call).
     """
     lib = _lib.load()
+    if isinstance(x, Planes) or out_planes:
+        return _linear_planes(x, weight, bias, ln, act, res, res_div, res_mod, out_planes)
     _req(x, "x"); _req(weight, "weight")
     K = x.shape[-1]
     N = weight.shape[0]
@@ -189,12 +210,63 @@ def _packed_linear_weight(weight, precision):
     return c[1]
 
 
-def mha(qkv, n_seq, L, n_heads, head_dim, slots_per_frame=0, res=None):
-    """ qkv: (n_seq*L, 3*n_heads*head_dim) -> (n_seq*L, n_heads*head_dim) (+ res of the same shape) """
+def _linear_planes(x, weight, bias, ln, act, res, res_div, res_mod, out_planes):
+    """ linear() with Planes on the input and / or output side (fp16x3 tensor-core kernel only) """
+    lib = _lib.load()
+    _req(weight, "weight")
+    N, K = weight.shape
+    xin = x.data if isinstance(x, Planes) else x
+    if isinstance(x, Planes):
+        if not xin.is_cuda or xin.dtype != torch.int16 or not xin.is_contiguous():
+            raise TypeError("linear: Planes operand must be a contiguous CUDA int16 tensor (2, M, K)")
+    else:
+        _req(xin, "x")
+    if xin.shape[-1] != K:
+        raise ValueError(f"linear: weight {tuple(weight.shape)} does not match input features {xin.shape[-1]}")
+    M = xin.numel() // K // (2 if isinstance(x, Planes) else 1)
+    if M < LINEAR_TC_MIN_ROWS:
+        raise ValueError("linear: plane operands need at least %d rows" % LINEAR_TC_MIN_ROWS)
+    g = b = None
+    eps = 0.0
+    if ln is not None:
+        g, b, eps = ln
+    ldres = 0
+    if res is not None:
+        _req(res, "res")
+        res = res.view(-1, N)
+        ldres = N
+        if res_mod is None:
+            res_mod = res.shape[0]
+    w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, 3)
+    if out_planes:
+        y = torch.empty(2, M, N, device=xin.device, dtype=torch.int16)
+        out = Planes(y)
+    else:
+        y = torch.empty(M, N, device=xin.device, dtype=torch.float32)
+        out = y
+    is_p = isinstance(x, Planes)
+    with _timed("linear_tc_p3", (M, N, K)):
+        st = lib.ps_linear_tc_planes(None if is_p else _ptr(xin), K, _ptr(xin) if is_p else None, M if is_p else 0, _ptr(w_tc),
+                                     float(w_scale), Kp, Npad, _ptr(bias), _ptr(g), _ptr(b), float(eps), _ptr(res), ldres,
+                                     int(res_div), int(res_mod or 0), None if out_planes else _ptr(y), _ptr(y) if out_planes else None,
+                                     M if out_planes else 0, N, M, N, K, int(act), _stream())
+    _lib.check(st, "ps_linear_tc_planes")
+    return out
+
+
+def mha(qkv, n_seq, L, n_heads, head_dim, slots_per_frame=0, res=None, out_planes=False):
+    """ qkv: (n_seq*L, 3*n_heads*head_dim) -> (n_seq*L, n_heads*head_dim) (+ res of the same shape); out_planes: as Planes """
     lib = _lib.load()
     _req(qkv, "qkv")
     inner = n_heads * head_dim
     qkv2 = qkv.view(n_seq * L, 3 * inner)
+    if out_planes:
+        y = torch.empty(2, n_seq * L, inner, device=qkv.device, dtype=torch.int16)
+        with _timed("mha"):
+            st = lib.ps_mha_planes(_ptr(qkv2), 3 * inner, _ptr(res), _ptr(y), n_seq * L, inner, n_seq, L, n_heads, head_dim,
+                                   int(slots_per_frame), _stream())
+        _lib.check(st, "ps_mha_planes")
+        return Planes(y)
     out = torch.empty(n_seq * L, inner, device=qkv.device, dtype=torch.float32)
     if res is not None:
         _req(res, "res")

@@ -160,6 +160,44 @@ def test_conv5x5_tensor_core(n, H, W, precision, tol):
     check("tc vs fp32 kernel", _unpack_split(a1, n, H, W, precision), y, tol)
 
 
+@pytest.mark.parametrize("M,H,K", [(3072, 512, 128), (300, 256, 64), (128, 96, 128)])
+def test_linear_plane_chain(M, H, K, linear_mode_guard):
+    """ fc1 -> (GELU) -> fp16 hi/lo planes -> fc2 with the planes loaded by TMA: same values as the fp32 hand-over """
+    from playslot_b200 import ops
+    linear_mode_guard.set_linear_mode("fp16x3")
+    x = g(M, K, seed=1)
+    gam, bet = 1.0 + 0.1 * g(K, seed=2), 0.1 * g(K, seed=3)
+    w1, b1 = g(H, K, seed=4, scale=K ** -0.5), 0.1 * g(H, seed=5)
+    w2, b2 = g(K, H, seed=6, scale=H ** -0.5), 0.1 * g(K, seed=7)
+    d = [t.to(DEV) for t in (x, gam, bet, w1, b1, w2, b2)]
+    h_ref = ops.linear(d[0], d[3], d[4], ln=(d[1], d[2], 1e-5), act=ops.ACT_GELU)
+    y_ref = ops.linear(h_ref, d[5], d[6], res=d[0])
+    hp = ops.linear(d[0], d[3], d[4], ln=(d[1], d[2], 1e-5), act=ops.ACT_GELU, out_planes=True)
+    assert isinstance(hp, ops.Planes) and tuple(hp.shape) == (M, H)
+    hv = hp.data.view(torch.float16).float()
+    check("planes out == split of the fp32 result", hv[0] + hv[1] / 2048.0, h_ref, 1e-6)
+    y = ops.linear(hp, d[5], d[6], res=d[0])
+    check("planes in", y, y_ref, 1e-6)
+    y64 = F.linear(F.gelu(F.linear(F.layer_norm(x.double(), (K,), gam.double(), bet.double(), 1e-5), w1.double(), b1.double())),
+                   w2.double(), b2.double()) + x.double()
+    check("chain vs fp64", y, y64.float(), 1e-5)
+
+
+def test_mha_planes_then_projection(linear_mode_guard):
+    from playslot_b200 import ops
+    linear_mode_guard.set_linear_mode("fp16x3")
+    n_seq, L, H, dh = 8, 48, 8, 64
+    qkv = g(n_seq * L, 3 * H * dh, seed=1).to(DEV)
+    w, b = g(128, H * dh, seed=2, scale=(H * dh) ** -0.5).to(DEV), g(128, seed=3, scale=0.1).to(DEV)
+    res = g(n_seq * L, 128, seed=4).to(DEV)
+    att = ops.mha(qkv, n_seq, L, H, dh, 6)
+    y_ref = ops.linear(att, w, b, res=res)
+    ap = ops.mha(qkv, n_seq, L, H, dh, 6, out_planes=True)
+    av = ap.data.view(torch.float16).float()
+    check("mha planes == split of the fp32 result", av[0] + av[1] / 2048.0, att, 1e-6)
+    check("projection from planes", ops.linear(ap, w, b, res=res), y_ref, 1e-6)
+
+
 @pytest.mark.parametrize("n_tok,K1,ldx", [(128 * 300 + 77, 64, 64), (4096, 32, 64), (1000, 32, 32), (131, 64, 64)])
 def test_enc_mlp_planes(n_tok, K1, ldx, linear_mode_guard):
     """ fused encoder MLP + norm_input planes (one tcgen05 kernel) vs fp64: LayerNorm -> Linear -> ReLU -> Linear -> LayerNorm
