@@ -312,11 +312,12 @@ __global__ __launch_bounds__(128) void mha_tiled_kernel(MhaParams p) {
         const int nTy = L6 / MHA_RT, nTx = L6 / MHA_CT;
         for (int t = tid; t < nTy * nTx; t += 128) {
             const int ty = t / nTx, tx = t - ty * nTx;
-            float acc[MHA_RT][MHA_CT];
+            // packed fp32x2 FMAs (sm_100 FFMA2): every accumulator is a pair of partial sums over even / odd feature pairs
+            float2 acc2[MHA_RT][MHA_CT];
 #pragma unroll
             for (int r = 0; r < MHA_RT; ++r)
 #pragma unroll
-                for (int c = 0; c < MHA_CT; ++c) acc[r][c] = 0.f;
+                for (int c = 0; c < MHA_CT; ++c) acc2[r][c] = make_float2(0.f, 0.f);
             const float* qr = Qs + ty * pitch;
             const float* kr = Ks + tx * pitch;
             const int qstep = nTy * pitch, kstep = nTx * pitch;
@@ -331,12 +332,15 @@ __global__ __launch_bounds__(128) void mha_tiled_kernel(MhaParams p) {
                 for (int r = 0; r < MHA_RT; ++r)
 #pragma unroll
                     for (int c = 0; c < MHA_CT; ++c) {
-                        acc[r][c] = fmaf(q[r].x, k[c].x, acc[r][c]);
-                        acc[r][c] = fmaf(q[r].y, k[c].y, acc[r][c]);
-                        acc[r][c] = fmaf(q[r].z, k[c].z, acc[r][c]);
-                        acc[r][c] = fmaf(q[r].w, k[c].w, acc[r][c]);
+                        acc2[r][c] = __ffma2_rn(make_float2(q[r].x, q[r].y), make_float2(k[c].x, k[c].y), acc2[r][c]);
+                        acc2[r][c] = __ffma2_rn(make_float2(q[r].z, q[r].w), make_float2(k[c].z, k[c].w), acc2[r][c]);
                     }
             }
+            float acc[MHA_RT][MHA_CT];
+#pragma unroll
+            for (int r = 0; r < MHA_RT; ++r)
+#pragma unroll
+                for (int c = 0; c < MHA_CT; ++c) acc[r][c] = acc2[r][c].x + acc2[r][c].y;
 #pragma unroll
             for (int r = 0; r < MHA_RT; ++r) {
                 const int i = ty + nTy * r;
@@ -374,26 +378,31 @@ __global__ __launch_bounds__(128) void mha_tiled_kernel(MhaParams p) {
         const int nTy = L6 / 6;
         for (int t = tid; t < nTy * dq; t += 128) {
             const int ty = t / dq, tx = t - ty * dq;
-            float acc[6][4];
+            // packed fp32x2 FMAs over row pairs: accp[rp][c] = (rows 2rp, 2rp+1) of output column c
+            float2 accp[3][4];
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+                for (int c = 0; c < 4; ++c) accp[r][c] = make_float2(0.f, 0.f);
             const float* pr = Pt + ty * 6;
             const float* vr = Vs + tx * 4;
 #pragma unroll 4
             for (int j = 0; j < L; ++j) {
                 const float4 v = *reinterpret_cast<const float4*>(vr + j * dh);
-                const float2 p0 = *reinterpret_cast<const float2*>(pr + j * Lt);
-                const float2 p1 = *reinterpret_cast<const float2*>(pr + j * Lt + 2);
-                const float2 p2 = *reinterpret_cast<const float2*>(pr + j * Lt + 4);
-                const float pv[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};
+                const float2 pp[3] = {*reinterpret_cast<const float2*>(pr + j * Lt), *reinterpret_cast<const float2*>(pr + j * Lt + 2),
+                                      *reinterpret_cast<const float2*>(pr + j * Lt + 4)};
+                const float2 vx = make_float2(v.x, v.x), vy = make_float2(v.y, v.y), vz = make_float2(v.z, v.z), vw = make_float2(v.w, v.w);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    acc[r][0] = fmaf(pv[r], v.x, acc[r][0]); acc[r][1] = fmaf(pv[r], v.y, acc[r][1]);
-                    acc[r][2] = fmaf(pv[r], v.z, acc[r][2]); acc[r][3] = fmaf(pv[r], v.w, acc[r][3]);
+                for (int r = 0; r < 3; ++r) {
+                    accp[r][0] = __ffma2_rn(pp[r], vx, accp[r][0]); accp[r][1] = __ffma2_rn(pp[r], vy, accp[r][1]);
+                    accp[r][2] = __ffma2_rn(pp[r], vz, accp[r][2]); accp[r][3] = __ffma2_rn(pp[r], vw, accp[r][3]);
                 }
             }
+            float acc[6][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { acc[2 * r][c] = accp[r][c].x; acc[2 * r + 1][c] = accp[r][c].y; }
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 const int i = ty * 6 + r;
