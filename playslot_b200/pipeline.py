@@ -109,3 +109,71 @@ class GraphedSeedRollout:
         out_host.copy_(res["pred_imgs"][:, 0], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host
+
+    def host_pipeline(self):
+        """ a HostPipeline over this graph: submit(video_host, out_host) per batch, wait() at the end """
+        return HostPipeline(self)
+
+
+class HostPipeline:
+    """
+    Streaming host <-> device path for evaluation / serving loops over a GraphedSeedRollout (what the reference's
+    DataLoader + `.to(device)` + `.cpu()` loop does, 05_evaluate_PlaySlot.py:75-108): every batch is uploaded from pinned host
+    memory and its predicted frames are downloaded into pinned host memory, but the PCIe copies run on their own streams
+    through staging buffers, so the upload of batch i+1 and the download of batch i-1 overlap the kernels of batch i.
+
+        pipe = graphed.host_pipeline()
+        for video_host, out_host in batches:        # pinned tensors
+            pipe.submit(video_host, out_host)       # returns at once
+        pipe.wait()                                 # every out_host is complete
+    """
+
+    def __init__(self, graphed):
+        self.g = graphed
+        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        self.video_stage = torch.empty_like(graphed.video)
+        self.noise_stage = torch.empty_like(graphed.noise)
+        self.out_stage = torch.empty_like(graphed.out["pred_imgs"][:, 0])
+        self._noise_pinned = [torch.empty(graphed.noise_shape, pin_memory=True) for _ in range(2)]
+        self._noise_done = [None, None]
+        self._stage_free = None         # main stream has copied the staging buffers into the graph's static inputs
+        self._d2h_done = None           # the download of the previous batch has left out_stage
+        self._n = 0
+
+    @torch.no_grad()
+    def submit(self, video_host, out_host, noise=None):
+        g, main = self.g, torch.cuda.current_stream()
+        b = self._n & 1
+        if self._noise_done[b] is not None:
+            self._noise_done[b].synchronize()                      # the upload two batches ago has read this pinned buffer
+        self._noise_pinned[b].copy_(g.draw_noise() if noise is None else noise)
+        with torch.cuda.stream(self.h2d):
+            if self._stage_free is not None:
+                self.h2d.wait_event(self._stage_free)
+            self.video_stage.copy_(video_host, non_blocking=True)
+            self.noise_stage.copy_(self._noise_pinned[b], non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(self.h2d)
+        self._noise_done[b] = uploaded
+        main.wait_event(uploaded)
+        g.video.copy_(self.video_stage, non_blocking=True)         # device-to-device, microseconds
+        g.noise.copy_(self.noise_stage, non_blocking=True)
+        self._stage_free = torch.cuda.Event()
+        self._stage_free.record(main)
+        g.graph.replay()
+        if self._d2h_done is not None:
+            main.wait_event(self._d2h_done)
+        self.out_stage.copy_(g.out["pred_imgs"][:, 0], non_blocking=True)
+        computed = torch.cuda.Event()
+        computed.record(main)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(computed)
+            out_host.copy_(self.out_stage, non_blocking=True)
+            self._d2h_done = torch.cuda.Event()
+            self._d2h_done.record(self.d2h)
+        self._n += 1
+
+    def wait(self):
+        self.h2d.synchronize()
+        torch.cuda.current_stream().synchronize()
+        self.d2h.synchronize()

@@ -521,6 +521,29 @@ def test_graphed_seed_rollout_equals_eager():
     assert torch.equal(g(v2, noise=noise)["pred_imgs"], eager2["pred_imgs"])
 
 
+def test_host_pipeline_equals_blocking_calls():
+    """ the streaming host path (uploads / downloads on copy streams) returns what the blocking graphed call returns """
+    from playslot_b200.pipeline import GraphedSeedRollout
+    fx, ssd, psd, video, noise, init_noise = load_case("buttonpress")
+    savi = make_savi(fx["savi_cfg"], ssd, DEV)
+    pred = make_predictor(fx["predictor_name"], fx["predictor_cfg"], psd, DEV)
+    B, ns, npred = 2, 3, 4
+    gr = GraphedSeedRollout(savi, pred, B, ns, npred)
+    gen = torch.Generator().manual_seed(5)
+    vids = [torch.rand(B, ns + npred, 3, 64, 64, generator=gen).pin_memory() for _ in range(4)]
+    noises = [torch.randn(gr.noise_shape, generator=gen) for _ in range(4)]
+    want = []
+    for v, n in zip(vids, noises):
+        want.append(gr(v, noise=n)["pred_imgs"][:, 0].clone().cpu())
+    outs = [torch.empty(B, npred, 3, 64, 64).pin_memory() for _ in range(4)]
+    pipe = gr.host_pipeline()
+    for v, n, o in zip(vids, noises, outs):
+        pipe.submit(v, o, noise=n)
+    pipe.wait()
+    for i, (o, w) in enumerate(zip(outs, want)):
+        assert torch.equal(o, w), f"batch {i}: streamed result differs from the blocking call"
+
+
 def test_config5_highres_many_slots_vs_oracle():
     """ BASELINE.json configs[4] shapes: Sketchy hyper-parameters at 128x128, 16 slots, context 10 (N = 16384 feature tokens,
     160 predictor tokens): a short clip through encode -> SlotAttention -> InvDyn -> rollout -> decode against the CPU oracle """
