@@ -1,15 +1,16 @@
-// tcgen05 implicit-GEMM 5x5 convolution, 64 -> 64 channels (decoder conv2..4 of every config, encoder
-// conv2..4 of the 64-channel configs).  Reference op: nn.Conv2d(64, 64, 5, padding=2) (+ReLU) in
+// tcgen05 implicit-GEMM 5x5 convolution, 64 -> 64 channels (decoder conv2..4 of every config, encoder conv2..4; 32-channel
+// encoders run zero-padded to 64 channels).  Reference op: nn.Conv2d(C, C, 5, padding=2) (+ReLU) in
 // src/models/BlocksUtils/model_blocks.py:48-79 as stacked by EncodersDecoders/{encoders,decoders}.py.
 //
-// Layout.  Activations live in HBM as zero-bordered NHWC bf16 planes: position p = (y+2)*Wp + (x+2),
+// Layout.  Activations live in HBM as zero-bordered NHWC 16-bit planes: position p = (y+2)*Wp + (x+2),
 // Wp = W+4, Hp = H+4, one 128-byte row of 64 channels per position; an activation tensor is two such planes
-// [hi | lo] with x ~= hi + lo (bf16 split of the fp32 value).  On this "padded-linear" grid a filter tap
-// (ky,kx) is a constant row shift (ky-2)*Wp + (kx-2), so for a tile of 128 consecutive positions the A operand
+// [hi | lo] (fp16 split of the fp32 value, see below; a single bf16 plane in the bf16 mode).  On this "padded-linear" grid a
+// filter tap (ky,kx) is a constant row shift (ky-2)*Wp + (kx-2), so for a tile of 128 consecutive positions the A operand
 // of every tap is a 128-row window of ONE shared-memory resident region (tile + halo), addressed purely by the
 // UMMA descriptor start address (128B swizzle is applied on absolute smem address bits, verified by
-// tools/tc_probe.cu).  Outputs computed at border columns are junk by construction and are written as zeros,
-// which maintains the zero border of the next layer's input.
+// tools/tc_probe.cu; tools/tc_rate.cu: windows that start off an 8-row swizzle atom cost nothing).  Outputs computed at
+// border columns are junk by construction and are written as zeros, which maintains the zero border of the next layer's
+// input.
 //
 // GEMM per tile: D[128 pos x 64 cout] += A_tap[128 x 64 cin] * W_tap[64 cout x 64 cin]^T over 25 taps, 16-bit
 // operands, fp32 accumulation in TMEM.  Precision modes:
@@ -20,7 +21,8 @@
 // (A bf16 hi/lo split was measured first and rejected: 16 mantissa bits put the decoder's slot-softmax masks
 //  at 1.6e-4..3.7e-4 max error, above the 1e-4 parity bar.)
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue.
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue.  Persistent (one CTA per
+// SM), double-buffered TMEM accumulators, 4-stage weight ring, staged region refilled chunk by chunk (see the kernel).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/playslot_b200.h"
