@@ -136,7 +136,8 @@ class _InvDynTail(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mv, noise, codebook, per_slot):
-        mv, codebook_c = _c(mv), _c(codebook.detach())
+        # a private copy of the codebook: the EMA quantizer updates its codewords in place later in the same forward
+        mv, codebook_c = _c(mv), codebook.detach().clone()
         out = ops.invdyn_tail(mv, noise, codebook_c, per_slot)
         ctx.save_for_backward(mv, noise, out["z"], out["idx"], codebook_c)
         ctx.per_slot = per_slot

@@ -84,7 +84,10 @@ extern "C" int ps_layernorm_bwd(const float* dy, const float* x, const float* me
     PS_CUDA(cudaMemsetAsync(dgamma, 0, K * sizeof(float), st));
     PS_CUDA(cudaMemsetAsync(dbeta, 0, K * sizeof(float), st));
     if (M == 0) return PS_OK;
-    const int rows_per_cta = 64;
+    // 8 rows per pass (one per warp); enough CTAs to fill the GPU at the training batch sizes (M = 256 .. a few thousand rows)
+    int rows_per_cta = ((M + 147) / 148 + 7) / 8 * 8;
+    if (rows_per_cta < 8) rows_per_cta = 8;
+    if (rows_per_cta > 64) rows_per_cta = 64;
     ln_bwd_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, 256, 2 * K * sizeof(float), st>>>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, K, rows_per_cta);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();

@@ -22,6 +22,8 @@ struct LinearParams {
     int M, N, K;
     int act;
     int vec_store;
+    int ksplit;      // > 1: the K range is split over gridDim.z CTAs that atomically accumulate into a zeroed Y (no LayerNorm,
+                     // activation or residual in that mode; the bias is added by the first slice)
 };
 
 #define LBM 64
@@ -70,8 +72,10 @@ __global__ __launch_bounds__(256) void linear_kernel(LinearParams p) {
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
     const int tx = tid & 15, ty = tid >> 4;
-    for (int k0 = 0; k0 < p.K; k0 += LBK) {
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    // the global loads of k-tile i+1 are issued before the FMAs of k-tile i (register prefetch): their latency hides behind
+    // the 256 FMAs per thread instead of being paid once per tile
+    auto load_tile = [&](int k0, float4& av, float4& bv) {
+        av = make_float4(0.f, 0.f, 0.f, 0.f); bv = av;
         const int k = k0 + lk;
         if (m0 + lr < p.M && k < p.K) {
             av = *reinterpret_cast<const float4*>(p.X + (size_t)(m0 + lr) * p.ldx + k);
@@ -86,9 +90,21 @@ __global__ __launch_bounds__(256) void linear_kernel(LinearParams p) {
         }
         if (n0 + lr < p.N && k < p.K)
             bv = *reinterpret_cast<const float4*>(p.W + (size_t)(n0 + lr) * p.K + k);
+    };
+    // split-K: this CTA's K range (multiples of LBK)
+    int kbeg = 0, kend = p.K;
+    if (p.ksplit > 1) {
+        const int per = ((p.K + p.ksplit - 1) / p.ksplit + LBK - 1) / LBK * LBK;
+        kbeg = blockIdx.z * per;
+        kend = min(p.K, kbeg + per);
+    }
+    float4 av, bv;
+    load_tile(kbeg, av, bv);
+    for (int k0 = kbeg; k0 < kend; k0 += LBK) {
         As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
         Bs[lk + 0][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
         __syncthreads();
+        if (k0 + LBK < kend) load_tile(k0 + LBK, av, bv);
 #pragma unroll
         for (int kk = 0; kk < LBK; ++kk) {
             float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -124,7 +140,11 @@ __global__ __launch_bounds__(256) void linear_kernel(LinearParams p) {
             o[j] = v;
         }
         float* dst = p.Y + (size_t)m * p.ldy + n;
-        if (p.vec_store && n + 3 < p.N) {
+        if (p.ksplit > 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) atomicAdd(dst + j, (blockIdx.z == 0 || !p.bias) ? o[j] : o[j] - p.bias[n + j]);
+        } else if (p.vec_store && n + 3 < p.N) {
             *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
 #pragma unroll
@@ -154,6 +174,19 @@ extern "C" int ps_linear(const float* X, int ldx, const float* W, const float* b
     dim3 grid((M + LBM - 1) / LBM, (N + LBN - 1) / LBN);
     PS_REQUIRE(grid.y <= 65535, "ps_linear: N=%d too large for one launch", N);
     cudaStream_t st = (cudaStream_t)stream;
+    // Few output tiles and a long K (the training-path GEMMs at the reference's batch size: 256 rows): split K over up to 8
+    // CTAs per tile so the launch fills the GPU; partial sums meet in Y through atomics (summation order not fixed).
+    p.ksplit = 1;
+    if (!ln_gamma && act == 0 && !res && ldy == N && grid.x * grid.y < 74 && K >= 256) {
+        int ks = 148 / (int)(grid.x * grid.y);
+        if (ks > 8) ks = 8;
+        if (ks > K / 128) ks = K / 128;
+        if (ks > 1) {
+            p.ksplit = ks;
+            grid.z = ks;
+            PS_CUDA(cudaMemsetAsync(Y, 0, (size_t)M * N * sizeof(float), st));
+        }
+    }
     if (ln_gamma) linear_kernel<true><<<grid, 256, 0, st>>>(p);
     else linear_kernel<false><<<grid, 256, 0, st>>>(p);
     PS_COUNT_LAUNCH();

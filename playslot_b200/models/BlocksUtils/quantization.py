@@ -28,22 +28,39 @@ class EmaCodebookMeter:
 
     def reset(self):
         self.bins = nn.Parameter(torch.ones(self.codebook_size) / self.codebook_size, requires_grad=False)
-        self.iters = 0
+        self._iters = torch.zeros((), dtype=torch.float32)      # device-side counter: updates stay sync-free (CUDA-graph safe)
+
+    @property
+    def iters(self):
+        return int(self._iters.item())
+
+    @iters.setter
+    def iters(self, value):
+        self._iters = torch.full((), float(value), dtype=torch.float32, device=self._iters.device)
 
     def bincount(self, val, weights=None):
         norm = val.shape[0]
-        weights = weights.reshape(-1) if weights is not None else None
-        count = torch.bincount(val.reshape(-1), minlength=self.codebook_size, weights=weights).detach()
-        self.iters += 1
-        return count / norm
+        flat = val.reshape(-1)
+        if weights is None:
+            count = F.one_hot(flat, num_classes=self.codebook_size).sum(0).to(torch.float32)
+        else:
+            count = torch.zeros(self.codebook_size, device=flat.device, dtype=torch.float32)
+            count.index_add_(0, flat, weights.reshape(-1).to(torch.float32))
+        self._iters = self._iters.to(flat.device) if self._iters.device != flat.device else self._iters
+        self._iters += 1
+        return count.detach() / norm
 
     def load(self, bins):
         self.bins = torch.load(bins)
 
     def update(self, val, weights=None):
+        """ same statistics as the reference (which keeps `bins` on the CPU and rebinds it every call); here the histogram
+        follows the indices' device and is updated in place, without a host synchronisation """
+        if self.bins.device != val.device:
+            self.bins = nn.Parameter(self.bins.data.to(val.device), requires_grad=False)
         count = self.bincount(val, weights=weights)
-        alpha = max(self.ema_alpha, 1 / (self.iters + 1))
-        self.bins = (1. - alpha) * self.bins + alpha * count.to(self.bins.device)
+        alpha = torch.clamp(1.0 / (self._iters + 1.0), min=self.ema_alpha)
+        self.bins.data.mul_(1. - alpha).add_(alpha * count)
 
     def get_hist(self):
         return self.bins
@@ -149,10 +166,12 @@ class EmaVectorQuantizer(nn.Module):
             packed = torch.cat([enc_sum, dw.flatten(), torch.tensor([float(B)], device=zf.device, dtype=zf.dtype)])
             torch.distributed.all_reduce(packed)
             enc_sum, dw, B = packed[:self.num_embs], packed[self.num_embs:-1].view_as(dw), float(packed[-1])
+        # same arithmetic as the reference; written IN PLACE (the reference rebinds the buffers) so that a training step
+        # captured in a CUDA graph (train.GraphedTrainStep) keeps advancing the same tensors on every replay
         cnt = self.ema_alpha * self.ema_count + (1 - self.ema_alpha) * enc_sum
-        self.ema_count = (cnt + self.epsilon) / (B + self.num_embs * self.epsilon) * B
-        self.ema_weight = self.ema_alpha * self.ema_weight + (1 - self.ema_alpha) * dw
-        self.vq.embeddings['0'].weight.data = self.ema_weight / (self.ema_count.unsqueeze(1) + 1e-8)
+        self.ema_count.copy_((cnt + self.epsilon) / (B + self.num_embs * self.epsilon) * B)
+        self.ema_weight.copy_(self.ema_alpha * self.ema_weight + (1 - self.ema_alpha) * dw)
+        self.vq.embeddings['0'].weight.data.copy_(self.ema_weight / (self.ema_count.unsqueeze(1) + 1e-8))
 
     def forward(self, z):
         z_q, losses, idx = self.vq(z)

@@ -86,6 +86,114 @@ def train_step(savi, predictor, optimizer, videos, num_seed, num_preds, bucket=N
     return loss.detach(), terms
 
 
-def make_optimizer(predictor, lr=1e-4):
-    """ Adam as in lib/setup_model.py:372 """
-    return torch.optim.Adam([p for p in predictor.parameters() if p.requires_grad], lr=lr)
+def make_optimizer(predictor, lr=1e-4, capturable=False):
+    """ Adam as in lib/setup_model.py:372; capturable=True keeps the step counter on the device (needed by GraphedTrainStep) """
+    return torch.optim.Adam([p for p in predictor.parameters() if p.requires_grad], lr=lr, capturable=capturable)
+
+
+def _trackers(module):
+    """ the python-side codeword-usage meters of the quantizers (not in the state_dict) """
+    for m in module.modules():
+        tr = getattr(m, "trackers", None)
+        if isinstance(tr, dict):
+            yield from tr.values()
+
+
+def _snapshot_training_state(predictor, optimizer):
+    with torch.no_grad():
+        return {
+            "params": [p.detach().clone() for p in predictor.parameters()],
+            "buffers": [b.detach().clone() for b in predictor.buffers()],
+            "opt": {p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()} for p, st in optimizer.state.items()},
+            "trackers": [(tr.bins.data.clone(), tr._iters.clone()) for tr in _trackers(predictor)],
+        }
+
+
+def _restore_training_state(predictor, optimizer, snap):
+    """ in place: the captured graph keeps reading and writing these very tensors """
+    with torch.no_grad():
+        for p, v in zip(predictor.parameters(), snap["params"]):
+            p.copy_(v)
+        for b, v in zip(predictor.buffers(), snap["buffers"]):
+            b.copy_(v)
+        for p, st in optimizer.state.items():
+            old = snap["opt"].get(p)
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    if old is not None and k in old:
+                        v.copy_(old[k])
+                    else:
+                        v.zero_()                  # a fresh Adam state: step 0, zero moments
+        for tr, (bins, iters) in zip(_trackers(predictor), snap["trackers"]):
+            tr.bins.data.copy_(bins)
+            tr._iters.copy_(iters)
+        optimizer.zero_grad(set_to_none=True)
+
+
+class GraphedTrainStep:
+    """
+    `train_step` for a fixed batch shape captured in ONE CUDA graph (forward, backward, clip, Adam, EMA-VQ update): at the
+    reference's batch size (8 videos per GPU) the ~3000 launches of a step are host-bound when issued from Python.
+    Single process only (the gradient all-reduce of multi-GPU training stays on the eager path).  The InvDyn noise is drawn
+    on the host with the reference's RNG call and uploaded into a static buffer before every replay, like
+    pipeline.GraphedSeedRollout.  The optimizer must be built with capturable=True.
+    """
+
+    def __init__(self, savi, predictor, optimizer, batch, num_seed, num_preds, resolution=(64, 64), clip_gradient=0.05, warmup=3):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise NotImplementedError("GraphedTrainStep covers single-GPU training; use train_step with a GradientBucket")
+        self.savi, self.predictor, self.optimizer = savi, predictor, optimizer
+        self.num_seed, self.num_preds = num_seed, num_preds
+        T = num_seed + num_preds
+        H, W = resolution
+        la = predictor.latent_action
+        per_slot = type(la).__name__ == "VQSimpleMLPSlotLatentAction"
+        S, A = savi.num_slots, la.action_dim
+        self.noise_shape = (batch, T - 1, S, A) if per_slot else (batch, T - 1, A)
+        dev = next(predictor.parameters()).device
+        self.video = torch.zeros(batch, T, 3, H, W, device=dev)
+        self.noise = torch.zeros(self.noise_shape, device=dev)
+        self._noise_pinned = torch.empty(self.noise_shape, pin_memory=True)
+        self._la = la
+        predictor.train()
+
+        def body():
+            optimizer.zero_grad(set_to_none=True)
+            loss, terms, _ = forward_loss(savi, predictor, self.video, num_seed, num_preds)
+            loss.backward()
+            if clip_gradient is not None:
+                torch.nn.utils.clip_grad_norm_(predictor.parameters(), clip_gradient)
+            optimizer.step()
+            return loss.detach(), terms
+
+        # The warm-up steps (they build lazy caches, workspaces and the optimizer state tensors the graph will update) are real
+        # optimisation steps on a dummy batch: snapshot every piece of training state first and put it back, IN PLACE, after
+        # the capture, so that constructing this object does not change the model.
+        snap = _snapshot_training_state(predictor, optimizer)
+        la._static_noise = self.noise
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self.graph):
+                self.loss, self.terms = body()
+        finally:
+            la._static_noise = None
+            _restore_training_state(predictor, optimizer, snap)
+
+    def draw_noise(self):
+        return torch.randn(self.noise_shape, dtype=torch.float32)
+
+    def __call__(self, videos, noise=None):
+        """ one optimisation step on `videos` (B, T, 3, H, W); returns (loss tensor, terms) -- static tensors of the graph """
+        self.video.copy_(videos, non_blocking=True)
+        self._noise_pinned.copy_(self.draw_noise() if noise is None else noise)
+        self.noise.copy_(self._noise_pinned, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.terms

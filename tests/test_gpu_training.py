@@ -260,3 +260,40 @@ def test_train_step_runs_and_learns():
         losses.append(float(l))
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0], losses
+
+
+def test_graphed_train_step_equals_eager():
+    """ train.GraphedTrainStep (one CUDA graph per optimisation step) follows the eager train_step: same losses and the same
+    parameters after three steps, up to the summation-order noise of the atomics in the weight-gradient kernels """
+    import copy
+    from playslot_b200 import configs, train
+    cfg = configs.experiment("ButtonPress")
+    torch.manual_seed(0)
+    savi, pred_a = configs.build_models(cfg, DEV)
+    for p in savi.parameters():
+        p.requires_grad_(False)
+    pred_b = copy.deepcopy(pred_a)
+    B, ns, npred = 2, 3, 3
+    gen = torch.Generator().manual_seed(11)
+    vids = [torch.rand(B, ns + npred, 3, 64, 64, generator=gen).to(DEV) for _ in range(3)]
+    opt_b = train.make_optimizer(pred_b, capturable=True)
+    graphed = train.GraphedTrainStep(savi, pred_b, opt_b, B, ns, npred)
+    noises = [torch.randn(graphed.noise_shape, generator=gen) for _ in range(3)]
+    opt_a = train.make_optimizer(pred_a)
+    la = pred_a.latent_action
+    losses_a, losses_b = [], []
+    for v, n in zip(vids, noises):
+        la._static_noise = n.to(DEV)
+        try:
+            loss, _ = train.train_step(savi, pred_a, opt_a, v, ns, npred)
+        finally:
+            la._static_noise = None
+        losses_a.append(float(loss))
+        losses_b.append(float(graphed(v, noise=n)[0]))
+    for i, (a, b) in enumerate(zip(losses_a, losses_b)):
+        assert abs(a - b) <= 2e-5 * abs(a), f"step {i}: eager loss {a} vs graphed {b}"
+    for (name, pa), pb in zip(pred_a.named_parameters(), pred_b.parameters()):
+        if pa.requires_grad:
+            assert float((pa.detach() - pb.detach()).abs().max()) <= 2e-5 * max(1.0, float(pa.detach().abs().max())), name
+    for (name, ba), bb in zip(pred_a.named_buffers(), pred_b.buffers()):
+        assert float((ba.float() - bb.float()).abs().max()) <= 2e-5 * max(1.0, float(ba.float().abs().max())), name

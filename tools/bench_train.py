@@ -20,6 +20,7 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--experiment", default="ButtonPress")
 ap.add_argument("--num-seed", type=int, default=6)
 ap.add_argument("--num-preds", type=int, default=8)
+ap.add_argument("--graph", action="store_true", help="capture the whole step in a CUDA graph (single GPU)")
 args = ap.parse_args()
 rank, world, local = shard.world()
 torch.cuda.set_device(local)
@@ -30,7 +31,7 @@ torch.manual_seed(0)
 savi, pred = configs.build_models(cfg, "cuda")
 for p in savi.parameters():
     p.requires_grad_(False)
-opt = train.make_optimizer(pred)
+opt = train.make_optimizer(pred, capturable=args.graph)
 bucket = train.GradientBucket(pred.parameters())
 T = args.num_seed + args.num_preds
 g = torch.Generator().manual_seed(7 + rank)
@@ -44,15 +45,20 @@ def sync():
     torch.cuda.synchronize()
 
 
+if args.graph:
+    graphed = train.GraphedTrainStep(savi, pred, opt, args.batch, args.num_seed, args.num_preds)
+    step = lambda: graphed(video)
+else:
+    step = lambda: train.train_step(savi, pred, opt, video, args.num_seed, args.num_preds, bucket=bucket)
 for _ in range(args.warmup):
-    loss, terms = train.train_step(savi, pred, opt, video, args.num_seed, args.num_preds, bucket=bucket)
+    loss, terms = step()
 sync()
 ops.reset_launch_count()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter()
 e0.record()
 for _ in range(args.steps):
-    loss, terms = train.train_step(savi, pred, opt, video, args.num_seed, args.num_preds, bucket=bucket)
+    loss, terms = step()
 e1.record()
 sync()
 wall = time.perf_counter() - t0
@@ -65,7 +71,7 @@ if rank == 0:
         "frames_per_sec": args.batch * world * T / (ms * 1e-3),
         "config": {"workload": f"{args.experiment} joint InvDyn+cOCVP training step, {args.batch} videos/GPU, {args.num_seed}+{args.num_preds} frames, "
                                "SAVi frozen (encode without gradients), decoder data gradient, MSE(img)+MSE(slots)+VQ, clip 0.05, Adam",
-                   "dtype": "f32 (decoder convolutions fp16x3 on tcgen05)"},
+                   "dtype": "f32 (decoder convolutions fp16x3 on tcgen05)", "cuda_graph": bool(args.graph)},
         "loss": float(loss), "trainable_params": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
         "gpu_launches_per_step": ops.launch_count() / args.steps}))
 if world > 1:
