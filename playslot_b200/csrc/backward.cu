@@ -436,49 +436,59 @@ __global__ void __launch_bounds__(256) dec_final_dgrad_kernel(const float* __res
                                                              const float* __restrict__ h, uint16_t* __restrict__ out_hi,
                                                              uint16_t* __restrict__ out_lo, const float* __restrict__ g_scale,
                                                              int n_img, int H, int W) {
-    __shared__ float s_w[64 * 9 * 4];
+    // One thread per pixel, all 64 input channels: the 36 incoming gradient values of the pixel's 3x3 neighbourhood live in
+    // registers, the weights are broadcast from shared memory (every lane reads the same float4), the ReLU mask reads of `h`
+    // are coalesced along x, and a thread writes whole 32-byte sectors of its 128-byte NHWC rows.
+    __shared__ __align__(16) float s_w[64 * 9 * 4];
     const float gs = g_scale ? *g_scale : 1.0f;          // power-of-two gradient scale (keeps the fp16 split in range)
     for (int i = threadIdx.x; i < 64 * 36; i += 256) s_w[i] = w_packed[i] * gs;
     __syncthreads();
     const int HW = H * W, Wp = W + 4, Hp = H + 4;
-    const long long total = (long long)n_img * HW * 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(i & 7);
-        const long long pix = i >> 3;
+    const long long total = (long long)n_img * HW;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(pix % W), y = (int)((pix / W) % H);
         const int img = (int)(pix / HW);
-        float go[9][4];
+        float4 go[9];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int yy = y + 1 - ky, xx = x + 1 - kx;
                 const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-#pragma unroll
-                for (int co = 0; co < 4; ++co) go[ky * 3 + kx][co] = ok ? g_o[((size_t)img * 4 + co) * HW + yy * W + xx] : 0.f;
+                const float* gp = g_o + (size_t)img * 4 * HW + yy * W + xx;
+                go[ky * 3 + kx] = ok ? make_float4(gp[0], gp[HW], gp[2 * HW], gp[3 * HW]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        float v[8];
+        const float* hp = h + (size_t)img * 64 * HW + y * W + x;
+        const size_t o = (((size_t)img * Hp + y + 2) * Wp + x + 2) * 64;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            float v[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int ci = g * 8 + j;
-            float acc = 0.f;
+            for (int j = 0; j < 16; ++j) {
+                const float4* wr = reinterpret_cast<const float4*>(s_w + (c0 + j) * 36);
+                float acc = 0.f;
 #pragma unroll
-            for (int t = 0; t < 9; ++t)
+                for (int t = 0; t < 9; ++t) {
+                    const float4 w4 = wr[t];
+                    acc = fmaf(w4.x, go[t].x, acc); acc = fmaf(w4.y, go[t].y, acc);
+                    acc = fmaf(w4.z, go[t].z, acc); acc = fmaf(w4.w, go[t].w, acc);
+                }
+                v[j] = hp[(size_t)(c0 + j) * HW] > 0.f ? acc : 0.f;
+            }
+            uint32_t hw[8], lw[8];
 #pragma unroll
-                for (int co = 0; co < 4; ++co) acc = fmaf(s_w[(ci * 9 + t) * 4 + co], go[t][co], acc);
-            v[j] = h[((size_t)img * 64 + ci) * HW + y * W + x] > 0.f ? acc : 0.f;
+            for (int j = 0; j < 8; ++j) {
+                const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                const float2 f = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn((v[2 * j] - f.x) * 2048.0f, (v[2 * j + 1] - f.y) * 2048.0f);
+                hw[j] = *reinterpret_cast<const uint32_t*>(&hh); lw[j] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(out_hi + o + c0), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]),
+                         "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7]) : "memory");
+            if (out_lo)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(out_lo + o + c0), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]),
+                             "r"(lw[3]), "r"(lw[4]), "r"(lw[5]), "r"(lw[6]), "r"(lw[7]) : "memory");
         }
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            const float2 f = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn((v[2 * j] - f.x) * 2048.0f, (v[2 * j + 1] - f.y) * 2048.0f);
-            hw[j] = *reinterpret_cast<const uint32_t*>(&hh); lw[j] = *reinterpret_cast<const uint32_t*>(&ll);
-        }
-        const size_t o = (((size_t)img * Hp + y + 2) * Wp + x + 2) * 64 + g * 8;
-        *reinterpret_cast<uint4*>(out_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
 }
 
@@ -502,7 +512,7 @@ extern "C" int ps_dec_final_dgrad(const float* g_o, const float* w_packed, const
     const long long P = (long long)n_img * (H + 4) * (W + 4);
     uint16_t* hi = reinterpret_cast<uint16_t*>(act_out);
     uint16_t* lo = precision == 3 ? hi + P * 64 : nullptr;
-    const long long total = (long long)n_img * H * W * 8;
+    const long long total = (long long)n_img * H * W;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     dec_final_dgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g_o, w_packed, h, hi, lo, g_scale, n_img, H, W);
