@@ -163,9 +163,9 @@ class EmaVectorQuantizer(nn.Module):
                 and torch.distributed.get_world_size() > 1:
             # batch-sharded training: the statistics of the GLOBAL batch make every rank's codebook identical to the
             # single-GPU run on the concatenated batch (one all-reduce of K + K*A + 1 floats)
-            packed = torch.cat([enc_sum, dw.flatten(), torch.tensor([float(B)], device=zf.device, dtype=zf.dtype)])
+            packed = torch.cat([enc_sum, dw.flatten(), torch.full((1,), float(B), device=zf.device, dtype=zf.dtype)])
             torch.distributed.all_reduce(packed)
-            enc_sum, dw, B = packed[:self.num_embs], packed[self.num_embs:-1].view_as(dw), float(packed[-1])
+            enc_sum, dw, B = packed[:self.num_embs], packed[self.num_embs:-1].view_as(dw), packed[-1]   # B stays on the device
         # same arithmetic as the reference; written IN PLACE (the reference rebinds the buffers) so that a training step
         # captured in a CUDA graph (train.GraphedTrainStep) keeps advancing the same tensors on every replay
         cnt = self.ema_alpha * self.ema_count + (1 - self.ema_alpha) * enc_sum

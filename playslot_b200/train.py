@@ -139,9 +139,13 @@ class GraphedTrainStep:
     pipeline.GraphedSeedRollout.  The optimizer must be built with capturable=True.
     """
 
-    def __init__(self, savi, predictor, optimizer, batch, num_seed, num_preds, resolution=(64, 64), clip_gradient=0.05, warmup=3):
+    def __init__(self, savi, predictor, optimizer, batch, num_seed, num_preds, resolution=(64, 64), clip_gradient=0.05, warmup=3,
+                 bucket=None):
+        # Single process only: capturing the NCCL all-reduces of a multi-GPU step with it hung in our 2-GPU trial, so sharded
+        # training keeps the eager train_step (with its GradientBucket).
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             raise NotImplementedError("GraphedTrainStep covers single-GPU training; use train_step with a GradientBucket")
+        self.bucket = None
         self.savi, self.predictor, self.optimizer = savi, predictor, optimizer
         self.num_seed, self.num_preds = num_seed, num_preds
         T = num_seed + num_preds
@@ -161,6 +165,8 @@ class GraphedTrainStep:
             optimizer.zero_grad(set_to_none=True)
             loss, terms, _ = forward_loss(savi, predictor, self.video, num_seed, num_preds)
             loss.backward()
+            if self.bucket is not None:
+                self.bucket.all_reduce_mean()
             if clip_gradient is not None:
                 torch.nn.utils.clip_grad_norm_(predictor.parameters(), clip_gradient)
             optimizer.step()

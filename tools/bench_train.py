@@ -46,7 +46,7 @@ def sync():
 
 
 if args.graph:
-    graphed = train.GraphedTrainStep(savi, pred, opt, args.batch, args.num_seed, args.num_preds)
+    graphed = train.GraphedTrainStep(savi, pred, opt, args.batch, args.num_seed, args.num_preds, bucket=bucket)
     step = lambda: graphed(video)
 else:
     step = lambda: train.train_step(savi, pred, opt, video, args.num_seed, args.num_preds, bucket=bucket)
