@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
                 const int ntok = min(p.tpc, p.N - tok0);
                 const int ntiles = (ntok + TILE - 1) / TILE;
                 for (int t = 0; t < ntiles; ++t, ++g) {
+                    // (an L2 prefetch of tiles ahead of the three-stage ring was measured and made the pass 8-14 % slower)
                     const int s = g % TC2_STAGES;
                     if (g >= TC2_STAGES) tc::mbar_wait(&bar_empty[s], ((g / TC2_STAGES) - 1) & 1);
                     uint8_t* st = stage0 + s * TC2_STAGE_BYTES;
@@ -500,22 +501,29 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
                 tc::umma_commit(&bar_lfull[g & 1]);
             };
             int g = 0, k_item = 0;
+            // The logits of the NEXT tile in stream order are always issued before the weighted sums of the current one -- also
+            // across an item boundary (the next item's folded queries were converted one item ahead), so the softmax groups are
+            // never starved at the start of an item.
+            auto issue_logits = [&](int gn, int item_k) {
+                tc::mbar_wait(&bar_full[gn % TC2_STAGES], (gn / TC2_STAGES) & 1);
+                if (gn >= 2) tc::mbar_wait(&bar_lfree[gn & 1], ((gn >> 1) - 1) & 1);
+                tc::tc_fence_after();
+                mma1(gn, item_k);
+            };
+            if (blockIdx.x < n_items) {
+                tc::mbar_wait(&bar_afull[0], 0);                                   // folded queries of the first item are in smem
+                issue_logits(0, 0);
+            }
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k_item) {
                 const int b = it / p.CH, chunk = it - b * p.CH;
                 const int ntok = min(p.tpc, p.N - chunk * p.tpc);
                 const int ntiles = (ntok + TILE - 1) / TILE;
-                tc::mbar_wait(&bar_afull[k_item & 1], (k_item >> 1) & 1);          // folded queries of this item are in smem
-                tc::mbar_wait(&bar_full[g % TC2_STAGES], (g / TC2_STAGES) & 1);
-                if (g >= 2) tc::mbar_wait(&bar_lfree[g & 1], ((g >> 1) - 1) & 1);
-                tc::tc_fence_after();
-                mma1(g, k_item);
                 for (int t = 0; t < ntiles; ++t, ++g) {
-                    if (t + 1 < ntiles) {                                          // next tile's logits before this tile's weighted sums
-                        const int gn = g + 1;
-                        tc::mbar_wait(&bar_full[gn % TC2_STAGES], (gn / TC2_STAGES) & 1);
-                        if (gn >= 2) tc::mbar_wait(&bar_lfree[gn & 1], ((gn >> 1) - 1) & 1);
-                        tc::tc_fence_after();
-                        mma1(gn, k_item);
+                    if (t + 1 < ntiles) {
+                        issue_logits(g + 1, k_item);
+                    } else if (it + (int)gridDim.x < n_items) {
+                        tc::mbar_wait(&bar_afull[(k_item + 1) & 1], ((k_item + 1) >> 1) & 1);
+                        issue_logits(g + 1, k_item + 1);
                     }
                     if (t == 0 && k_item >= 2) tc::mbar_wait(&bar_vfree[k_item & 1], ((k_item >> 1) - 1) & 1);
                     tc::mbar_wait(&bar_wfull[g & 1], (g >> 1) & 1);
