@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
                 const int ntok = min(p.tpc, p.N - tok0);
                 const int ntiles = (ntok + TILE - 1) / TILE;
                 for (int t = 0; t < ntiles; ++t, ++g) {
-                    // (an L2 prefetch of tiles ahead of the three-stage ring was measured and made the pass 8-14 % slower)
+                    // (measured and rejected: an L2 prefetch of tiles ahead of the three-stage ring, 8-14 % slower; releasing the
+                    //  stage after the logits MMA and re-loading the tile from L2 for the weighted sums, 6 % slower)
                     const int s = g % TC2_STAGES;
                     if (g >= TC2_STAGES) tc::mbar_wait(&bar_empty[s], ((g / TC2_STAGES) - 1) & 1);
                     uint8_t* st = stage0 + s * TC2_STAGE_BYTES;
