@@ -49,4 +49,13 @@ if what in ("mha",):
     for _ in range(3):
         ops.mha(qkv, 64, 48, 8, 64, 6)
     torch.cuda.synchronize()
+if what in ("composite",):
+    from playslot_b200 import configs
+    cfg = configs.experiment("GridShapes5Objs")
+    savi, pred = configs.build_models(cfg, "cuda")
+    slots = torch.randn(600, savi.num_slots, 128, device="cuda")
+    with torch.no_grad():
+        for _ in range(2):
+            savi.decode(slots)
+    torch.cuda.synchronize()
 print("done")
