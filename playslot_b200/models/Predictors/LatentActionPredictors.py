@@ -57,6 +57,8 @@ class BaseSlotLatentAction(nn.Module):
         return self.LATENT_ACTION_MODELS[name](slot_dim=self.slot_dim, num_actions=self.num_actions,
                                                action_dim=self.action_dim, **params)
 
+    batch_prior_samples = True      # run the random-action roll-outs of forward_multiple_samples as one batched roll-out
+
     @torch.no_grad()
     def forward_multiple_samples(self, slot_history, num_samples, num_seed, num_preds, use_posterior=False):
         """
@@ -79,10 +81,29 @@ class BaseSlotLatentAction(nn.Module):
                 protos = _per_slot(protos, S)
             pred, _ = self.autoregressive_inference(seed_slots=seed, action_protos=protos, action_vars=variab, N=num_preds)
             rollouts.append(pred)
-        for _ in range(num_samples - 1 if use_posterior else num_samples):
-            pred, idx = self.autoregressive_inference(seed_slots=seed, action_protos=None, action_vars=None, N=num_preds)
-            rollouts.append(pred)
-            prior_actions.append(idx)
+        n_prior = num_samples - 1 if use_posterior else num_samples
+        if n_prior > 1 and self.batch_prior_samples:
+            # The prior samples are independent roll-outs: draw their random actions (and variability latents) first, in the
+            # reference's order -- the dynamics model consumes no random numbers in between -- then run ONE roll-out over
+            # the batch axis n_prior * B.  The roll-out is latency-bound at batch B, so ten samples cost little more than one.
+            draws = []
+            for _ in range(n_prior):
+                protos, idx = self.get_random_actions(slots=seed, num_preds=num_preds)
+                variab = self.get_random_latents(slots=seed, num_preds=num_preds, src_action_idx=idx) if self.use_variability else None
+                draws.append((protos, idx, variab))
+            B = seed.shape[0]
+            pred, _ = self.autoregressive_inference(
+                seed_slots=seed.repeat(n_prior, 1, 1, 1),
+                action_protos=torch.cat([d[0] for d in draws], dim=0),
+                action_vars=torch.cat([d[2] for d in draws], dim=0) if self.use_variability else None, N=num_preds)
+            for i, d in enumerate(draws):
+                rollouts.append(pred[i * B:(i + 1) * B])
+                prior_actions.append(d[1])
+        else:
+            for _ in range(n_prior):
+                pred, idx = self.autoregressive_inference(seed_slots=seed, action_protos=None, action_vars=None, N=num_preds)
+                rollouts.append(pred)
+                prior_actions.append(idx)
         all_pred = torch.stack(rollouts, dim=1)
         if len(prior_actions) > 0:
             prior_actions = torch.stack(prior_actions, dim=1)

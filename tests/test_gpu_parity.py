@@ -462,6 +462,27 @@ def test_prior_rollout_runs_and_is_seeded():
     assert torch.isfinite(a).all()
 
 
+@pytest.mark.parametrize("case", ["blockpush", "gridshapes5"])
+def test_prior_samples_batched_equals_sequential(case):
+    """ forward_multiple_samples draws the random actions of all prior samples in the reference's order and rolls them out as
+    one batch: same slots and indices as one roll-out per sample (LatentActionPredictors.py:148-157) """
+    fx, ssd, psd, video, noise, init_noise = load_case(case)
+    pred = make_predictor(fx["predictor_name"], fx["predictor_cfg"], psd, DEV)
+    sh = fx["slot_history"].to(DEV)
+    ns = fx["num_seed"]
+    outs = []
+    for batched in (False, True):
+        pred.batch_prior_samples = batched
+        with torch.no_grad():
+            torch.manual_seed(5); torch.cuda.manual_seed(5)
+            with FixedRandn(noise):
+                outs.append(pred.forward_multiple_samples(sh, 4, ns, 3, use_posterior=True))
+    (a, ia), (b, ib) = outs
+    assert a.shape == b.shape and a.shape[1] == 4
+    assert torch.equal(ia, ib), "prior action indices differ"
+    check("batched prior roll-outs", b, a, 2e-6)
+
+
 def test_aux_predictors_match_reference_golden():
     """ rows a12 / a13 on the GPU: OCVPSeq behind PredictorWrapper, ActionCondtionalOCVP """
     from playslot_b200.models.Predictors.transformers import OCVPSeq
