@@ -40,15 +40,22 @@ class _LayerNorm(torch.autograd.Function):
         return dx, dg, db, None
 
 
+TRAIN_LINEAR_MODE = "fp32"      # arithmetic of the differentiable Linear: "fp32" (exact FFMA kernels) or "fp16x3" (tensor cores)
+
+
 class _Linear(torch.autograd.Function):
-    """ y = x W^T + b in exact fp32 (the weights change every optimiser step, see ops.linear) """
+    """ y = x W^T + b.  Default: exact fp32.  TRAIN_LINEAR_MODE = "fp16x3": the forward GEMM and the data-gradient GEMM run on
+    the tensor cores (fp32-grade split products); the weights change every optimiser step, so their packed copies are
+    rebuilt per step with the power-of-two scale chosen at the first packing (no host synchronisation: capturable). """
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         x = _c(x)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return ops.linear(x, _c(weight.detach()), None if bias is None else _c(bias.detach()), mode="fp32")
+        ctx.mode = TRAIN_LINEAR_MODE
+        w = weight if (ctx.mode != "fp32" and weight.is_contiguous()) else _c(weight.detach())     # the Parameter object carries the pack cache
+        return ops.linear(x, w, None if bias is None else _c(bias.detach()), mode=ctx.mode, reuse_pack_scale=True)
 
     @staticmethod
     def backward(ctx, dy):
@@ -57,7 +64,11 @@ class _Linear(torch.autograd.Function):
         N, K = weight.shape
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.linear(dy, weight.detach().t().contiguous(), None, mode="fp32").view(x.shape)     # dX = dY W
+            M = dy.numel() // N
+            if ctx.mode == "fp16x3" and M >= ops.LINEAR_TC_MIN_ROWS and N % 4 == 0 and weight.is_contiguous():
+                dx = ops.linear_dgrad_tc(dy, weight).view(x.shape)
+            else:
+                dx = ops.linear(dy, weight.detach().t().contiguous(), None, mode="fp32").view(x.shape)     # dX = dY W
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = ops.linear_wgrad(dy.view(-1, N), x.view(-1, K), want_bias=ctx.has_bias)
         return dx, dw, db

@@ -125,7 +125,8 @@ def planes_ok(rows, features=32):
     return _LINEAR_MODE == "fp16x3" and rows >= LINEAR_TC_MIN_ROWS and features % 32 == 0
 
 
-def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res_mod=None, out=None, mode=None, out_planes=False):
+def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res_mod=None, out=None, mode=None, out_planes=False,
+           reuse_pack_scale=False):
     """
     y = act(LN(x) @ weight.T + bias) + res_rows.   x: (..., K) contiguous; weight (N, K).
     ln = (gamma, beta, eps) fuses a LayerNorm over K in front.  `res` is a 2-D (R, N) tensor; output
@@ -163,7 +164,7 @@ def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res
     lmode = mode or _LINEAR_MODE
     if lmode != "fp32" and M >= LINEAR_TC_MIN_ROWS:
         prec = TC_PRECISION[lmode]
-        w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, prec)
+        w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, prec, reuse_scale=reuse_pack_scale)
         with _timed("linear_tc_p%d" % prec, (M, N, K)):
             st = lib.ps_linear_tc(_ptr(x2), K, _ptr(w_tc), float(w_scale), Kp, Npad, _ptr(bias), _ptr(g), _ptr(b), float(eps),
                                   _ptr(res), ldres, int(res_div), int(res_mod or 0), _ptr(y2), N, M, N, K, int(act), prec, _stream())
@@ -176,18 +177,21 @@ def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res
     return out
 
 
-def pack_linear_weight_tc(w, precision):
+def pack_linear_weight_tc(w, precision, scale=None):
     """
     nn.Linear weight (N, K) fp32 -> (16-bit tensor (2 [hi, lo], Npad, Kp), w_scale, Kp, Npad): K padded to a
     multiple of 64 and N to a multiple of 128 with zeros; weights multiplied by a power of two that puts max|w|
     near 1 (exact; undone in the kernel epilogue) so the fp16 parts stay away from the subnormal range.
+    `scale`: reuse a previously chosen power of two instead of measuring max|w| (no host synchronisation: the form the
+    training path uses to repack weights that change every step, also inside a CUDA-graph capture).
     """
     N, K = w.shape
     Kp, Npad = (K + 63) // 64 * 64, (N + 127) // 128 * 128
     wt = torch.zeros(Npad, Kp, device=w.device, dtype=torch.float32)
     wt[:N, :K] = w.detach().float()
-    amax = float(wt.abs().max())
-    scale = 1.0 if amax == 0.0 or precision == 1 else 2.0 ** (-round(math.log2(amax)))
+    if scale is None:
+        amax = float(wt.abs().max())
+        scale = 1.0 if amax == 0.0 or precision == 1 else 2.0 ** (-round(math.log2(amax)))
     wt = wt * scale
     if precision == 1:
         hi = wt.to(torch.bfloat16).view(torch.int16)
@@ -199,15 +203,41 @@ def pack_linear_weight_tc(w, precision):
     return torch.stack([hi, lo], dim=0).contiguous(), scale, Kp, Npad
 
 
-def _packed_linear_weight(weight, precision):
-    """ packed copy cached on the weight tensor object, rebuilt when the tensor is modified in place or moved """
+def _packed_linear_weight(weight, precision, transposed=False, reuse_scale=False):
+    """ packed copy (of weight, or of weight.t() for the data-gradient GEMM) cached on the weight tensor object, rebuilt when
+    the tensor is modified in place or moved; the power-of-two scale of the first packing is kept for the rebuilds """
+    attr = "_ps_tc_pack_t" if transposed else "_ps_tc_pack"
     key = (weight._version, weight.data_ptr(), precision)
-    c = getattr(weight, "_ps_tc_pack", None)
+    c = getattr(weight, attr, None)
     if c is None or c[0] != key:
         with torch.no_grad():
-            c = (key, pack_linear_weight_tc(weight, precision))
-        weight._ps_tc_pack = c
+            scale = getattr(weight, "_ps_tc_scale", None) if reuse_scale else None      # training: sync-free rebuilds
+            if scale is None and reuse_scale and precision != 1:
+                # no scale yet and no host synchronisation allowed (temporary weights such as a concatenated q/k/v matrix are
+                # new tensor objects every call): the power of two that normalises a Xavier-sized weight of this shape.  The
+                # scale only keeps the fp16 parts in range (6e-5 < |w| * scale < 65504), a few octaves off do not matter.
+                scale = 2.0 ** (-round(math.log2(math.sqrt(6.0 / (weight.shape[0] + weight.shape[1])))))
+            src = weight.detach().t() if transposed else weight
+            c = (key, pack_linear_weight_tc(src, precision, scale=scale))
+            if precision != 1:
+                weight._ps_tc_scale = c[1][1]
+        setattr(weight, attr, c)
     return c[1]
+
+
+def linear_dgrad_tc(dy, weight):
+    """ dX = dY @ W on the tensor cores (fp16x3): dy (M, N), weight (N, K) -> (M, K); packs W^T like a Linear weight """
+    lib = _lib.load()
+    _req(dy, "dy"); _req(weight, "weight")
+    N, K = weight.shape
+    M = dy.numel() // N
+    w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, 3, transposed=True, reuse_scale=True)   # a (K, N) "weight"
+    out = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+    with _timed("linear_tc_p3", (M, K, N)):
+        st = lib.ps_linear_tc(_ptr(dy.view(M, N)), N, _ptr(w_tc), float(w_scale), Kp, Npad, None, None, None, 0.0,
+                              None, 0, 1, 0, _ptr(out), K, M, K, N, 0, 3, _stream())
+    _lib.check(st, "ps_linear_tc")
+    return out
 
 
 def _linear_planes(x, weight, bias, ln, act, res, res_div, res_mod, out_planes):

@@ -137,10 +137,12 @@ class GraphedTrainStep:
     Single process only (the gradient all-reduce of multi-GPU training stays on the eager path).  The InvDyn noise is drawn
     on the host with the reference's RNG call and uploaded into a static buffer before every replay, like
     pipeline.GraphedSeedRollout.  The optimizer must be built with capturable=True.
+    linear_mode="fp16x3" runs the forward and data-gradient GEMMs of the predictor's Linear layers on the tensor cores
+    (weights repacked inside the graph every step); the default keeps them exact fp32.
     """
 
     def __init__(self, savi, predictor, optimizer, batch, num_seed, num_preds, resolution=(64, 64), clip_gradient=0.05, warmup=3,
-                 bucket=None):
+                 bucket=None, linear_mode="fp32"):
         # Single process only: capturing the NCCL all-reduces of a multi-GPU step with it hung in our 2-GPU trial, so sharded
         # training keeps the eager train_step (with its GradientBucket).
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -161,10 +163,18 @@ class GraphedTrainStep:
         self._la = la
         predictor.train()
 
+        from . import autograd as AG
+        if linear_mode not in ("fp32", "fp16x3"):
+            raise ValueError(f"linear_mode={linear_mode!r}; expected 'fp32' or 'fp16x3'")
+
         def body():
             optimizer.zero_grad(set_to_none=True)
-            loss, terms, _ = forward_loss(savi, predictor, self.video, num_seed, num_preds)
-            loss.backward()
+            old_mode, AG.TRAIN_LINEAR_MODE = AG.TRAIN_LINEAR_MODE, linear_mode     # arithmetic of the differentiable Linears
+            try:
+                loss, terms, _ = forward_loss(savi, predictor, self.video, num_seed, num_preds)
+                loss.backward()
+            finally:
+                AG.TRAIN_LINEAR_MODE = old_mode
             if self.bucket is not None:
                 self.bucket.all_reduce_mean()
             if clip_gradient is not None:

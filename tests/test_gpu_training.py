@@ -196,10 +196,21 @@ def test_decode_data_gradient(case, gscale):
     check("d_slots (recon only, oracle)", sd2.grad, so2.grad.float(), 1e-2)
 
 
+@pytest.fixture
+def train_linear_mode_guard():
+    from playslot_b200 import autograd as AG
+    old = AG.TRAIN_LINEAR_MODE
+    yield AG
+    AG.TRAIN_LINEAR_MODE = old
+
+
+@pytest.mark.parametrize("linear_mode", ["fp32", "fp16x3"])
 @pytest.mark.parametrize("case", ["buttonpress", "gridshapes5"])
-def test_training_step_matches_reference_golden(case):
-    """ forward + backward of src/04_train_PlaySlot.py:32-122 in train mode against the real reference """
+def test_training_step_matches_reference_golden(case, linear_mode, train_linear_mode_guard):
+    """ forward + backward of src/04_train_PlaySlot.py:32-122 in train mode against the real reference; "fp16x3" = forward and
+    data-gradient GEMMs of the Linear layers on the tensor cores """
     from playslot_b200 import train
+    train_linear_mode_guard.TRAIN_LINEAR_MODE = linear_mode
     fx, ssd, psd, video, noise = _load_train_case(case)
     scfg, pcfg = fx["savi_cfg"], fx["predictor_cfg"]
     ns, npred, B = fx["num_seed"], fx["num_preds"], fx["B"]

@@ -21,6 +21,7 @@ ap.add_argument("--experiment", default="ButtonPress")
 ap.add_argument("--num-seed", type=int, default=6)
 ap.add_argument("--num-preds", type=int, default=8)
 ap.add_argument("--graph", action="store_true", help="capture the whole step in a CUDA graph (single GPU)")
+ap.add_argument("--linear-mode", default="fp32", choices=["fp32", "fp16x3"], help="arithmetic of the predictor Linears (with --graph)")
 args = ap.parse_args()
 rank, world, local = shard.world()
 torch.cuda.set_device(local)
@@ -46,7 +47,7 @@ def sync():
 
 
 if args.graph:
-    graphed = train.GraphedTrainStep(savi, pred, opt, args.batch, args.num_seed, args.num_preds, bucket=bucket)
+    graphed = train.GraphedTrainStep(savi, pred, opt, args.batch, args.num_seed, args.num_preds, linear_mode=args.linear_mode)
     step = lambda: graphed(video)
 else:
     step = lambda: train.train_step(savi, pred, opt, video, args.num_seed, args.num_preds, bucket=bucket)
@@ -71,7 +72,7 @@ if rank == 0:
         "frames_per_sec": args.batch * world * T / (ms * 1e-3),
         "config": {"workload": f"{args.experiment} joint InvDyn+cOCVP training step, {args.batch} videos/GPU, {args.num_seed}+{args.num_preds} frames, "
                                "SAVi frozen (encode without gradients), decoder data gradient, MSE(img)+MSE(slots)+VQ, clip 0.05, Adam",
-                   "dtype": "f32 (decoder convolutions fp16x3 on tcgen05)", "cuda_graph": bool(args.graph)},
+                   "dtype": "f32 (decoder convolutions fp16x3 on tcgen05)", "cuda_graph": bool(args.graph), "linear_mode": args.linear_mode if args.graph else "fp32"},
         "loss": float(loss), "trainable_params": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
         "gpu_launches_per_step": ops.launch_count() / args.steps}))
 if world > 1:
