@@ -239,8 +239,9 @@ def slot_attention_config2(pk):
                 A = torch.empty(64, S, 128, device="cuda"); a0 = torch.empty(64, S, device="cuda")
                 ops.sa_update2(None, 1, slots, None, w, A, a0, 256, 1e-5, False, True)
                 planes = ops.sa_prepare(feats, 1e-5)
-                CH = 4
+                CH = 2                                          # the chunking SlotAttention.forward picks for this shape
                 partial = torch.empty(64, CH, ops.sa_partial_floats(S), device="cuda")
+                time.sleep(1.0)                                 # a kernel timed alone: let the clocks recover from the step loop
                 masks = torch.empty(64, S, 4096, device="cuda")
                 for with_masks in (False, True):
                     fn = lambda: ops.sa_main_tc2(planes, 0, 64, 4096, A, a0, partial, masks if with_masks else None, CH, 1e-8)
