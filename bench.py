@@ -239,7 +239,7 @@ def slot_attention_config2(pk):
                 A = torch.empty(64, S, 128, device="cuda"); a0 = torch.empty(64, S, device="cuda")
                 ops.sa_update2(None, 1, slots, None, w, A, a0, 256, 1e-5, False, True)
                 planes = ops.sa_prepare(feats, 1e-5)
-                CH = 2                                          # the chunking SlotAttention.forward picks for this shape
+                CH = ops.sa_tc2_chunks(64, 4096)                # partial slots per frame of the balanced tile partition
                 partial = torch.empty(64, CH, ops.sa_partial_floats(S), device="cuda")
                 time.sleep(1.0)                                 # a kernel timed alone: let the clocks recover from the step loop
                 masks = torch.empty(64, S, 4096, device="cuda")

@@ -120,6 +120,9 @@ int ps_sa_main_tc(const float* x, const float* A, const float* a0, float* partia
  * lo_offset_tokens: distance (in tokens) from the first hi row of this batch to its first lo row (>= B*N), so that a
  * batch may be a slice of planes prepared for many frames at once. */
 int ps_sa_prepare(const float* x, void* planes, long long n_tokens, int dim, float ln_eps, void* stream);
+/* partial slots per frame ps_sa_main_tc2 needs for this shape (its n_chunks argument / the CH extent of `partial`): the
+ * persistent CTAs take equally long contiguous ranges of the B * ceil(N/128) token tiles, so a frame is shared by a few CTAs */
+int ps_sa_tc2_chunks(int B, int N);
 int ps_sa_main_tc2(const void* planes, long long lo_offset_tokens, const float* A, const float* a0, float* partial,
                    float* masks /* may be NULL */, int B, int N, int S, int dim, int n_chunks, float attn_eps, void* stream);
 

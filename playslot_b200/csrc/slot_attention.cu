@@ -547,6 +547,7 @@ __device__ __forceinline__ float su2_sum(const float* part, int N, int KS, int o
 }
 
 __global__ __launch_bounds__(SU2_THREADS) void sa_update2_kernel(SaUpd2Params p) {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // PDL: the streaming pass that follows may start its feature loads (see slot_attention_tc.cu)
     __shared__ __align__(16) float s_h[SA_D * 4];            // hidden state / new slots, [d][r]
     __shared__ __align__(16) float s_u[SA_D * 4];            // normalised updates / LayerNorm outputs
     __shared__ __align__(16) float s_hid[512 * 4];           // MLP hidden

@@ -432,7 +432,14 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.S;
-    const int n_items = p.B * p.CH;
+    // Work partition: the B * tpf token tiles (tpf = tiles per frame) are dealt to the CTAs as contiguous, equally long
+    // ranges; a range is cut at frame boundaries into segments (the work items below).  Segment j of frame b -- counted over
+    // the CTAs that share the frame -- writes partial slot j; the CTA that finishes a frame zero-fills its unused slots.
+    const int tpf = (p.N + TILE - 1) / TILE;
+    const long long total_tiles = (long long)p.B * tpf;
+    const int g_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+    const int g_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+    auto owner = [&](long long gt) { return (int)(((gt + 1) * gridDim.x - 1) / total_tiles); };     // CTA that owns global tile gt
 
     if (tid == 0) {
         for (int s = 0; s < TC2_STAGES; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
@@ -448,6 +455,10 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tm = tmem_base;
+    // PDL: the feature planes were written long before the previous kernel (the slot update that produces A / a0), so the TMA
+    // producer starts filling the ring while that kernel is still running; everything that reads A / a0 or writes partial /
+    // masks (the softmax warps) waits for it.
+    tc::pdl_trigger();
 
     if (warp == 0) {
         // ------------------------------------------------------------------------ TMA producer
@@ -455,11 +466,11 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
             tc::tma_prefetch_desc(&mapC);
             const int lo_row0 = p.lo_row0;                         // first row of the lo plane
             int g = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const int b = it / p.CH, chunk = it - b * p.CH;
-                const int tok0 = chunk * p.tpc;
-                const int ntok = min(p.tpc, p.N - tok0);
-                const int ntiles = (ntok + TILE - 1) / TILE;
+            for (int gs = g_begin; gs < g_end;) {
+                const int b = gs / tpf, t_begin = gs - b * tpf;
+                const int ntiles = min(tpf - t_begin, g_end - gs);
+                const int tok0 = t_begin * TILE;
+                gs += ntiles;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     // (measured and rejected: an L2 prefetch of tiles ahead of the three-stage ring, 8-14 % slower; releasing the
                     //  stage after the logits MMA and re-loading the tile from L2 for the weighted sums, 6 % slower)
@@ -511,18 +522,18 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
                 tc::tc_fence_after();
                 mma1(gn, item_k);
             };
-            if (blockIdx.x < n_items) {
+            if (g_begin < g_end) {
                 tc::mbar_wait(&bar_afull[0], 0);                                   // folded queries of the first item are in smem
                 issue_logits(0, 0);
             }
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k_item) {
-                const int b = it / p.CH, chunk = it - b * p.CH;
-                const int ntok = min(p.tpc, p.N - chunk * p.tpc);
-                const int ntiles = (ntok + TILE - 1) / TILE;
+            for (int gs = g_begin; gs < g_end; ++k_item) {
+                const int t_begin = gs % tpf;
+                const int ntiles = min(tpf - t_begin, g_end - gs);
+                gs += ntiles;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     if (t + 1 < ntiles) {
                         issue_logits(g + 1, k_item);
-                    } else if (it + (int)gridDim.x < n_items) {
+                    } else if (gs < g_end) {
                         tc::mbar_wait(&bar_afull[(k_item + 1) & 1], ((k_item + 1) >> 1) & 1);
                         issue_logits(g + 1, k_item + 1);
                     }
@@ -550,6 +561,7 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
         // Two groups of four warps; group G owns the tiles with (global tile counter & 1) == G, i.e. always the L / weight
         // buffer G, so a tile's softmax has two tile periods to complete.  Group 1 converts the folded queries one item
         // ahead, group 0 writes the finished item's partial sums.
+        tc::pdl_wait();
         const int G = (warp - 2) >> 2;                           // group
         const int quad = warp & 3;                               // TMEM lane quadrant of this warp
         const int r = quad * 32 + lane;                          // token row of a tile == feature row of the V accumulators
@@ -559,8 +571,7 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
 #pragma unroll
         for (int s = 0; s < SPAD; ++s) rs[s] = 0.f;
 
-        auto convert_queries = [&](int k_item, int it) {         // A, a0 of item k_item -> operand buffer k_item & 1 (group 1)
-            const int b = it / p.CH;
+        auto convert_queries = [&](int k_item, int b) {         // A, a0 of frame b -> operand buffer k_item & 1 (group 1)
             uint8_t* aop = aop0 + (k_item & 1) * AOP_BYTES;
             for (int idx = gtid; idx < SPAD * 16; idx += 128) {
                 const int s = idx >> 4, c = idx & 15;
@@ -585,18 +596,25 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
             if (lane == 0) tc::mbar_arrive(&bar_afull[k_item & 1]);
         };
 
+        auto seg_len = [&](int gs) { return min(tpf - gs % tpf, g_end - gs); };
         if (G == 1) {
-            if (blockIdx.x < n_items) convert_queries(0, blockIdx.x);
-            if (blockIdx.x + gridDim.x < n_items) convert_queries(1, blockIdx.x + gridDim.x);
+            if (g_begin < g_end) {
+                convert_queries(0, g_begin / tpf);
+                const int gs1 = g_begin + seg_len(g_begin);
+                if (gs1 < g_end) convert_queries(1, gs1 / tpf);
+            }
         }
         int g = 0, k_item = 0;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k_item) {
-            const int b = it / p.CH, chunk = it - b * p.CH;
-            const int tok0 = chunk * p.tpc;
-            const int ntok = min(p.tpc, p.N - tok0);
-            const int ntiles = (ntok + TILE - 1) / TILE;
+        for (int gs = g_begin; gs < g_end; ++k_item) {
+            const int b = gs / tpf, t_begin = gs - b * tpf;
+            const int ntiles = seg_len(gs);
+            const int tok0 = t_begin * TILE;
+            const int ntok = min(p.N, (t_begin + ntiles) * TILE) - tok0;
+            const int slot = (int)blockIdx.x - owner((long long)b * tpf);          // partial slot of this segment inside frame b
+            const bool frame_done = t_begin + ntiles == tpf;
+            gs += ntiles;
             // queries of the NEXT item: its buffer was last read by the MMAs of item k-1, all complete by now
-            if (G == 1 && k_item >= 1 && it + gridDim.x < n_items) convert_queries(k_item + 1, it + gridDim.x);
+            if (G == 1 && k_item >= 1 && gs < g_end) convert_queries(k_item + 1, gs / tpf);
 
             for (int t = 0; t < ntiles; ++t, ++g) {
                 if ((g & 1) != G) continue;
@@ -680,11 +698,14 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bar_vfree[k_item & 1]);
                 const int pstride = S * SA_D + S;
-                float* pout = p.partial + ((size_t)b * p.CH + chunk) * pstride;
+                float* pout = p.partial + ((size_t)b * p.CH + slot) * pstride;
 #pragma unroll
                 for (int s = 0; s < SPAD; ++s)
                     if (s < S) pout[s * SA_D + r] = (v0[s] + (v0[SPAD + s] + v1[s]) * (1.0f / LO_SCALE)) * (1.0f / W_SCALE);
                 if (gtid < S) pout[S * SA_D + gtid] = rs_tot;
+                if (frame_done)                                   // the update kernel sums all CH slots of a frame
+                    for (int z = slot + 1; z < p.CH; ++z)
+                        for (int idx = gtid; idx < pstride; idx += 128) p.partial[((size_t)b * p.CH + z) * pstride + idx] = 0.f;
             }
         }
     }
@@ -703,8 +724,8 @@ int launch_sa_main_tc2(const CUtensorMap& mC, const SaTc2Params& p, cudaStream_t
     }
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int n_items = p.B * p.CH;
-    sa_main_tc2_kernel<SPAD><<<n_items < sms ? n_items : sms, 320, smem, st>>>(mC, p);
+    const long long total_tiles = (long long)p.B * ((p.N + TILE - 1) / TILE);
+    PS_CUDA(tc::launch_pdl(sa_main_tc2_kernel<SPAD>, dim3((unsigned)(total_tiles < sms ? total_tiles : sms)), dim3(320), smem, st, mC, p));
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;
@@ -727,6 +748,22 @@ extern "C" int ps_sa_prepare(const float* x, void* planes, long long n_tokens, i
     return PS_OK;
 }
 
+// Partial slots per frame ps_sa_main_tc2 needs: its CTAs take equally long contiguous ranges of the B * ceil(N / 128) token
+// tiles, a frame is shared by at most this many CTAs (each writes one slot; unused slots are zero-filled).
+extern "C" int ps_sa_tc2_chunks(int B, int N) {
+    if (B <= 0 || N <= 0) return 1;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tpf = (N + TILE - 1) / TILE, total = (long long)B * tpf;
+    const long long G = total < sms ? total : sms;
+    int worst = 1;
+    for (long long b = 0; b < B; ++b) {
+        const long long first = ((b * tpf + 1) * G - 1) / total, last = ((b * tpf + tpf) * G - 1) / total;
+        if ((int)(last - first + 1) > worst) worst = (int)(last - first + 1);
+    }
+    return worst;
+}
+
 extern "C" int ps_sa_main_tc2(const void* planes, long long lo_offset_tokens, const float* A, const float* a0, float* partial,
                               float* masks, int B, int N, int S, int dim, int n_chunks, float attn_eps, void* stream) {
     PS_REQUIRE(planes && A && a0 && partial, "ps_sa_main_tc2: null pointer");
@@ -739,10 +776,10 @@ extern "C" int ps_sa_main_tc2(const void* planes, long long lo_offset_tokens, co
     PS_REQUIRE(ps_aligned16(planes) && ps_aligned16(A), "ps_sa_main_tc2: pointers must be 16-byte aligned");
     SaTc2Params p;
     p.A = A; p.a0 = a0; p.partial = partial; p.masks = masks;
-    p.B = B; p.N = N; p.S = S; p.CH = n_chunks; p.tpc = (N + n_chunks - 1) / n_chunks;
+    p.B = B; p.N = N; p.S = S; p.CH = n_chunks; p.tpc = 0;
     p.attn_eps = attn_eps; p.lo_row0 = (int)lo_offset_tokens;
-
-    PS_REQUIRE((size_t)(n_chunks - 1) * p.tpc < (size_t)N, "ps_sa_main_tc2: n_chunks=%d leaves empty chunks for N=%d", n_chunks, N);
+    PS_REQUIRE(n_chunks >= ps_sa_tc2_chunks(B, N), "ps_sa_main_tc2: partial needs %d slots per frame for B=%d, N=%d (got %d): "
+               "size it with ps_sa_tc2_chunks", ps_sa_tc2_chunks(B, N), B, N, n_chunks);
     CUtensorMap mC;
     const int r = tc::make_tmap_2d_bf16_sw128(&mC, planes, (uint64_t)(lo_offset_tokens + (long long)B * N), SA_D, TILE, 64);
     PS_REQUIRE(r == 0, "ps_sa_main_tc2: cuTensorMapEncodeTiled failed (%d)", r);

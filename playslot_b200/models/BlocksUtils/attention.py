@@ -130,20 +130,12 @@ class SlotAttention(nn.Module):
         dev = slots.device
         if mode == "tc" and planes is None:
             planes, first_token = ops.sa_prepare(x, self.norm_input.eps), 0
-        tokens = self.TOKENS_PER_CTA
-        if mode == "tc" and "PLAYSLOT_SA_TOKENS" not in os.environ:
-            # persistent kernel, items = (frame, chunk of `tokens`) dealt round-robin to 148 CTAs: take the chunk size with the
-            # shortest critical path, counted in 128-token tiles (1.8 us each) plus 0.35 tile per item switch (measured with
-            # tools/bench_sa_kernel.py: at B = 64, N = 4096 whole 2048-token chunks on 128 CTAs beat finer splits)
-            best = None
-            for cand in (2048, 1024, 512, 256):
-                items = B * ((N + cand - 1) // cand)
-                rounds = (items + 147) // 148
-                cost = rounds * (((min(cand, N) + 127) // 128) + 0.35)
-                if best is None or cost < best[0] - 1e-9:
-                    best = (cost, cand)
-            tokens = best[1]
-        n_chunks = max(1, (N + tokens - 1) // tokens)
+        if mode == "tc":
+            # persistent kernel with a balanced tile partition: a frame's tokens are shared by a few CTAs, one partial slot each
+            n_chunks = ops.sa_tc2_chunks(B, N)
+        else:
+            tokens = self.TOKENS_PER_CTA
+            n_chunks = max(1, (N + tokens - 1) // tokens)
         partial = torch.empty(B, n_chunks, ops.sa_partial_floats(S), device=dev, dtype=torch.float32)
         A = torch.empty(B, S, self.dim_slots, device=dev, dtype=torch.float32)
         a0 = torch.empty(B, S, device=dev, dtype=torch.float32)

@@ -404,6 +404,11 @@ def enc_mlp_planes(tokens, K1, ln, fc1, fc2, out_eps):
     return planes
 
 
+def sa_tc2_chunks(B, N):
+    """ partial slots per frame sa_main_tc2 needs for a (B, N) batch """
+    return int(_lib.load().ps_sa_tc2_chunks(int(B), int(N)))
+
+
 def sa_main_tc2(planes, first_token, B, N, A, a0, partial, masks, n_chunks, attn_eps):
     """ planes: (2, n_tokens, 128) int16 from sa_prepare; the batch covers tokens [first_token, first_token + B*N) """
     lib = _lib.load()

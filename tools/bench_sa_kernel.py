@@ -32,13 +32,16 @@ def timeit(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-for tokens in (128, 256, 512, 1024, 2048):
+CH2 = ops.sa_tc2_chunks(B, N)
+partial = torch.empty(B, CH2, ops.sa_partial_floats(S), device="cuda")
+t2 = timeit(lambda: ops.sa_main_tc2(planes, 0, B, N, A, a0, partial, None, CH2, 1e-8))
+t2m = timeit(lambda: ops.sa_main_tc2(planes, 0, B, N, A, a0, partial, masks, CH2, 1e-8))
+print(f"tc2 (balanced tile partition, {CH2} partial slots per frame): {t2:6.1f} us ({by / t2 / 1e3:6.0f} GB/s)  +masks {t2m:6.1f} us")
+for tokens in (256, 512, 1024, 2048):
     CH = N // tokens
     partial = torch.empty(B, CH, ops.sa_partial_floats(S), device="cuda")
-    t2 = timeit(lambda: ops.sa_main_tc2(planes, 0, B, N, A, a0, partial, None, CH, 1e-8))
-    t2m = timeit(lambda: ops.sa_main_tc2(planes, 0, B, N, A, a0, partial, masks, CH, 1e-8))
     t1 = timeit(lambda: ops.sa_main_tc(feats, A, a0, partial, None, CH, 1e-5, 1e-8))
-    print(f"tokens/item {tokens:5d}: tc2 {t2:6.1f} us ({by / t2 / 1e3:6.0f} GB/s)  tc2+masks {t2m:6.1f} us  tc1 {t1:6.1f} us ({by / t1 / 1e3:6.0f} GB/s)")
+    print(f"tokens/item {tokens:5d}: tc1 {t1:6.1f} us ({by / t1 / 1e3:6.0f} GB/s)")
 tp = timeit(lambda: ops.sa_prepare(feats, 1e-5))
 print(f"sa_prepare {tp:.1f} us ({2 * by / tp / 1e3:.0f} GB/s read+write)")
 partial = torch.empty(B, 16, ops.sa_partial_floats(S), device="cuda")
