@@ -389,22 +389,26 @@ __global__ __launch_bounds__(128) void mha_tiled_kernel(MhaParams p) {
     }
     __syncthreads();
     float* Pt = Qs;                            // [L][Lt]: Pt[j][i], columns i >= L zero
-    for (int i = w; i < Lt; i += 4) {
-        if (i >= L) {
-            for (int j = lane; j < L; j += 32) Pt[j * Lt + i] = 0.f;
-            continue;
+    // softmax over the keys of every query row: four lanes per row (two shuffle steps per reduction), 32 rows per pass; the
+    // probabilities are written transposed, consecutive rows to consecutive addresses
+    {
+        const int l4 = tid & 3;
+        for (int i0 = 0; i0 < Lt; i0 += 32) {               // uniform trip count: every lane takes part in the shuffles
+            const int i = i0 + (tid >> 2);
+            const bool valid = i < L;
+            const float* srow = Ss + (valid ? i : 0) * (L + 1);
+            float mx = -INFINITY;
+            for (int j = l4; j < L; j += 4) mx = fmaxf(mx, srow[j]);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.f;
+            for (int j = l4; j < L; j += 4) sum += expf(srow[j] - mx);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = 1.0f / sum;
+            if (i < Lt)
+                for (int j = l4; j < L; j += 4) Pt[j * Lt + i] = valid ? expf(srow[j] - mx) * inv : 0.f;   // rows >= L: zero padding
         }
-        float mx = -INFINITY;
-        for (int j = lane; j < L; j += 32) mx = fmaxf(mx, Ss[i * (L + 1) + j]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < L; j += 32) {
-            const float e = expf(Ss[i * (L + 1) + j] - mx);
-            Ss[i * (L + 1) + j] = e;
-            sum += e;
-        }
-        const float inv = 1.0f / warp_sum(sum);
-        for (int j = lane; j < L; j += 32) Pt[j * Lt + i] = Ss[i * (L + 1) + j] * inv;
     }
     __syncthreads();
     {
