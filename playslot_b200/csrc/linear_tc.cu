@@ -314,14 +314,15 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
 #pragma unroll
             for (int j = 0; j < CW; ++j) scratch[lane * 33 + j] = v[j] * p.out_scale;
             __syncwarp();
-            if (CW == 32 && p.vec_out && n0 + col0 + 32 <= p.N) {
-                // lanes walk along rows in float4 pieces: one store instruction writes 4 rows x 128 bytes
-                const int rsub4 = lane >> 3, c4o = (lane & 7) * 4;
+            if (p.vec_out && n0 + col0 + CW <= p.N) {
+                // lanes walk along rows in float4 pieces: one store instruction writes RPV rows x CW floats
+                constexpr int LPR = CW / 4, RPV = 32 / LPR;          // lanes per row, rows per store instruction
+                const int rsub4 = lane / LPR, c4o = (lane % LPR) * 4;
                 const int n = n0 + col0 + c4o;
                 float4 bv4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias) bv4 = *reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll 2
-                for (int r = 0; r < 32; r += 4) {
+                for (int r = 0; r < 32; r += RPV) {
                     const int row = q * 32 + r + rsub4;
                     const int m = m0 + row;
                     const float* sp = scratch + (r + rsub4) * 33 + c4o;
@@ -504,7 +505,6 @@ static int linear_tc_run(const float* X, int ldx, const void* x_planes, long lon
     int bn = 256;
     while (bn > 32 && (bn / 2 >= n32 || mt * ((N + bn - 1) / bn) < 74)) bn >>= 1;
     if (bn == 256 && nsplit == 1) bn = 128;            // (the single-product instantiation of the widest tile is not built)
-    if (y_planes && bn < 64) bn = 64;                  // the plane epilogue is the 32-column float4 path
     const int stage_bytes = nsplit * (A_TILE + bn * 128);
     int stages = (100 * 1024) / stage_bytes;         // at most ~100 KB per CTA: two CTAs per SM overlap each other's phases
     if (bn == 256) stages = 2;                       // 96 KB stages, one CTA per SM (its 512 TMEM columns fill the SM anyway)

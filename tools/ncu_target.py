@@ -58,4 +58,15 @@ if what in ("composite",):
         for _ in range(2):
             savi.decode(slots)
     torch.cuda.synchronize()
+if what in ("rolllin",):
+    M = 3072
+    x = torch.randn(M, 128, device="cuda"); g_, b_ = torch.ones(128, device="cuda"), torch.zeros(128, device="cuda")
+    w1 = torch.randn(512, 128, device="cuda") * 0.09; b1 = torch.zeros(512, device="cuda")
+    w2 = torch.randn(128, 512, device="cuda") * 0.05; b2 = torch.zeros(128, device="cuda")
+    wq = torch.randn(1536, 128, device="cuda") * 0.09
+    for _ in range(3):
+        q = ops.linear(x, wq, None, ln=(g_, b_, 1e-6))
+        h = ops.linear(x, w1, b1, ln=(g_, b_, 1e-6), act=ops.ACT_GELU, out_planes=True)
+        y = ops.linear(h, w2, b2, res=x)
+    torch.cuda.synchronize()
 print("done")
