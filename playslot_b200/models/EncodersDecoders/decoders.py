@@ -4,7 +4,7 @@ Decoders -- mirror of src/models/EncodersDecoders/decoders.py.
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .._common import print_, require_cuda, no_grad_only, f32c
+from .._common import print_
 from ..BlocksUtils.model_blocks import ConvBlock
 
 DECODERS = ["ConvDecoder"]

@@ -10,9 +10,8 @@ ps_linear(MLP-2 + residual); the head is ps_linear(LN fused).
 import torch
 import torch.nn as nn
 
-from ... import ops
 from ... import autograd as AG
-from .._common import DerivedWeights, require_cuda, no_grad_only, f32c
+from .._common import DerivedWeights, require_cuda, f32c
 from ..BlocksUtils.attention import TransformerDecoder
 from ..BlocksUtils.model_blocks import SlotPositionalEncoding
 from ..BlocksUtils.model_utils import build_slot_causal_mask

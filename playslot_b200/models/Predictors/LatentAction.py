@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from ... import ops
 from ... import autograd as AG
-from .._common import DerivedWeights, require_cuda, no_grad_only, f32c
+from .._common import DerivedWeights, require_cuda, f32c
 from ..BlocksUtils.attention import TransformerEncoderBlock
 from ..BlocksUtils.quantization import VectorQuantizer, EmaVectorQuantizer
 
