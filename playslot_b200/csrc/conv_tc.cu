@@ -613,7 +613,8 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
     uint8_t* sA0 = smem + ((CT_WBYTES + 1023) & ~1023);    // nbuf x [hi | lo] regions
     __shared__ uint64_t bar_w, bar_afull[2], bar_aempty[2], bar_accfull[2], bar_accempty[2];
     __shared__ uint32_t tmem_base;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform (see conv5x5_tc_kernel)
     const int n_items = p.M * p.tiles_per_img;
     const int S = p.S, NBUF = p.nbuf;
 
@@ -654,36 +655,43 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
             }
         }
     } else if (warp == 1) {
-        if (tc::elect_one()) {
+        // the whole warp walks the loop (uniform control flow, uniform-register descriptor arithmetic, no division by the
+        // run-time buffer count); one elected lane issues -- same reasoning as in conv5x5_tc_kernel
+        const bool leader = tc::elect_one();
+        {
             const uint32_t idesc16 = tc::umma_idesc_f16(TILE_M, 16), idesc8 = tc::umma_idesc_f16(TILE_M, 8);
             const uint64_t dW = tc::umma_desc_sw128(tc::smem_u32(sW), 1024, 0);
-            const uint64_t dA = tc::umma_desc_sw128(tc::smem_u32(sA0), 1024, 0);
+            const uint64_t dA = tc::umma_desc_sw128(tc::smem_u32(sA0) + (uint32_t)p.halo * ROWB, 1024, 0);
+            const uint64_t buf_units = (uint64_t)((2 * a_bytes) / 16), lo_units = (uint64_t)(a_bytes / 16);
+            const int row_step = (p.Wp - 3) * (ROWB / 16);
             tc::mbar_wait(&bar_w, 0);
-            int q = 0, i = 0;
+            int buf = 0;
+            uint32_t bph = 0;
+            int i = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
                 const int ab = i & 1;
                 if (i >= 2) tc::mbar_wait(&bar_accempty[ab], ((i >> 1) - 1) & 1);
-                for (int s = 0; s < S; ++s, ++q) {
-                    const int buf = q % NBUF;
-                    tc::mbar_wait(&bar_afull[buf], (q / NBUF) & 1);
+                for (int s = 0; s < S; ++s) {
+                    tc::mbar_wait(&bar_afull[buf], bph);
                     tc::tc_fence_after();
-                    const uint64_t a_hi = dA + (uint64_t)((buf * 2 * a_bytes) / 16);
-                    const uint64_t a_lo = a_hi + (uint64_t)(a_bytes / 16);
+                    const uint64_t a_hi0 = dA + (uint64_t)buf * buf_units;
                     const uint32_t acc = tm + ab * ACC_COLS + s * 16;
+                    int a_off = (-p.Wp - 1) * (ROWB / 16);                       // tap (0, 0) shift, 16-byte units
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const int ky = tap / 3, kx = tap - ky * 3;
-                        const uint64_t row = (uint64_t)((p.halo + (ky - 1) * p.Wp + (kx - 1)) * (ROWB / 16));
+                        const uint64_t a_hi = a_hi0 + (uint64_t)(int64_t)a_off;
 #pragma unroll
                         for (int k = 0; k < C / 16; ++k) {
                             const uint64_t bd = dW + (uint64_t)((tap * 16 * ROWB + k * 32) / 16);
-                            tc::umma_bf16(acc, a_hi + row + (uint64_t)(k * 2), bd, idesc16, (tap | k) ? 1u : 0u);   // D0 | D1 += A_hi [w_hi | w_lo]
-                            tc::umma_bf16(acc + 8, a_lo + row + (uint64_t)(k * 2), bd, idesc8, 1u);               // D1 += A_lo w_hi
+                            if (leader) tc::umma_bf16(acc, a_hi + (uint64_t)(k * 2), bd, idesc16, (tap | k) ? 1u : 0u);   // D0 | D1 += A_hi [w_hi | w_lo]
+                            if (leader) tc::umma_bf16(acc + 8, a_hi + lo_units + (uint64_t)(k * 2), bd, idesc8, 1u);        // D1 += A_lo w_hi
                         }
+                        a_off += (tap % 3 == 2) ? row_step + ROWB / 16 : ROWB / 16;
                     }
-                    tc::umma_commit(&bar_aempty[buf]);
+                    if (leader) tc::umma_commit(&bar_aempty[buf]);
+                    if (++buf == NBUF) { buf = 0; bph ^= 1u; }
                 }
-                tc::umma_commit(&bar_accfull[ab]);
+                if (leader) tc::umma_commit(&bar_accfull[ab]);
             }
         }
     } else {
