@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
     __shared__ uint32_t tmem_base;
     __shared__ float s_mean[BM], s_rstd[BM];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay on the uniform datapath
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int STAGES = p.stages;
 
@@ -372,39 +373,44 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer
-        if (tc::elect_one()) {
+        // the whole warp walks the loop (uniform control flow and descriptor arithmetic, ring slot / parity advanced without
+        // divisions); one elected lane issues the MMAs and the commits
+        const bool leader = tc::elect_one();
+        {
             const uint32_t idesc = p.bf16 ? tc::umma_idesc_bf16(BM, BN) : tc::umma_idesc_f16(BM, BN);
             const uint32_t idesc2 = tc::umma_idesc_f16(BM, 2 * BN <= 256 ? 2 * BN : BN);
-            const uint32_t base = tc::smem_u32(smem);
+            const uint64_t dA = tc::umma_desc_sw128(tc::smem_u32(smem), 1024, 0);
+            constexpr uint64_t STAGE_U = STAGE_BYTES / 16, A_U = A_TILE / 16, W_U = W_TILE / 16;
+            int st = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < p.nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                tc::mbar_wait(&bar_wfull[s], ph);
-                if (!p.a_planes) tc::mbar_wait(&bar_afull[s], ph);
+                tc::mbar_wait(&bar_wfull[st], ph);
+                if (!p.a_planes) tc::mbar_wait(&bar_afull[st], ph);
                 tc::tc_fence_after();
-                const uint32_t a_base = base + s * STAGE_BYTES;
-                const uint32_t w_base = a_base + NSPLIT * A_TILE;
+                const uint64_t a_hi0 = dA + (uint64_t)st * STAGE_U;
+                const uint64_t w_hi0 = a_hi0 + NSPLIT * A_U;
 #pragma unroll
                 for (int k = 0; k < KB / 16; ++k) {
                     const uint32_t first = (uint32_t)(kb | k) ? 1u : 0u;
-                    const uint64_t a_hi = tc::umma_desc_sw128(a_base + k * 32, 1024, 0);
-                    const uint64_t b_hi = tc::umma_desc_sw128(w_base + k * 32, 1024, 0);
+                    const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2);
+                    const uint64_t b_hi = w_hi0 + (uint64_t)(k * 2);
                     if (NSPLIT == 2 && 2 * BN <= 256) {
                         // A_hi x [W_hi ; W_lo] in one N = 2*BN MMA (the two weight tiles are adjacent in the stage, D0 | D1
                         // adjacent in TMEM), then D1 += A_lo x W_hi
-                        tc::umma_bf16(tm, a_hi, b_hi, idesc2, first);
-                        tc::umma_bf16(tm + BN, tc::umma_desc_sw128(a_base + A_TILE + k * 32, 1024, 0), b_hi, idesc, 1u);
+                        if (leader) tc::umma_bf16(tm, a_hi, b_hi, idesc2, first);
+                        if (leader) tc::umma_bf16(tm + BN, a_hi + A_U, b_hi, idesc, 1u);
                     } else if (NSPLIT == 2) {                      // BN = 256: an MMA cannot be wider, three N = BN products
-                        tc::umma_bf16(tm, a_hi, b_hi, idesc, first);
-                        tc::umma_bf16(tm + BN, a_hi, tc::umma_desc_sw128(w_base + W_TILE + k * 32, 1024, 0), idesc, first);
-                        tc::umma_bf16(tm + BN, tc::umma_desc_sw128(a_base + A_TILE + k * 32, 1024, 0), b_hi, idesc, 1u);
+                        if (leader) tc::umma_bf16(tm, a_hi, b_hi, idesc, first);
+                        if (leader) tc::umma_bf16(tm + BN, a_hi, b_hi + W_U, idesc, first);
+                        if (leader) tc::umma_bf16(tm + BN, a_hi + A_U, b_hi, idesc, 1u);
                     } else {
-                        tc::umma_bf16(tm, a_hi, b_hi, idesc, first);
+                        if (leader) tc::umma_bf16(tm, a_hi, b_hi, idesc, first);
                     }
                 }
-                tc::umma_commit(&bar_empty[s]);
+                if (leader) tc::umma_commit(&bar_empty[st]);
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
             }
-            tc::umma_commit(&bar_acc);
+            if (leader) tc::umma_commit(&bar_acc);
         }
     } else {
         // ------------------------------------------------------------------ TMA producer of the weights
