@@ -64,6 +64,16 @@ __device__ __forceinline__ void split_store4(const float4 v, uint8_t* hi, uint8_
     }
 }
 
+// ring slot / round of K block kb for a run-time ring depth (1..4) without an integer division
+__device__ __forceinline__ void ring_pos(int kb, int stages, int& s, int& q) {
+    switch (stages) {
+        case 4: s = kb & 3; q = kb >> 2; break;
+        case 3: q = kb / 3; s = kb - 3 * q; break;
+        case 2: s = kb & 1; q = kb >> 1; break;
+        default: s = 0; q = kb; break;
+    }
+}
+
 template <int BN, int NSPLIT, bool PIPE>
 __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapA, const LinTcParams p) {
     constexpr int W_TILE = BN * 128;
@@ -174,7 +184,8 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
             }
         };
         auto store_kb = [&](const float4 (&v)[8], int kb) {
-            const int s = kb % STAGES;
+            int s, rq;
+            ring_pos(kb, STAGES, s, rq);
             uint8_t* a_hi = smem + s * STAGE_BYTES;
             uint8_t* a_lo = a_hi + A_TILE;
             const int k = kb * KB + c4 * 4;
@@ -184,7 +195,7 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
                 g4 = *reinterpret_cast<const float4*>(p.ln_g + k);
                 b4 = *reinterpret_cast<const float4*>(p.ln_b + k);
             }
-            if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], ((kb / STAGES) - 1) & 1);
+            if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], (rq - 1) & 1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = i * 16 + r_sub;
@@ -242,7 +253,8 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
                 if (kb >= p.nkb) break;
-                const int s = kb % STAGES;
+                int s, rq;
+                ring_pos(kb, STAGES, s, rq);
                 uint8_t* a_hi = smem + s * STAGE_BYTES;
                 uint8_t* a_lo = a_hi + A_TILE;
                 const int k = kb * KB + c4 * 4;
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
                     g4 = *reinterpret_cast<const float4*>(p.ln_g + k);
                     b4 = *reinterpret_cast<const float4*>(p.ln_b + k);
                 }
-                if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], ((kb / STAGES) - 1) & 1);
+                if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], (rq - 1) & 1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = i * 16 + r_sub;
@@ -418,8 +430,9 @@ __global__ void __launch_bounds__(LT_THREADS, PIPE ? 1 : 2) linear_tc_kernel(con
             tc::tma_prefetch_desc(&mapW);
             if (p.a_planes) tc::tma_prefetch_desc(&mapA);
             for (int kb = 0; kb < p.nkb; ++kb) {
-                const int s = kb % STAGES;
-                if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], ((kb / STAGES) - 1) & 1);
+                int s, rq;
+                ring_pos(kb, STAGES, s, rq);
+                if (kb >= STAGES) tc::mbar_wait(&bar_empty[s], (rq - 1) & 1);
                 uint8_t* a_hi = smem + s * STAGE_BYTES;
                 uint8_t* w_hi = a_hi + NSPLIT * A_TILE;
                 tc::mbar_expect_tx(&bar_wfull[s], NSPLIT * W_TILE + (p.a_planes ? NSPLIT * A_TILE : 0));

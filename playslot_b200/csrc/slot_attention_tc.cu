@@ -430,7 +430,8 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
     __shared__ float s_a0[2][SPAD];
     __shared__ float s_red[2][2][4][SPAD];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay on the uniform datapath
     const int S = p.S;
     // Work partition: the B * tpf token tiles (tpf = tiles per frame) are dealt to the CTAs as contiguous, equally long
     // ranges; a range is cut at frame boundaries into segments (the work items below).  Segment j of frame b -- counted over
@@ -488,7 +489,9 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------ MMA issuer
-        if (tc::elect_one()) {
+        // (the whole warp walks the loop with uniform control flow; one elected lane issues the MMAs and the commits)
+        const bool leader = tc::elect_one();
+        {
             const uint32_t idesc1 = tc::umma_idesc_f16_major(128, N1, 0, 0);
             const uint32_t idesc2 = tc::umma_idesc_f16_major(128, N1, 1, 1);
             const uint32_t st_base = tc::smem_u32(stage0), ao = tc::smem_u32(aop0), wo = tc::smem_u32(wop0);
@@ -507,10 +510,10 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t bd = q + (uint64_t)((h * AOP_HALF + k * 32) / 16);
                         const uint32_t acc = (h | k) ? 1u : 0u;
-                        tc::umma_bf16(lb, a + (uint64_t)((h * C_HALF + k * 32) / 16), bd, idesc1, acc);
-                        tc::umma_bf16(lb + N1, a + (uint64_t)(((2 + h) * C_HALF + k * 32) / 16), bd, idesc1, acc);
+                        if (leader) tc::umma_bf16(lb, a + (uint64_t)((h * C_HALF + k * 32) / 16), bd, idesc1, acc);
+                        if (leader) tc::umma_bf16(lb + N1, a + (uint64_t)(((2 + h) * C_HALF + k * 32) / 16), bd, idesc1, acc);
                     }
-                tc::umma_commit(&bar_lfull[g & 1]);
+                if (leader) tc::umma_commit(&bar_lfull[g & 1]);
             };
             int g = 0, k_item = 0;
             // The logits of the NEXT tile in stream order are always issued before the weighted sums of the current one -- also
@@ -547,12 +550,12 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint64_t bd = wd + (uint64_t)(kk * 2 * WOP_GROUP / 16);
                         const uint32_t acc = (t | kk) ? 1u : 0u;
-                        tc::umma_bf16(vb, a + (uint64_t)(kk * 2048 / 16), bd, idesc2, acc);
-                        tc::umma_bf16(vb + N1, a + (uint64_t)((2 * C_HALF + kk * 2048) / 16), bd, idesc2, acc);
+                        if (leader) tc::umma_bf16(vb, a + (uint64_t)(kk * 2048 / 16), bd, idesc2, acc);
+                        if (leader) tc::umma_bf16(vb + N1, a + (uint64_t)((2 * C_HALF + kk * 2048) / 16), bd, idesc2, acc);
                     }
-                    tc::umma_commit(&bar_empty[g % TC2_STAGES]);                   // feature tile consumed
-                    tc::umma_commit(&bar_wfree[g & 1]);
-                    if (t == ntiles - 1) tc::umma_commit(&bar_vfull[k_item & 1]);
+                    if (leader) tc::umma_commit(&bar_empty[g % TC2_STAGES]);                   // feature tile consumed
+                    if (leader) tc::umma_commit(&bar_wfree[g & 1]);
+                    if (t == ntiles - 1) if (leader) tc::umma_commit(&bar_vfull[k_item & 1]);
                 }
             }
         }
