@@ -4,7 +4,7 @@ bench.py -- PlaySlot seed + rollout throughput (frames/s) on N B200s, with the r
 kernel, the SlotAttention roofline (BASELINE.json metric) and the CPU baseline beside it.
 
   python bench.py --gpus N --steps K --warmup W            (our arm; torchrun launches N>1)
-  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle port of the reference)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the unmodified reference from oracle/_ref)
 
 A "step" = one pass of the seed+rollout path of src/05_evaluate_PlaySlot.py:112-139 over one batch of
 synthetic video per GPU: savi(videos, decode=False) -> forward_multiple_samples(posterior) -> savi.decode.
@@ -88,7 +88,37 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
+# ------------------------------------------------------------------------------------------------ reference arm
+
+def reference_models(experiment, device, seed=0):
+    """ the UNMODIFIED reference modules (oracle/_ref, installed by oracle/install_ref.py) built by the reference's own
+    lib/setup_model.py:29-116 from the shipped experiment_params.json, random-init, eval mode """
+    import contextlib
+    import copy
+    from oracle.install_ref import load_reference
+    with contextlib.redirect_stdout(sys.stderr):                   # the reference's builders print their configuration
+        setup_model, setup_predictor, experiment_json = load_reference()
+        j = experiment_json(experiment)
+        torch.manual_seed(seed)
+        savi = setup_model(copy.deepcopy(j["model"])).eval().to(device)
+        pred = setup_predictor(copy.deepcopy(j)).eval().to(device)
+    return savi, pred
+
+
+@torch.no_grad()
+def reference_pipeline(savi, pred, video, ns, npred):
+    """ src/05_evaluate_PlaySlot.py:112-139 through the reference's public API """
+    out = savi(video, num_imgs=ns + npred, decode=False)
+    pred_slots, _ = pred.forward_multiple_samples(out["slot_history"], 1, ns, npred, use_posterior=True)
+    B, n, P, S, D = pred_slots.shape
+    imgs, _ = savi.decode(pred_slots.reshape(B * n * P, S, D))
+    return imgs
+
+
+def reference_available():
+    from oracle.install_ref import available
+    return available()
+
 
 def oracle_models(cfg, seed=0):
     """ random-init weights of the architecture (our module mirror's initialiser), as CPU state dicts """
@@ -115,58 +145,74 @@ def oracle_step(cfg, ssd, psd, B, seed):
     return time.perf_counter() - t0
 
 
-def torch_cuda_baseline(cfg, ssd, psd, B):
-    """ the same workload through the oracle port on the GPU: eager ATen / cuDNN / cuBLAS launches with PyTorch's default
-    flags (cuDNN TF32 convolutions on), i.e. what the reference's own nn.Modules dispatch to on CUDA.  Informational. """
-    from oracle import playslot_oracle as O
-    scfg, pcfg = cfg["model"]["model_params"], cfg["predictor"]["predictor_params"]
-    dev = "cuda"
-    ssd = {k: v.to(dev) for k, v in ssd.items()}
-    psd = {k: v.to(dev) for k, v in psd.items()}
+def cpu_reference_timer(cores):
+    """ returns (step(B, seed) -> seconds, kind, description): the unmodified reference on the host cores when oracle/_ref
+    travelled with the snapshot, otherwise the oracle port """
+    torch.set_num_threads(cores)
+    if reference_available():
+        savi, pred = reference_models(EXPERIMENT, "cpu")
+
+        def step(B, seed):
+            g = torch.Generator().manual_seed(seed)
+            video = torch.rand(B, NUM_SEED + NUM_PREDS, 3, 64, 64, generator=g)
+            t0 = time.perf_counter()
+            reference_pipeline(savi, pred, video, NUM_SEED, NUM_PREDS)
+            return time.perf_counter() - t0
+        return step, "reference", "the unmodified reference modules (oracle/_ref, lib/setup_model.py builders), torch CPU fp32"
+    from playslot_b200 import configs
+    cfg = configs.experiment(EXPERIMENT)
+    ssd, psd = oracle_models(cfg)
+    return (lambda B, seed: oracle_step(cfg, ssd, psd, B, seed)), "port", "torch CPU fp32 oracle port (oracle/_ref absent)"
+
+
+def torch_cuda_baseline(B, reps=10):
+    """ the 10x target's denominator ('GPU reference baseline'): the unmodified reference modules
+    .to('cuda'), eager, PyTorch's default flags (cuDNN TF32 convolutions on, fp32 matmuls), CUDA-event timed """
+    savi, pred = reference_models(EXPERIMENT, "cuda")
     T = NUM_SEED + NUM_PREDS
-    S, D, A = scfg["num_slots"], scfg["slot_dim"], pcfg["action_dim"]
-    video = torch.rand(B, T, 3, 64, 64, device=dev)
-    per_slot = pcfg["LatentAction"]["model_name"] == "VQSimpleMLPSlotLatentAction"
-    noise = torch.randn((B, T - 1, S, A) if per_slot else (B, T - 1, A), device=dev)
-    init_noise = torch.randn(B, S, D, device=dev) if scfg["initializer"] == "LearnedRandom" else None
+    video = torch.rand(B, T, 3, 64, 64, device="cuda")
     ts = []
-    with torch.no_grad():
-        for i in range(3):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            O.seed_rollout_pipeline(ssd, scfg, psd, pcfg, video, NUM_SEED, NUM_PREDS, noise, init_noise)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-    ms = min(ts[1:])
-    return {"value": B * T / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "kind": "oracle port run with torch on cuda:0 (eager ATen/cuDNN/cuBLAS, "
-            "default flags: TF32 convolutions)", "batch": B}
+    for i in range(2 + reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reference_pipeline(savi, pred, video, NUM_SEED, NUM_PREDS)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts = sorted(ts[2:])
+    ms = ts[len(ts) // 2]
+    del savi, pred
+    torch.cuda.empty_cache()
+    return {"value": B * T / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "ms_min": ts[0], "ms_max": ts[-1], "timed_reps": reps,
+            "warmup_reps": 2, "batch": B,
+            "kind": "unmodified reference modules (oracle/_ref) on cuda:0: eager ATen / cuDNN / cuBLAS, default flags (TF32 "
+                    "convolutions, fp32 matmuls); median of the timed reps"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from playslot_b200 import configs
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = configs.experiment(EXPERIMENT)
-    ssd, psd = oracle_models(cfg)
+    step, kind, what = cpu_reference_timer(cores)
     B = args.ref_batch
     for i in range(args.warmup):
-        oracle_step(cfg, ssd, psd, 1, 100 + i)
-    times = [oracle_step(cfg, ssd, psd, B, 200 + i) for i in range(args.steps)]
+        step(1, 100 + i)
+    times = [step(B, 200 + i) for i in range(args.steps)]
     tot = sum(times)
     frames = B * (NUM_SEED + NUM_PREDS) * args.steps
     val = frames / tot
+    cfg = workload_config(args.batch, args.gpus)                   # the workload of our arm ...
+    cfg["ref_batch"] = B                                           # ... and what this arm actually ran per step
+    cfg["sample"] = (f"bounded sample: {B} videos x {NUM_SEED + NUM_PREDS} frames per step on the host cores (the GPU arm runs "
+                     f"{args.batch} videos per GPU per step); frames/s is normalised per frame")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.batch, args.gpus),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{B} videos x {NUM_SEED + NUM_PREDS} frames per step, {args.steps} steps, torch CPU fp32, "
-                                   f"{cores} threads (oracle port of the reference; the PyTorch reference itself cannot travel to the GPU box)"},
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{B} videos x {NUM_SEED + NUM_PREDS} frames per step, {args.steps} steps, {cores} threads; {what}"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -453,18 +499,24 @@ def run_ours(args):
                 savi.conv_mode = args.conv_mode
                 ops.set_linear_mode(args.conv_mode)
         cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        ssd, psd = oracle_models(cfg)
-        oracle_step(cfg, ssd, psd, 1, 7)                                # warm-up
-        bs = args.ref_batch
-        dt = oracle_step(cfg, ssd, psd, bs, 8)
         try:
-            line["torch_cuda_baseline"] = torch_cuda_baseline(cfg, ssd, psd, B)
+            if not reference_available():
+                raise FileNotFoundError("oracle/_ref did not travel with the snapshot")
+            tcb = torch_cuda_baseline(B)
+            line["torch_cuda_baseline"] = tcb
+            line["vs_torch_cuda"] = {"device_resident": value / tcb["value"], "e2e": e2e_value / tcb["value"],
+                                     "target": 10.0, "note": "our frames/s / the reference's PyTorch-CUDA frames/s, same GPU, same batch"}
+            if "value" in line.get("tf32_class_mode", {}):
+                line["vs_torch_cuda"]["tf32_class_mode"] = line["tf32_class_mode"]["value"] / tcb["value"]
         except Exception as e:                                         # informational only
             line["torch_cuda_baseline"] = {"error": repr(e)[:200]}
-        line["cpu_baseline"] = {"value": bs * T / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        step_cpu, kind, what = cpu_reference_timer(cores)
+        step_cpu(1, 7)                                                  # warm-up
+        bs = args.ref_batch
+        dt = step_cpu(bs, 8)
+        line["cpu_baseline"] = {"value": bs * T / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"{bs} videos x {T} frames of the same workload, one pass after a 1-video warm-up "
-                                          f"({dt:.1f} s), torch CPU fp32 oracle port, {cores} threads"}
+                                          f"({dt:.1f} s), {cores} threads; {what}"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

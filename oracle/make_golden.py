@@ -42,6 +42,9 @@ CASES = {
     "buttonpress":      ("ButtonPress",     2, 4, 3, 13, 1.0, {}),
     "gridshapes5":      ("GridShapes5Objs", 2, 6, 4, 14, 1.0, {}),
     "sketchy_sharp":    ("Sketchy",         1, 6, 6, 15, 4.0, {}),
+    # the benchmark length (BASELINE.json configs[2]: 6 seed + 15 predicted frames): errors compound over 15 roll-out steps
+    "gridshapes5_bench": ("GridShapes5Objs", 2, 6, 15, 16, 1.0, {"decode_last": 1}),
+    "blockpush_bench":   ("BlockPush",       2, 6, 15, 17, 1.0, {"decode_last": 1}),
 }
 DECODE_LAST = 2       # decode only the last 2 predicted frames of every video (fixture size)
 
@@ -51,7 +54,8 @@ def manifest_of(module):
 
 
 def run_case(name, setup_model, setup_predictor):
-    exp, B, ns, npred, wseed, sharpen, _ = CASES[name]
+    exp, B, ns, npred, wseed, sharpen, over = CASES[name]
+    decode_last = over.get("decode_last", DECODE_LAST)
     j = json.load(open(os.path.join(REF, "experiments", exp, "predictors", "PlaySlot", "experiment_params.json")))
     scfg = copy.deepcopy(j["model"]["model_params"])
     pcfg = copy.deepcopy(j["predictor"]["predictor_params"])
@@ -101,7 +105,7 @@ def run_case(name, setup_model, setup_predictor):
         finally:
             torch.randn = real_randn
         pred_slots = pred_slots[:, 0]
-        dec_in = pred_slots[:, -DECODE_LAST:].reshape(B * DECODE_LAST, S, D)
+        dec_in = pred_slots[:, -decode_last:].reshape(B * decode_last, S, D)
         recon, (recons, masks) = savi.decode(dec_in)
 
         # margins of the VQ argmin (for the exact index comparison)
@@ -113,7 +117,7 @@ def run_case(name, setup_model, setup_predictor):
 
     fx = {
         "case": name, "experiment": exp, "B": B, "num_seed": ns, "num_preds": npred,
-        "weight_seed": wseed, "sharpen": sharpen, "decode_last": DECODE_LAST,
+        "weight_seed": wseed, "sharpen": sharpen, "decode_last": decode_last,
         "savi_cfg": scfg, "predictor_cfg": pcfg,
         "predictor_name": j["predictor"]["predictor_name"],
         "savi_manifest": sman, "predictor_manifest": pman,
@@ -188,22 +192,99 @@ def run_aux_cases(setup_predictor):
     return res
 
 
+class _RecordDraws:
+    """ records every torch.randint / torch.rand result the reference draws while sampling prior actions, in call order """
+
+    def __enter__(self):
+        self.randint, self.rand = [], []
+        self._ri, self._r = torch.randint, torch.rand
+
+        def ri(*a, **k):
+            t = self._ri(*a, **k)
+            self.randint.append(t.clone().cpu())
+            return t
+
+        def r(*a, **k):
+            t = self._r(*a, **k)
+            self.rand.append(t.clone().cpu())
+            return t
+        torch.randint, torch.rand = ri, r
+        return self
+
+    def __exit__(self, *exc):
+        torch.randint, torch.rand = self._ri, self._r
+        return False
+
+
+def run_prior_cases(setup_predictor):
+    """ forward_multiple_samples with PRIOR samples (random codebook actions + random variability latents,
+    LatentActionPredictors.py:148-157,383-396,511-532): the reference's draws are recorded so that the CUDA path can replay
+    them; single-action model with variability (BlockPush) and per-slot model without (GridShapes5Objs) """
+    res = {}
+    for exp, wseed in (("BlockPush", 41), ("GridShapes5Objs", 42)):
+        j = json.load(open(os.path.join(REF, "experiments", exp, "predictors", "PlaySlot", "experiment_params.json")))
+        pred = setup_predictor(copy.deepcopy(j)).eval()
+        man = manifest_of(pred)
+        sd = synth_state_dict(man, wseed)
+        sd["dynamics_model.pos_emb.pe"] = pred.state_dict()["dynamics_model.pos_emb.pe"].clone()
+        pred.load_state_dict(sd, strict=True)
+        S = j["model"]["model_params"]["num_slots"]
+        A = j["predictor"]["predictor_params"]["action_dim"]
+        B, ns, npred, nsamp = 2, 6, 4, 3
+        g = torch.Generator().manual_seed(wseed + 5)
+        sh = torch.randn(B, ns + npred, S, 128, generator=g)
+        per_slot = j["predictor"]["predictor_params"]["LatentAction"]["model_name"] == "VQSimpleMLPSlotLatentAction"
+        noise = synth_noise((B, ns + npred - 1, S, A) if per_slot else (B, ns + npred - 1, A), wseed)
+        torch.manual_seed(wseed)
+        real_randn = torch.randn
+        torch.randn = lambda *a, **k: noise.clone()
+        try:
+            with torch.no_grad(), _RecordDraws() as rec:
+                prior, prior_idx = pred.forward_multiple_samples(sh, nsamp, ns, npred, use_posterior=False)
+                n_prior_only = (len(rec.randint), len(rec.rand))
+                mixed, mixed_idx = pred.forward_multiple_samples(sh, nsamp, ns, npred, use_posterior=True)
+        finally:
+            torch.randn = real_randn
+        res[exp] = {"manifest": man, "weight_seed": wseed, "cfg": j["predictor"]["predictor_params"],
+                    "predictor_name": j["predictor"]["predictor_name"], "input_seed": wseed + 5,
+                    "B": B, "num_seed": ns, "num_preds": npred, "num_samples": nsamp, "num_slots": S,
+                    "randint_draws": rec.randint, "rand_draws": rec.rand, "draws_prior_only": n_prior_only,
+                    "prior_pred_slots": prior.clone(), "prior_action_idx": prior_idx.clone(),
+                    "mixed_pred_slots": mixed.clone(), "mixed_action_idx": mixed_idx.clone(),
+                    "sh_checksum": float(sh.double().sum())}
+    return res
+
+
 def main():
     setup_model, setup_predictor = _import_reference()
     outdir = os.path.join(REPO, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
-    for name in ([] if os.environ.get("GOLDEN_ONLY_AUX") else CASES):
+    if os.environ.get("GOLDEN_ONLY_PRIOR"):
+        pr = run_prior_cases(setup_predictor)
+        path = os.path.join(outdir, "prior_samples.pt")
+        torch.save(pr, path)
+        print(f"prior_samples: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+        return
+    only = os.environ.get("GOLDEN_ONLY_CASES")
+    cases = [c for c in CASES if (not only or c in only.split(","))]
+    for name in ([] if os.environ.get("GOLDEN_ONLY_AUX") else cases):
         fx = run_case(name, setup_model, setup_predictor)
         path = os.path.join(outdir, f"{name}.pt")
         torch.save(fx, path)
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB), vq margin {fx['vq_margin_min']:.3e}, "
               f"mask max {float(fx['masks'].max()):.3f}, sa mask max {float(fx['sa_masks_last'].max()):.3f}")
+    if only:
+        return
     aux = run_aux_cases(setup_predictor)
     path = os.path.join(outdir, "aux_predictors.pt")
     torch.save(aux, path)
     print(f"aux_predictors: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
     if os.environ.get("GOLDEN_ONLY_AUX"):
         return
+    pr = run_prior_cases(setup_predictor)
+    path = os.path.join(outdir, "prior_samples.pt")
+    torch.save(pr, path)
+    print(f"prior_samples: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
     sa = run_slot_attention_cases(setup_model)
     path = os.path.join(outdir, "slot_attention.pt")
     torch.save(sa, path)

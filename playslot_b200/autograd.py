@@ -160,11 +160,19 @@ class _InvDynTail(torch.autograd.Function):
         mv, noise, z, idx, codebook = ctx.saved_tensors
         d_mv = ops.invdyn_tail_bwd(mv, noise, z, idx, codebook, g_dist, g_z, g_proto, g_var, g_quant, ctx.per_slot)
         d_cb = None
-        if ctx.needs_input_grad[2] and g_commit is not None:
+        if ctx.needs_input_grad[2]:
+            # trainable (non-EMA) codebook
             A = codebook.shape[1]
-            zq = codebook[idx.reshape(-1)]
-            contrib = (2.0 / A) * (zq - z.reshape(-1, A)) * g_commit.reshape(-1, 1)       # commit = mean_A (z_q - sg(z))^2
-            d_cb = torch.zeros_like(codebook).index_add_(0, idx.reshape(-1), contrib)
+            d_cb = torch.zeros_like(codebook)
+            if g_commit is not None:
+                zq = codebook[idx.reshape(-1)]
+                contrib = (2.0 / A) * (zq - z.reshape(-1, A)) * g_commit.reshape(-1, 1)   # commit = mean_A (z_q - sg(z))^2
+                d_cb.index_add_(0, idx.reshape(-1), contrib)
+            if not ctx.per_slot and g_var is not None:
+                # InvDynS: variability = z - E[idx] comes from a second, differentiable codebook lookup
+                # (quantization.py:365-368 via LatentAction.py:118-125), so d E[idx] -= g_var.  (InvDynM passes the
+                # straight-through prototype: variability = z - sg-equivalent value, no codebook gradient.)
+                d_cb.index_add_(0, idx.reshape(-1), -g_var.reshape(-1, A))
         return d_mv, None, d_cb, None
 
 

@@ -15,11 +15,28 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
+def _digest(paths):
+    """ content hash of the sources + the compiler flags: the rebuild decision does not trust mtimes """
+    import hashlib
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale(target, sources):
-    if not os.path.exists(target):
+    """ True when `target` is missing or was built from different source contents (stamp file next to it) """
+    stamp = target + ".stamp"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    return open(stamp).read().strip() != _digest(sources)
+
+
+def _mark(target, sources):
+    with open(target + ".stamp", "w") as f:
+        f.write(_digest(sources))
 
 
 def build(force=False, verbose=False):
@@ -27,23 +44,26 @@ def build(force=False, verbose=False):
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "playslot_b200.h")]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    headers = [d for d in deps if not d.endswith(".cu")]
     objs, procs = [], []
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        if force or _stale(o, [s] + [d for d in deps if not d.endswith(".cu")]):
+        if force or _stale(o, [s] + headers):
             cmd = [NVCC] + FLAGS + ["-c", s, "-o", o]
-            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
-    for s, pr in procs:
+    for s, o, pr in procs:
         out, _ = pr.communicate()
         log.append(f"== {os.path.basename(s)}\n{out}")
         if pr.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError(f"nvcc failed on {s}")
-    if procs or force or _stale(LIB, objs):
+        _mark(o, [s] + headers)
+    if procs or force or _stale(LIB, deps):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda"]
         subprocess.run(cmd, check=True)
+        _mark(LIB, deps)
     with open(os.path.join(objdir, "ptxas.log"), "a" if not force else "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -315,11 +315,8 @@ extern "C" int ps_mha_bwd(const float* qkv, int ld, const float* dout, int ldo, 
     p.spf = slots_per_frame; p.scale = 1.0f / sqrtf((float)head_dim);
     const size_t smem = (size_t)(4 * L * (head_dim + 1) + 2 * L * L) * sizeof(float);
     PS_REQUIRE(smem <= 200 * 1024, "ps_mha_bwd: %d tokens x head_dim %d exceed the shared-memory budget of the backward kernel", L, head_dim);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        PS_CUDA(cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
+    static PsSmemConfig smem_cfg = {};
+    if (smem > 48 * 1024) PS_CUDA(ps_ensure_smem(mha_bwd_kernel, smem, smem_cfg, 200 * 1024));
     PS_REQUIRE(n_heads <= 65535, "ps_mha_bwd: too many heads");
     mha_bwd_kernel<<<dim3(n_seq, n_heads), 256, smem, (cudaStream_t)stream>>>(p);
     PS_COUNT_LAUNCH();

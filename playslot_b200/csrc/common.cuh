@@ -43,6 +43,23 @@ void ps_set_error(const char* fmt, ...);
 extern unsigned long long g_ps_launch_count;
 #define PS_COUNT_LAUNCH() (++g_ps_launch_count)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE setting of a kernel: remember, per device, the largest size that
+// has been configured (a process may drive several GPUs).  `set_bytes` (default: smem) is the value passed to the driver.
+struct PsSmemConfig { size_t bytes[64]; };
+template <typename Kernel>
+static inline cudaError_t ps_ensure_smem(Kernel kernel, size_t smem, PsSmemConfig& cfg, size_t set_bytes = 0) {
+    if (set_bytes == 0) set_bytes = smem;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)set_bytes);
+    if (smem > cfg.bytes[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)set_bytes);
+        if (e != cudaSuccess) return e;
+        cfg.bytes[dev] = set_bytes;
+    }
+    return cudaSuccess;
+}
+
 static inline bool ps_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 #ifdef __CUDACC__

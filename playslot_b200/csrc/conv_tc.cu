@@ -381,11 +381,8 @@ int launch_conv_tc(const CUtensorMap& mA_hi, const CUtensorMap& mA_lo, const CUt
                    const CUtensorMap& mW, const ConvTcParams& p, cudaStream_t st) {
     const size_t smem = (size_t)NSPLIT * p.a_rows * ROWB + (size_t)p.stages * NSPLIT * WTAP_BYTES + 1024;
     PS_REQUIRE(smem <= 227 * 1024, "ps_conv5x5_tc: image width %d needs %zu bytes of shared memory", p.W, smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        PS_CUDA(cudaFuncSetAttribute(conv5x5_tc_kernel<TILES, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static PsSmemConfig smem_cfg = {};
+    PS_CUDA(ps_ensure_smem(conv5x5_tc_kernel<TILES, NSPLIT>, smem, smem_cfg));
     const int n_items = p.n_img * p.items_per_img;
     conv5x5_tc_kernel<TILES, NSPLIT><<<n_items < p.n_ctas ? n_items : p.n_ctas, 192, smem, st>>>(mA_hi, mA_lo, mA_hi8, mA_lo8, mW, p);
     PS_COUNT_LAUNCH();
@@ -760,11 +757,8 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
 template <int SPAD>
 int launch_comp_tc(const CUtensorMap& mA_hi, const CUtensorMap& mA_lo, const CUtensorMap& mW, const CompTcParams& p, cudaStream_t st) {
     const size_t smem = ((CT_WBYTES + 1023) & ~1023) + (size_t)p.nbuf * 2 * p.a_rows * ROWB + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PS_CUDA(cudaFuncSetAttribute(dec_composite_tc_kernel<SPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static PsSmemConfig smem_cfg = {};
+    PS_CUDA(ps_ensure_smem(dec_composite_tc_kernel<SPAD>, smem, smem_cfg));
     const int n_items = p.M * p.tiles_per_img;
     dec_composite_tc_kernel<SPAD><<<n_items < p.n_ctas ? n_items : p.n_ctas, 192, smem, st>>>(mA_hi, mA_lo, mW, p);
     PS_COUNT_LAUNCH();

@@ -484,11 +484,8 @@ static int mha_run(const float* qkv, int ld, const float* res, float* out, void*
                "ps_mha_planes: plane output needs head_dim %% 4 == 0, 12 <= L and a sequence that fits the tiled kernel");
     if (vec && L >= 12 && smem_tiled <= 200 * 1024) {
         const size_t smem = smem_tiled;
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            PS_CUDA(cudaFuncSetAttribute(mha_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = 200 * 1024;
-        }
+        static PsSmemConfig smem_cfg = {};
+        if (smem > 48 * 1024) PS_CUDA(ps_ensure_smem(mha_tiled_kernel, smem, smem_cfg, 200 * 1024));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(n_seq, n_heads); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
         cudaLaunchAttribute attr[1];
@@ -499,11 +496,8 @@ static int mha_run(const float* qkv, int ld, const float* res, float* out, void*
     } else {
         size_t smem = (size_t)(L * (head_dim + 1) + L * head_dim + 4 + 16 * L + 16 * head_dim) * sizeof(float);
         PS_REQUIRE(smem <= 200 * 1024, "ps_mha: sequence of %d tokens x head_dim %d does not fit in shared memory", L, head_dim);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            PS_CUDA(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = 200 * 1024;
-        }
+        static PsSmemConfig smem_cfg = {};
+        if (smem > 48 * 1024) PS_CUDA(ps_ensure_smem(mha_kernel, smem, smem_cfg, 200 * 1024));
         mha_kernel<<<dim3(n_seq, n_heads), 128, smem, (cudaStream_t)stream>>>(p);
     }
     PS_COUNT_LAUNCH();
@@ -679,11 +673,8 @@ template <int KS, int COUT_T>
 static int launch_conv(const ConvParams& p, cudaStream_t st) {
     constexpr int HH = CV_T + KS - 1;
     const size_t smem = (size_t)(CV_CI * HH * CV_HS + CV_CI * KS * KS * 8 * COUT_T) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        PS_CUDA(cudaFuncSetAttribute(conv2d_kernel<KS, COUT_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static PsSmemConfig smem_cfg = {};
+    PS_CUDA(ps_ensure_smem(conv2d_kernel<KS, COUT_T>, smem, smem_cfg));
     dim3 grid((p.H / CV_T) * (p.W / CV_T), p.n);
     conv2d_kernel<KS, COUT_T><<<grid, 256, smem, st>>>(p);
     PS_COUNT_LAUNCH();

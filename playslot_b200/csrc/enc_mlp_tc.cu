@@ -363,11 +363,8 @@ extern "C" int ps_enc_mlp_planes(const float* X, int ldx, int K1, const float* l
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = EM_SMEM + 1024;
-    static bool configured = false;
-    if (!configured) {
-        PS_CUDA(cudaFuncSetAttribute(enc_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static PsSmemConfig smem_cfg = {};
+    PS_CUDA(ps_ensure_smem(enc_mlp_tc_kernel, smem, smem_cfg));
     enc_mlp_tc_kernel<<<p.n_tiles < sms ? p.n_tiles : sms, EM_THREADS, smem, (cudaStream_t)stream>>>(mW1, mW2, p);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();

@@ -458,11 +458,8 @@ int launch_linear_tc_impl(const CUtensorMap& mW, const CUtensorMap& mA, const Li
     size_t smem = (size_t)p.stages * STAGE_BYTES;
     if (smem < 8 * 32 * 33 * sizeof(float)) smem = 8 * 32 * 33 * sizeof(float);      // epilogue transpose scratch
     smem += 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PS_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, NSPLIT, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static PsSmemConfig smem_cfg = {};
+    PS_CUDA(ps_ensure_smem(linear_tc_kernel<BN, NSPLIT, PIPE>, smem, smem_cfg));
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
     PS_CUDA(tc::launch_pdl(linear_tc_kernel<BN, NSPLIT, PIPE>, grid, dim3(LT_THREADS), smem, st, mW, mA, p));
     PS_COUNT_LAUNCH();

@@ -236,11 +236,8 @@ __global__ __launch_bounds__(256, 1) void sa_main_kernel(SaMainParams p) {
 template <int SMAX>
 static int launch_sa_main(const SaMainParams& p, cudaStream_t st) {
     const size_t smem = (size_t)(2 * SA_TT * SA_XS + SMAX * SA_D + SA_TT * SMAX + SA_TT + 8 * SMAX) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        PS_CUDA(cudaFuncSetAttribute(sa_main_kernel<SMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static PsSmemConfig smem_cfg = {};
+    PS_CUDA(ps_ensure_smem(sa_main_kernel<SMAX>, smem, smem_cfg));
     sa_main_kernel<SMAX><<<dim3(p.CH, p.B), 256, smem, st>>>(p);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();

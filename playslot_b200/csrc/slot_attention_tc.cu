@@ -301,11 +301,8 @@ __global__ void __launch_bounds__(288, 2) sa_main_tc_kernel(const SaTcParams p) 
 template <int SPAD>
 int launch_sa_main_tc(const SaTcParams& p, cudaStream_t st) {
     const size_t smem = 4 * C_HALF + 2 * (2 * SPAD * 128) + 16 * (2 * (SPAD / 8) * 128) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        PS_CUDA(cudaFuncSetAttribute(sa_main_tc_kernel<SPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static PsSmemConfig smem_cfg = {};
+    PS_CUDA(ps_ensure_smem(sa_main_tc_kernel<SPAD>, smem, smem_cfg));
     sa_main_tc_kernel<SPAD><<<dim3(p.CH, p.B), 288, smem, st>>>(p);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
@@ -720,11 +717,8 @@ __global__ void __launch_bounds__(320, 1) sa_main_tc2_kernel(const __grid_consta
 template <int SPAD>
 int launch_sa_main_tc2(const CUtensorMap& mC, const SaTc2Params& p, cudaStream_t st) {
     const size_t smem = (size_t)TC2_STAGES * TC2_STAGE_BYTES + 2 * (2 * (2 * SPAD) * 128) + 2 * (16 * 2 * (SPAD / 8) * 128) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        PS_CUDA(cudaFuncSetAttribute(sa_main_tc2_kernel<SPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static PsSmemConfig smem_cfg = {};
+    PS_CUDA(ps_ensure_smem(sa_main_tc2_kernel<SPAD>, smem, smem_cfg));
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long total_tiles = (long long)p.B * ((p.N + TILE - 1) / TILE);

@@ -232,6 +232,21 @@ class MetaAttention(nn.Module):
     def forward(self, x):
         raise NotImplementedError("Base-Class does not implement a 'forward' method...")
 
+    def attention(self, query, key, value, mask=None, **kwargs):
+        """ reference API (attention.py:211-240): softmax(q k^T / sqrt(d_h), mask==0 -> -1e9) v on head-split tensors
+        (B * heads, L, d_h), through the attention kernel (self-attention geometry: as many keys as queries; mask=None or the
+        block-causal staircase).  The (L, L) attention maps are not materialised. """
+        require_cuda(query, type(self).__name__)
+        no_grad_only(type(self).__name__, query, key, value)
+        if query.shape != key.shape or key.shape != value.shape:
+            raise NotImplementedError("MetaAttention.attention: the kernel covers self-attention shapes (num_queries == num_keys)")
+        n, L, dh = query.shape
+        qkv = torch.cat([f32c(query), f32c(key), f32c(value)], dim=-1).reshape(n * L, 3 * dh)
+        scale_fix = (dh ** -0.5) / (self.head_dim ** -0.5)             # the reference scales by self.head_dim, the kernel by d_h
+        if scale_fix != 1.0:
+            qkv[:, :dh] *= scale_fix
+        return ops.mha(qkv, n, L, 1, dh, self.spf_of(mask, L)).view(n, L, dh)
+
     def get_attention_masks(self, reshape=None):
         """ The fused kernel never writes the (B*heads, L, L) attention maps to memory. """
         if self.attention_masks is None:

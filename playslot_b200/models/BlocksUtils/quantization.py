@@ -99,6 +99,12 @@ class VectorQuantizer(nn.Module):
         for i, b in bins.items():
             self.trackers[i].load(b)
 
+    def reset(self, i):
+        """ as upstream (quantization.py:247-250), including its quirk: the tracker DICT is replaced by one meter sized
+        by the chunk dimension """
+        for i in self.trackers.keys():
+            self.trackers = EmaCodebookMeter(self.chunk_dims[int(i)])
+
     def track_assigment(self, emb_ind, i):
         self.trackers[i].update(emb_ind)
 
@@ -171,7 +177,7 @@ class EmaVectorQuantizer(nn.Module):
         cnt = self.ema_alpha * self.ema_count + (1 - self.ema_alpha) * enc_sum
         self.ema_count.copy_((cnt + self.epsilon) / (B + self.num_embs * self.epsilon) * B)
         self.ema_weight.copy_(self.ema_alpha * self.ema_weight + (1 - self.ema_alpha) * dw)
-        self.vq.embeddings['0'].weight.data.copy_(self.ema_weight / (self.ema_count.unsqueeze(1) + 1e-8))
+        self.vq.embeddings['0'].weight.copy_(self.ema_weight / (self.ema_count.unsqueeze(1) + 1e-8))    # bumps _version
 
     def forward(self, z):
         z_q, losses, idx = self.vq(z)

@@ -1,6 +1,7 @@
 """
 Decoders -- mirror of src/models/EncodersDecoders/decoders.py.
 """
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -74,6 +75,29 @@ class Decoder(nn.Module):
         return self.decoder[-1]
 
     def forward(self, x):
-        """ Generic module-level forward (B*S, C, H, W) -> (B*S, 4, H, W) is not a hot path: SAVi.decode fuses the
-        first conv with the broadcast and the last one with the compositing.  Not implemented stand-alone. """
-        raise NotImplementedError("Decoder.forward: use SAVi.decode (fused broadcast / conv chain / compositing kernels)")
+        """ Stand-alone module forward (decoders.py:103-111): (n, C, H, W) -> (n, out_channels, H, W) through the exact fp32
+        convolution kernels.  Not the hot path -- SAVi.decode collapses the first convolution with the broadcast and fuses
+        the last one with the compositing -- but callable like the reference's. """
+        from ... import ops
+        from .._common import require_cuda, no_grad_only, f32c
+        require_cuda(x, "Decoder")
+        fc = self.final_conv()
+        no_grad_only("Decoder", x, fc.weight)
+        h = f32c(x)
+        for m in self.decoder[:-1]:
+            if isinstance(m, ConvBlock):
+                h = m.run(h)
+            elif isinstance(m, Upsample):
+                h = m(h)
+                h = h if h.is_contiguous() else h.contiguous()
+        co, ci, k, _ = fc.weight.shape
+        if k not in (3, 5) or co > 32:
+            raise NotImplementedError("Decoder.forward: final convolution must be 3x3 / 5x5 with <= 32 output channels")
+        # the direct-convolution kernel computes 32 output channels per pass: pad the 4-channel head with zero filters
+        wp = torch.zeros(32, ci, k, k, device=h.device, dtype=torch.float32)
+        wp[:co] = fc.weight.detach()
+        bp = torch.zeros(32, device=h.device, dtype=torch.float32)
+        if fc.bias is not None:
+            bp[:co] = fc.bias.detach()
+        y = ops.conv2d(h, ops.pack_conv_weight(wp), bp, k, False)
+        return y[:, :co].contiguous()

@@ -211,10 +211,13 @@ class SlotGPTDymamicsModel(BaseSlotDynamicsModel):
         B, Fr, S, D = slots.shape
         if Fr > self.context_length:
             raise ValueError(f"num_frames = {Fr} cannot be > {self.context_length = }")
-        if self.training and self.pos_emb.dropout.p > 0:
-            raise NotImplementedError("positional-encoding dropout > 0 in train mode is not implemented")
         pe = f32c(self.pos_emb.table())
-        t = self._embed(slots, action_protos, action_vars, pe_table=pe, n_frames=Fr).view(B, Fr * S, -1)
+        t = self._embed(slots, action_protos, action_vars, pe_table=pe, n_frames=Fr)
+        if self.training and self.pos_emb.dropout.p > 0:
+            # train-mode dropout after the positional encoding (model_blocks.py:211): the same nn.Dropout call on the same
+            # (B, F, S, E) tensor, device RNG, like the reference on CUDA
+            t = self.pos_emb.dropout(t.view(B, Fr, S, -1))
+        t = t.reshape(B, Fr * S, -1)
         for blk in self.dynamics_model:
             t = blk.run(t, slots_per_frame=S)
         out = self._head(t).view(B, Fr, S, D)

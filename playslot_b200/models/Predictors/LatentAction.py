@@ -102,11 +102,18 @@ class BaseSlotLatentAction(nn.Module):
         variability = out["variability"]
         if self.training:
             self._train_side_effects(out["z"].detach(), idx)
-            if self.use_ema_vq and self.quantizer.update and not per_slot:
-                # the reference looks the codeword up a second time for the variability (quantization.py:365-368), i.e.
-                # AFTER the EMA update of the codebook in train mode; z keeps its gradient, the codeword does not
-                _, zq2, _, _ = ops.vq_lookup(f32c(out["z"].detach()), self._codebook())
-                variability = out["z"] - zq2
+            if not per_slot:
+                # the reference looks the codeword up a second time for the variability (forward_one inside get_variability,
+                # quantization.py:365-368): its usage meter is updated a second time per forward ...
+                vq = self.quantizer.vq if self.use_ema_vq else self.quantizer
+                if self.use_ema_vq and self.quantizer.update:
+                    # ... and in train mode with EMA the second lookup sees the ALREADY-UPDATED codebook; z keeps its
+                    # gradient, the codeword does not
+                    _, zq2, idx2, _ = ops.vq_lookup(f32c(out["z"].detach()), self._codebook())
+                    variability = out["z"] - zq2
+                    vq.track_assigment(idx2.reshape(-1, 1).detach(), 0)
+                else:
+                    vq.track_assigment(idx.reshape(-1, 1).detach(), 0)
         if per_slot:
             res = {
                 "action_dist": out["action_dist"],                            # (B, T-1, 2, S, A)

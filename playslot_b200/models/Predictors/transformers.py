@@ -42,9 +42,9 @@ class _SlotTokenPredictor(nn.Module):
     def _tokens(self, inputs):
         """ (B, F, S, D) -> (B, F, S, E) tokens with the per-frame sinusoidal encoding added in the GEMM epilogue """
         B, Fr, S, _ = inputs.shape
-        if self.training and self.pe.dropout.p > 0:
-            raise NotImplementedError("positional-encoding dropout > 0 in train mode is not implemented")
         t = ops.linear(inputs, self.mlp_in.weight, self.mlp_in.bias, res=f32c(self.pe.table()), res_div=S, res_mod=Fr)
+        if self.training and self.pe.dropout.p > 0:
+            t = self.pe.dropout(t)          # train-mode dropout after the positional encoding (model_blocks.py:211)
         return t
 
     def _slots(self, tokens, inputs):

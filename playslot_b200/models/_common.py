@@ -17,7 +17,7 @@ class DerivedWeights:
     """
     Cache of tensors derived from parameters (packed / transposed / concatenated weights, weight-only
     position-embedding maps).  Rebuilt whenever any source tensor changes storage, device or version
-    (optimizer steps and load_state_dict bump `_version`).
+    (optimizer steps and load_state_dict bump `_version`; graph-replayed optimiser steps bump ops.weight_generation()).
     """
 
     def __init__(self):
@@ -25,7 +25,8 @@ class DerivedWeights:
         self._val = None
 
     def get(self, sources, builder):
-        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in sources)
+        from .. import ops
+        key = (ops.weight_generation(),) + tuple((t.data_ptr(), t._version, str(t.device)) for t in sources)
         if key != self._key:
             with torch.no_grad():
                 self._val = builder()

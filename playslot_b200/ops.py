@@ -32,6 +32,21 @@ def linear_mode():
     return _LINEAR_MODE
 
 
+# Weight generation: derived-weight caches (packed tensor-core copies, concatenated matrices) are keyed on the parameters'
+# (data_ptr, _version) AND on this counter.  A CUDA-graph replay of a training step updates parameters on the device without
+# touching the Python-side `_version`, so train.GraphedTrainStep bumps the counter after every replay.
+_WEIGHT_GEN = 0
+
+
+def weight_generation():
+    return _WEIGHT_GEN
+
+
+def bump_weight_generation():
+    global _WEIGHT_GEN
+    _WEIGHT_GEN += 1
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -207,7 +222,7 @@ def _packed_linear_weight(weight, precision, transposed=False, reuse_scale=False
     """ packed copy (of weight, or of weight.t() for the data-gradient GEMM) cached on the weight tensor object, rebuilt when
     the tensor is modified in place or moved; the power-of-two scale of the first packing is kept for the rebuilds """
     attr = "_ps_tc_pack_t" if transposed else "_ps_tc_pack"
-    key = (weight._version, weight.data_ptr(), precision)
+    key = (weight._version, weight.data_ptr(), precision, _WEIGHT_GEN)
     c = getattr(weight, attr, None)
     if c is None or c[0] != key:
         with torch.no_grad():

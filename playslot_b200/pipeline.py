@@ -45,6 +45,27 @@ def seed_rollout_host(savi, predictor, videos_host, num_seed, num_preds, out_hos
     return out_host, res
 
 
+class PinnedRing:
+    """ two pinned host staging buffers for a small per-step upload (the InvDyn noise): the host may run several steps
+    ahead of the device, so a buffer is rewritten only after the asynchronous copy that last read it has completed """
+
+    def __init__(self, shape, dtype=torch.float32, depth=2):
+        self.bufs = [torch.empty(shape, dtype=dtype, pin_memory=True) for _ in range(depth)]
+        self.done = [None] * depth
+        self.n = 0
+
+    def upload(self, host_tensor, device_dst):
+        i = self.n % len(self.bufs)
+        self.n += 1
+        if self.done[i] is not None:
+            self.done[i].synchronize()
+        self.bufs[i].copy_(host_tensor)
+        device_dst.copy_(self.bufs[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.done[i] = ev
+
+
 class GraphedSeedRollout:
     """
     `seed_rollout` for a fixed batch shape, captured once in a CUDA graph and replayed: the ~800 kernel launches of
@@ -69,7 +90,7 @@ class GraphedSeedRollout:
         self.noise_shape = (batch, T - 1, S, A) if per_slot else (batch, T - 1, A)
         self.video = torch.zeros(batch, T, 3, H, W, device=device)
         self.noise = torch.zeros(self.noise_shape, device=device)
-        self._noise_pinned = torch.empty(self.noise_shape, pin_memory=True)
+        self._noise_ring = PinnedRing(self.noise_shape)
         la._static_noise = self.noise
         try:
             side = torch.cuda.Stream()
@@ -97,8 +118,7 @@ class GraphedSeedRollout:
     def __call__(self, videos, noise=None):
         """ videos: (B, T, 3, H, W) on the host (pinned) or on the device; returns the static output dict """
         self.video.copy_(videos, non_blocking=True)
-        self._noise_pinned.copy_(self.draw_noise() if noise is None else noise)
-        self.noise.copy_(self._noise_pinned, non_blocking=True)
+        self._noise_ring.upload(self.draw_noise() if noise is None else noise, self.noise)
         self.graph.replay()
         return self.out
 

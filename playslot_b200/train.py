@@ -41,45 +41,74 @@ def forward_loss(savi, predictor, videos, num_seed, num_preds, **init_kwargs):
 
 
 class GradientBucket:
-    """ one flat fp32 buffer for all trainable gradients: a single NCCL all-reduce per step """
+    """
+    One flat fp32 buffer holding ALL trainable gradients: the parameters' `.grad` tensors are views into it (autograd
+    accumulates straight into the bucket), so a step issues a single NCCL all-reduce with no copy in or out.  The last
+    element carries the rank's sample count: ranks whose shards differ in size (B % world != 0, shard.shard_range) weight
+    their mean-loss gradients by it, which makes the result the gradient of the GLOBAL-batch mean loss
+    (basePredictorTrainer.py:320-333 on the concatenated batch).
+    """
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat = torch.zeros(n + 1, device=dev, dtype=torch.float32)
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self.grads = self.flat[:n]
+        self.count = self.flat[n:]
 
-    def all_reduce_mean(self):
-        """ grads -> bucket -> all-reduce(SUM) / world -> grads; no-op bookkeeping when not distributed """
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return 0
+    def attach(self):
+        """ make every parameter's .grad the bucket view (zeroed); call instead of optimizer.zero_grad(set_to_none=True) """
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def _gather_detached(self):
+        """ gradients that autograd rebound (set_to_none users): copy them in; the fast path never takes this branch """
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
+                p.grad = v
+
+    def all_reduce_mean(self, local_count=None, async_op=False):
+        """ in-place all-reduce of the bucket to the global-batch mean gradient; returns the bytes reduced (0 when not
+        distributed) or, with async_op, the work handle (call .wait(), then `finish()`) """
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return 0
+        self._gather_detached()
+        if local_count is None:
+            self.count.fill_(1.0)
+        else:
+            self.count.fill_(float(local_count))
+            self.grads.mul_(float(local_count))
+        if async_op:
+            return dist.all_reduce(self.flat, async_op=True)
         dist.all_reduce(self.flat)
-        self.flat.div_(dist.get_world_size())
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+        self.finish()
         return self.flat.numel() * 4
+
+    def finish(self):
+        self.grads.div_(self.count)                 # device-side division by the global count: no host synchronisation
 
 
 def train_step(savi, predictor, optimizer, videos, num_seed, num_preds, bucket=None, clip_gradient=0.05, **init_kwargs):
     """ one optimisation step on this rank's shard of the batch; returns (loss value tensor, terms) """
     predictor.train()
-    optimizer.zero_grad(set_to_none=True)
+    if bucket is not None:
+        bucket.attach()
+    else:
+        optimizer.zero_grad(set_to_none=True)
     loss, terms, _ = forward_loss(savi, predictor, videos, num_seed, num_preds, **init_kwargs)
     loss.backward()
     if bucket is not None:
-        bucket.all_reduce_mean()
+        bucket.all_reduce_mean(local_count=videos.shape[0])
     if clip_gradient is not None:
         torch.nn.utils.clip_grad_norm_(predictor.parameters(), clip_gradient)
     optimizer.step()
@@ -159,7 +188,8 @@ class GraphedTrainStep:
         dev = next(predictor.parameters()).device
         self.video = torch.zeros(batch, T, 3, H, W, device=dev)
         self.noise = torch.zeros(self.noise_shape, device=dev)
-        self._noise_pinned = torch.empty(self.noise_shape, pin_memory=True)
+        from .pipeline import PinnedRing
+        self._noise_ring = PinnedRing(self.noise_shape)
         self._la = la
         predictor.train()
 
@@ -209,7 +239,11 @@ class GraphedTrainStep:
     def __call__(self, videos, noise=None):
         """ one optimisation step on `videos` (B, T, 3, H, W); returns (loss tensor, terms) -- static tensors of the graph """
         self.video.copy_(videos, non_blocking=True)
-        self._noise_pinned.copy_(self.draw_noise() if noise is None else noise)
-        self.noise.copy_(self._noise_pinned, non_blocking=True)
+        self._noise_ring.upload(self.draw_noise() if noise is None else noise, self.noise)
         self.graph.replay()
+        # the replay advanced the parameters on the device without bumping their Python-side `_version`: invalidate every
+        # derived-weight cache (packed tensor-core copies, concatenated q/k/v / embedding / head matrices) so that an eager
+        # forward after this step sees the new weights
+        from . import ops
+        ops.bump_weight_generation()
         return self.loss, self.terms

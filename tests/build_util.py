@@ -49,3 +49,30 @@ class FixedRandn:
     def __exit__(self, *exc):
         torch.randn = self._orig
         return False
+
+
+class ReplayDraws:
+    """ context manager replaying recorded torch.randint / torch.rand results in call order (prior-sample fixtures made by
+    oracle/make_golden.py::_RecordDraws): the CUDA path consumes exactly the random numbers the reference drew """
+
+    def __init__(self, randint_draws, rand_draws):
+        self.ri, self.r = list(randint_draws), list(rand_draws)
+
+    def __enter__(self):
+        self._ri, self._r = torch.randint, torch.rand
+
+        def pop(queue, what, a, k):
+            assert queue, f"the CUDA path drew more torch.{what} tensors than the reference"
+            t = queue.pop(0)
+            size = k.get("size", None)
+            if size is not None:
+                assert tuple(t.shape) == tuple(size), f"torch.{what}: shape {tuple(size)} vs recorded {tuple(t.shape)}"
+            dev = k.get("device", None)
+            return t.clone().to(dev) if dev is not None else t.clone()
+        torch.randint = lambda *a, **k: pop(self.ri, "randint", a, k)
+        torch.rand = lambda *a, **k: pop(self.r, "rand", a, k)
+        return self
+
+    def __exit__(self, *exc):
+        torch.randint, torch.rand = self._ri, self._r
+        return False

@@ -6,7 +6,8 @@ import torch
 from synth import synth_state_dict, synth_video, synth_noise
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-PIPELINE_CASES = ["blockpush", "blockpush_sharp", "buttonpress", "gridshapes5", "sketchy_sharp"]
+PIPELINE_CASES = ["blockpush", "blockpush_sharp", "buttonpress", "gridshapes5", "sketchy_sharp",
+                  "gridshapes5_bench", "blockpush_bench"]          # *_bench: the benchmark length, 6 seed + 15 predicted frames
 
 
 def load_case(name):

@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from golden_util import GOLDEN_DIR, PIPELINE_CASES, load_case
-from build_util import make_savi, make_predictor, to_dev, FixedRandn
+from build_util import make_savi, make_predictor, to_dev, FixedRandn, ReplayDraws
 from synth import synth_state_dict, rel_l2, max_rel
 from oracle import playslot_oracle as O
 
@@ -481,6 +481,97 @@ def test_prior_samples_batched_equals_sequential(case):
     assert a.shape == b.shape and a.shape[1] == 4
     assert torch.equal(ia, ib), "prior action indices differ"
     check("batched prior roll-outs", b, a, 2e-6)
+
+
+@pytest.mark.parametrize("exp", ["BlockPush", "GridShapes5Objs"])
+@pytest.mark.parametrize("batched", [True, False])
+def test_prior_samples_match_reference_golden(exp, batched):
+    """ prior sampling pinned against the REAL reference (LatentActionPredictors.py:148-157,383-396,511-532): the fixture holds
+    the torch.randint / torch.rand tensors the reference drew; replaying them, the CUDA path must reproduce its random action
+    indices exactly and its rolled-out slots to 1e-4 -- for the pure-prior call and for posterior + prior samples """
+    fx = torch.load(os.path.join(GOLDEN_DIR, "prior_samples.pt"), weights_only=False)[exp]
+    psd = synth_state_dict(fx["manifest"], fx["weight_seed"])
+    pred = make_predictor(fx["predictor_name"], fx["cfg"], psd, DEV)
+    pred.batch_prior_samples = batched
+    B, ns, npred, nsamp, S = fx["B"], fx["num_seed"], fx["num_preds"], fx["num_samples"], fx["num_slots"]
+    gen = torch.Generator().manual_seed(fx["input_seed"])
+    sh = torch.randn(B, ns + npred, S, 128, generator=gen)
+    assert abs(float(sh.double().sum()) - fx["sh_checksum"]) < 1e-6 * max(1.0, abs(fx["sh_checksum"]))
+    A = fx["cfg"]["action_dim"]
+    per_slot = fx["cfg"]["LatentAction"]["model_name"] == "VQSimpleMLPSlotLatentAction"
+    from synth import synth_noise
+    noise = synth_noise((B, ns + npred - 1, S, A) if per_slot else (B, ns + npred - 1, A), fx["weight_seed"])
+    n_ri, n_r = fx["draws_prior_only"]
+    with torch.no_grad():
+        with ReplayDraws(fx["randint_draws"][:n_ri], fx["rand_draws"][:n_r]) as rd:
+            prior, idx = pred.forward_multiple_samples(sh.to(DEV), nsamp, ns, npred, use_posterior=False)
+            assert not rd.ri and not rd.r, "the CUDA path drew fewer random tensors than the reference"
+        assert torch.equal(idx.cpu(), fx["prior_action_idx"]), "prior action indices differ"
+        check("prior pred_slots", prior, fx["prior_pred_slots"])
+        with ReplayDraws(fx["randint_draws"][n_ri:], fx["rand_draws"][n_r:]) as rd, FixedRandn(noise):
+            mixed, idx2 = pred.forward_multiple_samples(sh.to(DEV), nsamp, ns, npred, use_posterior=True)
+            assert not rd.ri and not rd.r
+        assert torch.equal(idx2.cpu(), fx["mixed_action_idx"])
+        check("posterior + prior pred_slots", mixed, fx["mixed_pred_slots"])
+
+
+def test_decoder_forward_and_attention_api():
+    """ stand-alone reference APIs that the fused path bypasses: Decoder.forward (decoders.py:103-111) and
+    MetaAttention.attention (attention.py:211-240), against plain torch on the same tensors """
+    fx, ssd, psd, video, noise, init_noise = load_case("buttonpress")
+    savi = make_savi(fx["savi_cfg"], ssd, DEV)
+    x = g(2, 128, 64, 64, seed=3)
+    with torch.no_grad():
+        y = savi.decoder(x.to(DEV))
+        h = x
+        for i in (0, 2, 4, 6):
+            h = F.relu(F.conv2d(h, ssd[f"decoder.decoder.{i}.block.0.weight"], ssd[f"decoder.decoder.{i}.block.0.bias"], padding=2))
+        r = F.conv2d(h, ssd["decoder.decoder.7.weight"], ssd["decoder.decoder.7.bias"], padding=1)
+    check("Decoder.forward", y, r)
+    from playslot_b200.models.BlocksUtils.attention import MultiHeadSelfAttention
+    att = MultiHeadSelfAttention(emb_dim=128, head_dim=32, num_heads=4).to(DEV)
+    q, k, v = g(8, 12, 32, seed=4), g(8, 12, 32, seed=5), g(8, 12, 32, seed=6)
+    with torch.no_grad():
+        o = att.attention(q.to(DEV), k.to(DEV), v.to(DEV))
+    ref = torch.softmax(torch.einsum("bid,bjd->bij", q, k) * 32 ** -0.5, dim=-1) @ v
+    check("MetaAttention.attention", o, ref)
+
+
+def test_bench_object_matches_oracle():
+    """ the exact object bench.py times -- GraphedSeedRollout, GridShapes5Objs, 64 videos, 6 + 15 frames, random-init weights --
+    against the CPU oracle on 2 of its 64 videos (the chained path: our slots -> our predictor -> our decoder) """
+    from playslot_b200 import configs
+    from playslot_b200.pipeline import GraphedSeedRollout
+    cfg = configs.experiment("GridShapes5Objs")
+    torch.manual_seed(0)
+    savi, pred = configs.build_models(cfg, DEV)
+    B, ns, npred = 64, 6, 15
+    gen = torch.Generator().manual_seed(99)
+    video = torch.rand(B, ns + npred, 3, 64, 64, generator=gen)
+    per_slot_shape = (B, ns + npred - 1, 6, cfg["predictor"]["predictor_params"]["action_dim"])
+    noise = torch.randn(per_slot_shape, generator=gen)
+    init_noise = torch.randn(B, 6, 128, generator=gen)
+    # the LearnedRandom initialiser draws torch.randn on the device INSIDE the captured graph: capture with a fixed device-side
+    # draw (a device-to-device clone is capturable) so that the oracle can be given the same initial slots
+    init_dev = init_noise.to(DEV)
+    real_randn = torch.randn
+    torch.randn = lambda *a, **k: init_dev.clone() if k.get("device", None) is not None else real_randn(*a, **k)
+    try:
+        gr = GraphedSeedRollout(savi, pred, B, ns, npred)
+    finally:
+        torch.randn = real_randn
+    assert tuple(gr.noise_shape) == per_slot_shape
+    out = gr(video.to(DEV), noise=noise)
+    pick = [0, 63]
+    ssd = {k: v.detach().cpu() for k, v in savi.state_dict().items()}
+    psd = {k: v.detach().cpu() for k, v in pred.state_dict().items()}
+    with torch.no_grad():
+        ref = O.seed_rollout_pipeline(ssd, cfg["model"]["model_params"], psd, cfg["predictor"]["predictor_params"],
+                                      video[pick], ns, npred, noise[pick], init_noise[pick])
+    check("slot_history", out["slot_history"][pick], ref["slot_history"])
+    check("pred_slots (15 chained steps)", out["pred_slots"][pick, 0], ref["pred_slots"])
+    check("pred_imgs", out["pred_imgs"][pick, 0].reshape(ref["recon"].shape), ref["recon"])
+    check("pred_masks", out["pred_masks"][pick, 0].reshape(ref["masks"].shape), ref["masks"])
 
 
 def test_aux_predictors_match_reference_golden():

@@ -308,3 +308,50 @@ def test_graphed_train_step_equals_eager():
             assert float((pa.detach() - pb.detach()).abs().max()) <= 2e-5 * max(1.0, float(pa.detach().abs().max())), name
     for (name, ba), bb in zip(pred_a.named_buffers(), pred_b.buffers()):
         assert float((ba.float() - bb.float()).abs().max()) <= 2e-5 * max(1.0, float(ba.float().abs().max())), name
+
+
+def test_eager_forward_after_graphed_steps_sees_new_weights():
+    """ GraphedTrainStep replays update the parameters on the device without bumping their Python-side `_version`; every
+    derived-weight cache (packed tensor-core copies, concatenated q/k/v / embedding / head matrices) must still be rebuilt:
+    an eager no_grad forward after the replays equals the forward of a freshly deep-copied model """
+    import copy
+    from playslot_b200 import configs, train
+    cfg = configs.experiment("ButtonPress")
+    torch.manual_seed(0)
+    savi, pred = configs.build_models(cfg, DEV)
+    for p in savi.parameters():
+        p.requires_grad_(False)
+    B, ns, npred = 2, 3, 3
+    gen = torch.Generator().manual_seed(12)
+    sh = torch.randn(B, ns + npred, 4, 128, generator=gen).to(DEV)
+    noise = torch.randn(B, ns + npred - 1, cfg["predictor"]["predictor_params"]["action_dim"], generator=gen)
+    pred.eval()
+    with torch.no_grad(), FixedRandnLocal(noise):
+        before, _ = pred.forward_multiple_samples(sh, 1, ns, npred, use_posterior=True)      # fills every cache
+    opt = train.make_optimizer(pred, lr=1e-2, capturable=True)
+    graphed = train.GraphedTrainStep(savi, pred, opt, B, ns, npred, clip_gradient=None)
+    for _ in range(3):
+        graphed(torch.rand(B, ns + npred, 3, 64, 64, generator=gen).to(DEV))
+    torch.cuda.synchronize()
+    pred.eval()
+    fresh = copy.deepcopy(pred)                                   # new tensor objects: no cache can survive the copy
+    with torch.no_grad(), FixedRandnLocal(noise):
+        after, _ = pred.forward_multiple_samples(sh, 1, ns, npred, use_posterior=True)
+    with torch.no_grad(), FixedRandnLocal(noise):
+        want, _ = fresh.forward_multiple_samples(sh, 1, ns, npred, use_posterior=True)
+    assert float((after - before).abs().max()) > 1e-4, "three optimiser steps at lr 1e-2 must change the prediction"
+    assert torch.equal(after, want), "eager inference after graph replays ran on stale derived weights"
+
+
+class FixedRandnLocal:
+    def __init__(self, value):
+        self.value = value
+
+    def __enter__(self):
+        self._orig = torch.randn
+        torch.randn = lambda *a, **k: self.value.clone().to(k["device"]) if k.get("device") is not None else self.value.clone()
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn = self._orig
+        return False

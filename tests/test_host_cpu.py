@@ -4,6 +4,7 @@ manifests recorded from the real reference, loud failure without CUDA, host-side
 """
 import copy
 import ctypes
+import json
 import os
 import re
 
@@ -186,3 +187,55 @@ def test_aux_predictor_manifests_match_reference():
     fx = aux["action_cond"]
     m = ActionCondtionalOCVP(**copy.deepcopy(fx["cfg"]))
     assert list({k: list(v.shape) for k, v in m.state_dict().items()}.items()) == list(fx["manifest"].items())
+
+
+def _reference_root():
+    """ a tree holding the reference's src/lib/setup_model.py: the mounted reference or the copy made by oracle/install_ref.py """
+    for root in ("/root/reference", os.path.join(ROOT, "oracle", "_ref")):
+        if os.path.isfile(os.path.join(root, "src", "lib", "setup_model.py")):
+            return root
+    return None
+
+
+@pytest.mark.skipif(_reference_root() is None, reason="neither /root/reference nor oracle/_ref is present")
+@pytest.mark.parametrize("exp", ["BlockPush", "ButtonPress", "GridShapes5Objs", "Sketchy"])
+def test_reference_factory_builds_and_loads_the_mirror(exp, tmp_path):
+    """ the drop-in boundary, driven by the REFERENCE's own code: lib/setup_model.py's setup_model / setup_predictor
+    (:29-116) instantiate the mirror through launch.install(), save_checkpoint-style files round-trip through its
+    load_checkpoint (:245-298, strict load_state_dict + the pos_emb.pe re-injection), and the state_dict layout equals the one
+    the real reference modules have (manifests recorded in the golden fixtures) """
+    import subprocess
+    import sys
+    root = _reference_root()
+    code = f"""
+import copy, json, os, sys, torch
+sys.path.insert(0, {ROOT!r})
+os.chdir({root!r})
+sys.path.insert(0, os.path.join({root!r}, "src"))
+from playslot_b200 import launch
+launch.install(reference_src=os.path.join({root!r}, "src"))
+from lib.setup_model import setup_model, setup_predictor, load_checkpoint
+j = json.load(open(os.path.join({root!r}, "experiments", {exp!r}, "predictors", "PlaySlot", "experiment_params.json")))
+savi = setup_model(copy.deepcopy(j["model"]))
+pred = setup_predictor(copy.deepcopy(j))
+assert type(savi).__module__ == "playslot_b200.models.SAVi", type(savi).__module__
+assert type(pred).__module__.startswith("playslot_b200.models.Predictors"), type(pred).__module__
+for name, m in (("savi", savi), ("pred", pred)):
+    path = os.path.join({str(tmp_path)!r}, name + ".pth")
+    sd = {{k: torch.randn_like(v) if v.is_floating_point() else v.clone() for k, v in m.state_dict().items()}}
+    torch.save({{"model_state_dict": {{"module." + k: v for k, v in sd.items()}}}}, path)     # DataParallel-style prefix
+    load_checkpoint(path, model=m, only_model=True)
+    for k, v in m.state_dict().items():
+        if not k.endswith("pos_emb.pe"):
+            assert torch.equal(v, sd[k]), k
+print("MANIFEST " + json.dumps({{"savi": {{k: list(v.shape) for k, v in savi.state_dict().items()}},
+                                  "pred": {{k: list(v.shape) for k, v in pred.state_dict().items()}}}}))
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("MANIFEST ")][-1]
+    got = json.loads(line[len("MANIFEST "):])
+    case = {"BlockPush": "blockpush", "ButtonPress": "buttonpress", "GridShapes5Objs": "gridshapes5", "Sketchy": "sketchy_sharp"}[exp]
+    fx = torch.load(os.path.join(GOLDEN_DIR, f"{case}.pt"), weights_only=False)
+    assert list(got["savi"].items()) == [(k, list(v)) for k, v in fx["savi_manifest"].items()]
+    assert list(got["pred"].items()) == [(k, list(v)) for k, v in fx["predictor_manifest"].items()]

@@ -79,11 +79,13 @@ def _train_worker(rank, world_size, port, q):
         frozen = torch.nn.Linear(3, 3).requires_grad_(False)
         bucket = train.GradientBucket(list(lin.parameters()) + list(frozen.parameters()))
         g = torch.Generator().manual_seed(100)
-        x_all = torch.randn(6 * world_size, 5, generator=g)
+        x_all = torch.randn(6 * world_size + 1, 5, generator=g)      # shards of UNEQUAL size
         a, b = shard.shard_range(x_all.shape[0], rank, world_size)
-        lin(x_all[a:b]).pow(2).mean().backward()          # per-rank mean loss on the shard (DDP convention)
+        bucket.attach()                                   # .grad tensors are views of the flat bucket: no copy in / out
+        lin(x_all[a:b]).pow(2).mean().backward()          # per-rank mean loss on the shard
+        assert lin[0].weight.grad.data_ptr() == bucket.views[0].data_ptr()
         lin[1].bias.grad = None                           # a parameter without gradient on this rank must still take part
-        nbytes = bucket.all_reduce_mean()
+        nbytes = bucket.all_reduce_mean(local_count=b - a)
         grads = [None if p.grad is None else p.grad.clone() for p in lin.parameters()]
         # EMA codebook statistics on the global batch
         torch.manual_seed(1)
@@ -111,19 +113,14 @@ def test_training_collectives_equal_single_process(world_size):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    # single-process reference: mean over ranks of the per-shard gradients
+    # single-process reference: the gradient of the mean loss over the GLOBAL (concatenated) batch
     torch.manual_seed(0)
     lin = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
     g = torch.Generator().manual_seed(100)
-    x_all = torch.randn(6 * world_size, 5, generator=g)
-    acc = [torch.zeros_like(p) for p in lin.parameters()]
-    for r in range(world_size):
-        a, b = shard.shard_range(x_all.shape[0], r, world_size)
-        lin.zero_grad()
-        lin(x_all[a:b]).pow(2).mean().backward()
-        for i, p in enumerate(lin.parameters()):
-            if i != 3:                                     # lin[1].bias was dropped on every rank
-                acc[i] += p.grad / world_size
+    x_all = torch.randn(6 * world_size + 1, 5, generator=g)
+    lin(x_all).pow(2).mean().backward()
+    acc = [p.grad.clone() for p in lin.parameters()]
+    acc[3].zero_()                                         # lin[1].bias was dropped on every rank
     torch.manual_seed(1)
     vq = EmaVectorQuantizer(num_embs=4, emb_dim=3)
     vq.sync_stats = False
@@ -132,7 +129,7 @@ def test_training_collectives_equal_single_process(world_size):
     vq.ema_update(z_all, idx_all)
     n_float = sum(p.numel() for p in lin.parameters())
     for rank, nbytes, grads, cnt, wgt, emb in res:
-        assert nbytes == 4 * n_float                       # one flat bucket of every trainable parameter
+        assert nbytes == 4 * (n_float + 1)                 # one flat bucket: every trainable parameter + the sample count
         for got, ref in zip(grads, acc):
             assert got is not None
             assert torch.allclose(torch.tensor(got), ref, atol=1e-6)
