@@ -30,6 +30,10 @@ const char* ps_last_error(void);
 unsigned long long ps_launch_count(void);      /* kernels launched through this library by this process */
 void ps_reset_launch_count(void);
 int ps_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* SMs the persistent kernels (ps_conv5x5_tc, ps_dec_composite_tc) leave free for kernels of a concurrent stream: the decoder of
+ * predicted frame i (side stream) overlaps the cOCVP step of frame i+1 (src/05_evaluate_PlaySlot.py:112-139 runs them back to back) */
+int ps_set_sm_reserve(int n_sms);
+int ps_get_sm_reserve(void);
 
 /* ---- dense building blocks ---------------------------------------------------------------------------- */
 

@@ -16,6 +16,8 @@ SIGNATURES = {
     "ps_launch_count": (ctypes.c_ulonglong, []),
     "ps_reset_launch_count": (None, []),
     "ps_device_info": (c_i, [ctypes.POINTER(c_i)] * 3),
+    "ps_set_sm_reserve": (c_i, [c_i]),
+    "ps_get_sm_reserve": (c_i, []),
     "ps_linear": (c_i, [c_f, c_i, c_f, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_linear_tc": (c_i, [c_f, c_i, c_f, c_fl, c_i, c_i, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_linear_tc_planes": (c_i, [c_f, c_i, c_f, ctypes.c_longlong, c_f, c_fl, c_i, c_i, c_f, c_f, c_f, c_fl, c_f, c_i, c_i, c_i, c_f, c_f,

@@ -42,6 +42,9 @@ void ps_set_error(const char* fmt, ...);
 // every launch made through the C-ABI bumps this counter (bench.py reports it as gpu_launches)
 extern unsigned long long g_ps_launch_count;
 #define PS_COUNT_LAUNCH() (++g_ps_launch_count)
+// SMs the persistent kernels leave free (ps_set_sm_reserve)
+extern int g_ps_sm_reserve;
+static inline int ps_persistent_ctas(int sms) { const int n = sms - g_ps_sm_reserve; return n < 1 ? 1 : n; }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE setting of a kernel: remember, per device, the largest size that
 // has been configured (a process may drive several GPUs).  `set_bytes` (default: smem) is the value passed to the driver.

@@ -440,7 +440,7 @@ static int conv5x5_tc_run(const void* act_in, const void* w_tc, const float* bia
     {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        p.n_ctas = sms;
+        p.n_ctas = ps_persistent_ctas(sms);
     }
     const uint16_t* in_hi = reinterpret_cast<const uint16_t*>(act_in);
     CUtensorMap mA_hi, mA_lo, mA_hi8, mA_lo8, mW;
@@ -791,7 +791,7 @@ extern "C" int ps_dec_composite_tc(const void* act_in, const void* w_tc, float w
     {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        p.n_ctas = sms;
+        p.n_ctas = ps_persistent_ctas(sms);
     }
     const uint16_t* in_hi = reinterpret_cast<const uint16_t*>(act_in);
     CUtensorMap mA_hi, mA_lo, mW;

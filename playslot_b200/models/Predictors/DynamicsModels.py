@@ -200,6 +200,9 @@ class SlotGPTDymamicsModel(BaseSlotDynamicsModel):
             cur, a, v = self.enforce_window(slots=cur, action_protos=a, action_vars=v)
             nxt = self.forward_single(slots=cur, action_protos=a, action_vars=v)[:, -1:]
             preds.append(nxt)
+            hook = getattr(self, "step_hook", None)
+            if hook is not None:
+                hook(i, nxt)          # pipeline.seed_rollout: decode this frame on a side stream while the next step runs
             if not get_pred_only and i < num_seed - 1:
                 cur = slots[:, :upto + 1]
             else:

@@ -119,6 +119,23 @@ def reset_launch_count():
     _lib.load().ps_reset_launch_count()
 
 
+class sm_reserve:
+    """ context manager: the persistent kernels launched inside leave `n` SMs free for the kernels of a concurrent stream """
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __enter__(self):
+        lib = _lib.load()
+        self.old = int(lib.ps_get_sm_reserve())
+        _lib.check(lib.ps_set_sm_reserve(self.n), "ps_set_sm_reserve")
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().ps_set_sm_reserve(self.old)
+        return False
+
+
 # ------------------------------------------------------------------------------------------------ dense
 
 class Planes:

@@ -4,29 +4,96 @@ The seed + rollout path a user of the reference runs (src/05_evaluate_PlaySlot.p
     ns, np, use_posterior=True) -> savi.decode(pred_slots)
 exposed as one call, plus a host-buffer variant used for end-to-end timing.
 """
+import os
+
 import torch
+
+from . import ops
+
+
+# Measured on B200 (tools/bench_overlap.py, tools/probe_overlap.py; profiles/r02_overlap_probe.md): NO gain -- the roll-out kernels
+# (96-144 CTAs each) are not purely latency-bound; confined to the 8-32 SMs a persistent decoder kernel can spare they slow down
+# 3-9x and become the critical path (56.1 ms sequential vs 55.9-58.2 ms overlapped).  Kept as an option, off by default.
+OVERLAP_DECODE = os.environ.get("PLAYSLOT_OVERLAP_DECODE", "0") != "0"
+SM_RESERVE = int(os.environ.get("PLAYSLOT_SM_RESERVE", "16"))
 
 
 @torch.no_grad()
-def seed_rollout(savi, predictor, videos, num_seed, num_preds, num_samples=1, use_posterior=True, decode=True, **init_kwargs):
+def seed_rollout(savi, predictor, videos, num_seed, num_preds, num_samples=1, use_posterior=True, decode=True, overlap=None,
+                 **init_kwargs):
     """
     videos (B, >= num_seed+num_preds, 3, H, W) on the GPU ->
       dict(slot_history (B, ns+np, S, D), pred_slots (B, num_samples, np, S, D), pred_imgs (B, num_samples, np, 3, H, W),
            pred_objs, pred_masks)
+
+    overlap (default: off, see OVERLAP_DECODE; posterior roll-out with num_samples == 1 only): the roll-out is a chain of small kernels
+    and the decoder a throughput-bound stack of persistent convolutions, so predicted frame i is decoded on a side stream
+    while the cOCVP step of frame i+1 runs on the main stream; the persistent decoder kernels leave SM_RESERVE SMs free for
+    it (ops.sm_reserve).  Same kernels on the same data as the sequential order: results are bit-identical.
     """
     T = num_seed + num_preds
     out = savi(videos, num_imgs=T, decode=False, **init_kwargs)
     slot_history = out["slot_history"]
-    pred_slots, actions = predictor.forward_multiple_samples(
-        slot_history=slot_history, num_samples=num_samples, num_seed=num_seed, num_preds=num_preds, use_posterior=use_posterior)
+    dyn = getattr(predictor, "dynamics_model", None)
+    if overlap is None:
+        overlap = OVERLAP_DECODE
+    overlap = bool(overlap and decode and num_samples == 1 and use_posterior and dyn is not None and num_preds > 1)
+    if not overlap:
+        pred_slots, actions = predictor.forward_multiple_samples(
+            slot_history=slot_history, num_samples=num_samples, num_seed=num_seed, num_preds=num_preds, use_posterior=use_posterior)
+        res = {"slot_history": slot_history, "pred_slots": pred_slots, "actions": actions}
+        if decode:
+            B, n, P, S, D = pred_slots.shape
+            imgs, (objs, masks) = savi.decode(pred_slots.reshape(B * n * P, S, D))
+            res["pred_imgs"] = imgs.view(B, n, P, *imgs.shape[1:])
+            res["pred_objs"] = objs.view(B, n, P, *objs.shape[1:])
+            res["pred_masks"] = masks.view(B, n, P, *masks.shape[1:])
+        return res
+
+    main = torch.cuda.current_stream()
+    side = _side_stream(videos.device)
+    capturing = torch.cuda.is_current_stream_capturing()
+    B, S, D = slot_history.shape[0], slot_history.shape[2], slot_history.shape[3]
+    frames = []                                                  # per predicted frame: (recon, recons, masks), made on `side`
+    side.wait_stream(main)
+
+    def decode_step(i, nxt):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        last = i == num_preds - 1
+        with torch.cuda.stream(side), ops.sm_reserve(0 if last else SM_RESERVE):
+            recon, (recons, masks) = savi.decode(nxt.reshape(B, S, D))
+        if not capturing:
+            for t in (nxt,):
+                t.record_stream(side)
+        frames.append((recon, recons, masks))
+
+    dyn.step_hook = decode_step
+    try:
+        pred_slots, actions = predictor.forward_multiple_samples(
+            slot_history=slot_history, num_samples=1, num_seed=num_seed, num_preds=num_preds, use_posterior=True)
+    finally:
+        dyn.step_hook = None
+    main.wait_stream(side)
     res = {"slot_history": slot_history, "pred_slots": pred_slots, "actions": actions}
-    if decode:
-        B, n, P, S, D = pred_slots.shape
-        imgs, (objs, masks) = savi.decode(pred_slots.reshape(B * n * P, S, D))
-        res["pred_imgs"] = imgs.view(B, n, P, *imgs.shape[1:])
-        res["pred_objs"] = objs.view(B, n, P, *objs.shape[1:])
-        res["pred_masks"] = masks.view(B, n, P, *masks.shape[1:])
+    for key, j in (("pred_imgs", 0), ("pred_objs", 1), ("pred_masks", 2)):
+        parts = [f[j] for f in frames]
+        if not capturing:
+            for t in parts:
+                t.record_stream(main)
+        res[key] = torch.stack(parts, dim=1).unsqueeze(1)        # (B, 1, P, ...)
     return res
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=key)
+    return _SIDE[key]
 
 
 @torch.no_grad()

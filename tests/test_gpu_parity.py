@@ -426,10 +426,19 @@ def test_pipeline_matches_reference_golden(case, conv_mode, linear_mode_guard):
         check("recon", recon, fx["recon"])
         check("masks", masks, fx["masks"])
         check("recons_m0", recons[0], fx["recons_m0"])
-        # end-to-end chained run (our slots -> our predictor -> our decoder): looser, errors compound over 11 frames
+        # end-to-end chained run (our slots -> our InvDyn -> our roll-out -> our decoder), same 1e-4 bar: measured
+        # (profiles/r02_chained_error.json) pred_slots <= 6.2e-6, decoded frames <= 9.3e-6, masks <= 7.0e-5 over all cases,
+        # including the 6 + 15-frame benchmark length
+        with FixedRandn(noise):
+            act2 = pred.latent_action.compute_actions(sh)
+        assert torch.equal(act2["action_idxs"].cpu().reshape(-1), fx["action_idxs"].reshape(-1)), "VQ indices differ (chained)"
         with FixedRandn(noise):
             ps2, _ = pred.forward_multiple_samples(sh, 1, ns, npred, use_posterior=True)
-        check("pred_slots (chained)", ps2[:, 0], fx["pred_slots"], 5e-4)
+        check("pred_slots (chained)", ps2[:, 0], fx["pred_slots"])
+        recon2, (_, masks2) = savi.decode(ps2[:, 0, -k:].reshape(B * k, S, D))
+        check("recon (chained)", recon2, fx["recon"])
+        # (the two sharpened stress cases sit at 6e-5 / 7e-5: judged at the same 3e-4 as their SlotAttention masks above)
+        check("masks (chained)", masks2, fx["masks"], 3e-4 if case.endswith("_sharp") else TOL)
 
 
 def test_decode_true_shapes_and_empty_stacks():
@@ -625,7 +634,7 @@ def test_graphed_seed_rollout_equals_eager():
         out = g(v, noise=noise)
         for k in ("slot_history", "pred_slots", "pred_imgs", "pred_masks"):
             assert torch.equal(out[k], eager[k]), f"{k} differs between graph replay {rep} and eager launches"
-    check("pred_slots vs reference", out["pred_slots"][:, 0], fx["pred_slots"], 5e-4)
+    check("pred_slots vs reference", out["pred_slots"][:, 0], fx["pred_slots"])
     # a different video through the same graph
     v2 = torch.rand_like(v)
     with FixedRandn(noise):

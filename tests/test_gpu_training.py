@@ -109,7 +109,8 @@ def test_invdyn_tail_backward(per_slot, R):
     z = noise.double() * torch.sqrt(v + 1e-6) + m
     zq, idx, _ = O.vq_lookup(cbr, z)
     proto = z + (zq - z).detach()
-    variab = (z - proto) if per_slot else (z - zq.detach())
+    # InvDynS: get_variability re-runs forward_one (quantization.py:365-368), z_q = onehot @ E stays differentiable w.r.t. E
+    variab = (z - proto) if per_slot else (z - zq)
     quant = ((zq.detach() - z) ** 2).mean(-1)
     commit = ((zq - z.detach()) ** 2).mean(-1)
     dist = torch.stack([m, v], dim=2)
