@@ -24,9 +24,37 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-EXPERIMENT = "GridShapes5Objs"
-NUM_SEED, NUM_PREDS = 6, 15
 METRIC, UNIT = "seed_rollout_frames_per_sec", "frames/s"
+
+# --config: the workload.  "gridshapes5" is BASELINE.json configs[2], the configuration the headline metric is quoted on (and
+# the default); the shipped 32-channel-encoder experiments and configs[4] (Sketchy-shaped 128x128, 16 slots, 6 + 30 frames)
+# are reported with the same code path.
+WORKLOADS = {
+    "gridshapes5":   {"experiment": "GridShapes5Objs", "batch": 64, "ns": 6, "np": 15, "res": 64, "slots": None, "ref_batch": 4,
+                      "what": "BASELINE.json configs[2]"},
+    "blockpush":     {"experiment": "BlockPush", "batch": 64, "ns": 6, "np": 15, "res": 64, "slots": None, "ref_batch": 4,
+                      "what": "BlockPush experiment (BASELINE.json configs[0] shapes), 8 slots, 32-channel encoder"},
+    "buttonpress":   {"experiment": "ButtonPress", "batch": 64, "ns": 6, "np": 15, "res": 64, "slots": None, "ref_batch": 4,
+                      "what": "ButtonPress experiment, 4 slots, 32-channel encoder"},
+    "sketchy":       {"experiment": "Sketchy", "batch": 64, "ns": 6, "np": 15, "res": 64, "slots": None, "ref_batch": 4,
+                      "what": "Sketchy experiment, 8 slots, 32-channel encoder, context 10"},
+    "sketchy_hires": {"experiment": "Sketchy", "batch": 8, "ns": 6, "np": 30, "res": 128, "slots": 16, "ref_batch": 1,
+                      "what": "BASELINE.json configs[4]: Sketchy-shaped 128x128 video, 16 slots, 6 + 30 frames, context 10"},
+}
+WORKLOAD = "gridshapes5"
+EXPERIMENT, NUM_SEED, NUM_PREDS, RES, NUM_SLOTS = "GridShapes5Objs", 6, 15, 64, None
+
+
+def set_workload(name):
+    global WORKLOAD, EXPERIMENT, NUM_SEED, NUM_PREDS, RES, NUM_SLOTS
+    w = WORKLOADS[name]
+    WORKLOAD, EXPERIMENT, NUM_SEED, NUM_PREDS, RES, NUM_SLOTS = name, w["experiment"], w["ns"], w["np"], w["res"], w["slots"]
+    return w
+
+
+def experiment_cfg():
+    from playslot_b200 import configs
+    return configs.experiment(EXPERIMENT, num_slots=NUM_SLOTS, resolution=(RES, RES) if RES != 64 else None)
 
 
 def peaks():
@@ -99,6 +127,11 @@ def reference_models(experiment, device, seed=0):
     with contextlib.redirect_stdout(sys.stderr):                   # the reference's builders print their configuration
         setup_model, setup_predictor, experiment_json = load_reference()
         j = experiment_json(experiment)
+        if NUM_SLOTS is not None:
+            j["model"]["model_params"]["num_slots"] = NUM_SLOTS
+        if RES != 64:
+            j["model"]["model_params"]["encoder"]["encoder_params"]["resolution"] = [RES, RES]
+            j["model"]["model_params"]["decoder"]["decoder_params"]["resolution"] = [RES, RES]
         torch.manual_seed(seed)
         savi = setup_model(copy.deepcopy(j["model"])).eval().to(device)
         pred = setup_predictor(copy.deepcopy(j)).eval().to(device)
@@ -154,13 +187,12 @@ def cpu_reference_timer(cores):
 
         def step(B, seed):
             g = torch.Generator().manual_seed(seed)
-            video = torch.rand(B, NUM_SEED + NUM_PREDS, 3, 64, 64, generator=g)
+            video = torch.rand(B, NUM_SEED + NUM_PREDS, 3, RES, RES, generator=g)
             t0 = time.perf_counter()
             reference_pipeline(savi, pred, video, NUM_SEED, NUM_PREDS)
             return time.perf_counter() - t0
         return step, "reference", "the unmodified reference modules (oracle/_ref, lib/setup_model.py builders), torch CPU fp32"
-    from playslot_b200 import configs
-    cfg = configs.experiment(EXPERIMENT)
+    cfg = experiment_cfg()
     ssd, psd = oracle_models(cfg)
     return (lambda B, seed: oracle_step(cfg, ssd, psd, B, seed)), "port", "torch CPU fp32 oracle port (oracle/_ref absent)"
 
@@ -170,7 +202,7 @@ def torch_cuda_baseline(B, reps=10):
     .to('cuda'), eager, PyTorch's default flags (cuDNN TF32 convolutions on, fp32 matmuls), CUDA-event timed """
     savi, pred = reference_models(EXPERIMENT, "cuda")
     T = NUM_SEED + NUM_PREDS
-    video = torch.rand(B, T, 3, 64, 64, device="cuda")
+    video = torch.rand(B, T, 3, RES, RES, device="cuda")
     ts = []
     for i in range(2 + reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -219,8 +251,10 @@ def run_reference(args):
 
 
 def workload_config(batch_per_gpu, n_gpus):
+    slots = NUM_SLOTS or experiment_cfg()["model"]["model_params"]["num_slots"]
     return {"workload": f"{EXPERIMENT} seed+rollout: {batch_per_gpu} videos/GPU x {n_gpus} GPU, {NUM_SEED} seed + {NUM_PREDS} pred frames, "
-                        "64x64 RGB, 6 slots, encode(decode=False) -> InvDyn posterior + cOCVP rollout -> decode",
+                        f"{RES}x{RES} RGB, {slots} slots, encode(decode=False) -> InvDyn posterior + cOCVP rollout -> decode",
+            "name": WORKLOAD, "what": WORKLOADS[WORKLOAD]["what"],
             "batch_per_gpu": batch_per_gpu, "num_seed": NUM_SEED, "num_preds": NUM_PREDS,
             "l2_policy": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no flush needed",
             "parallelism": f"videos sharded over {n_gpus} GPU(s), no data-path collective"}
@@ -321,7 +355,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pk = peaks()
-    cfg = configs.experiment(EXPERIMENT)
+    cfg = experiment_cfg()
     torch.manual_seed(0)                                           # same random-init weights on every rank
     savi, pred = configs.build_models(cfg, "cuda")
     savi.conv_mode = args.conv_mode
@@ -329,9 +363,9 @@ def run_ours(args):
     savi.slot_attention.mode = "fp32" if args.conv_mode == "fp32" else "tc"
     B, T = args.batch, NUM_SEED + NUM_PREDS
     g = torch.Generator().manual_seed(1234 + rank)                 # a different synthetic shard per rank
-    video_host = torch.rand(B, T, 3, 64, 64, generator=g).pin_memory()
+    video_host = torch.rand(B, T, 3, RES, RES, generator=g).pin_memory()
     video = video_host.cuda()
-    out_host = torch.empty(B, NUM_PREDS, 3, 64, 64, pin_memory=True)
+    out_host = torch.empty(B, NUM_PREDS, 3, RES, RES, pin_memory=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -343,7 +377,7 @@ def run_ours(args):
         return shard.max_over_ranks(ms, device="cuda")
 
     from playslot_b200.pipeline import GraphedSeedRollout
-    graphed = None if args.eager else GraphedSeedRollout(savi, pred, B, NUM_SEED, NUM_PREDS)
+    graphed = None if args.eager else GraphedSeedRollout(savi, pred, B, NUM_SEED, NUM_PREDS, resolution=(RES, RES))
     step = (lambda: graphed(video)) if graphed else (lambda: seed_rollout(savi, pred, video, NUM_SEED, NUM_PREDS))
     step_host = (lambda: graphed.run_host(video_host, out_host)) if graphed else \
         (lambda: seed_rollout_host(savi, pred, video_host, NUM_SEED, NUM_PREDS, out_host))
@@ -469,7 +503,8 @@ def run_ours(args):
         "kernel_time_shares": shares, "peaks": pk,
     }
     if world == 1 and not args.skip_extras:
-        line["slot_attention_config2"] = slot_attention_config2(pk)
+        if WORKLOAD == "gridshapes5":
+            line["slot_attention_config2"] = slot_attention_config2(pk)
         if args.conv_mode == "fp16x3" and graphed is not None:
             # The reference's PyTorch-CUDA path runs its convolutions in TF32 (10-bit mantissa, cuDNN default).  The same
             # workload with single fp16 products (11-bit significand; stated tolerance 1e-2) is the
@@ -477,7 +512,7 @@ def run_ours(args):
             try:
                 savi.conv_mode = "fp16"
                 ops.set_linear_mode("fp16")
-                g16 = GraphedSeedRollout(savi, pred, B, NUM_SEED, NUM_PREDS)
+                g16 = GraphedSeedRollout(savi, pred, B, NUM_SEED, NUM_PREDS, resolution=(RES, RES))
                 for _ in range(3):
                     g16(video)
                 torch.cuda.synchronize()
@@ -528,13 +563,29 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="videos per GPU")
-    ap.add_argument("--ref-batch", type=int, default=4, help="videos per step of the CPU arm (bounded sample)")
+    ap.add_argument("--config", default="gridshapes5", choices=sorted(WORKLOADS), help="workload (default: BASELINE.json configs[2])")
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "train"],
+                    help="rollout = seed + rollout inference (the headline metric); train = BASELINE.json configs[3], the joint "
+                         "InvDyn + cOCVP training step on ButtonPress with the NCCL gradient all-reduce")
+    ap.add_argument("--batch", type=int, default=None, help="videos per GPU (default: the workload's)")
+    ap.add_argument("--ref-batch", type=int, default=None, help="videos per step of the CPU arm (bounded sample)")
+    ap.add_argument("--train-arith", default="fp32", choices=["fp32", "fp16x3", "bf16"],
+                    help="--mode train: arithmetic of the predictor's Linear layers (bf16 = one bf16 tensor-core product, fp32 master "
+                         "weights; the decoder convolutions then run single fp16 products)")
     ap.add_argument("--conv-mode", default=os.environ.get("PLAYSLOT_CONV_MODE", "fp16x3"), choices=["fp16x3", "fp16", "bf16", "fp32"],
                     help="arithmetic of the 64->64 5x5 convolutions (fp16x3 = split fp16 tensor-core products, fp32-grade)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--skip-extras", action="store_true", help="skip the config-2 SlotAttention sweep and the CPU baseline")
     args = ap.parse_args()
+    if args.mode == "train":
+        from bench_train import run_train, run_train_reference
+        (run_train_reference if args.impl == "reference" else run_train)(args)
+        return
+    w = set_workload(args.config)
+    if args.batch is None:
+        args.batch = w["batch"]
+    if args.ref_batch is None:
+        args.ref_batch = w["ref_batch"]
     if args.impl == "reference":
         run_reference(args)
     else:

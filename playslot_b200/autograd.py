@@ -40,7 +40,10 @@ class _LayerNorm(torch.autograd.Function):
         return dx, dg, db, None
 
 
-TRAIN_LINEAR_MODE = "fp32"      # arithmetic of the differentiable Linear: "fp32" (exact FFMA kernels) or "fp16x3" (tensor cores)
+# arithmetic of the differentiable Linear: "fp32" (exact FFMA kernels), "fp16x3" (tensor cores, fp32-grade) or "bf16" (tensor
+# cores, one bf16 product per GEMM with fp32 accumulation, fp32 master weights and fp32 weight gradients: the "bf16" training
+# mode of BASELINE.json configs[3])
+TRAIN_LINEAR_MODE = "fp32"
 
 
 class _Linear(torch.autograd.Function):
@@ -65,8 +68,8 @@ class _Linear(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             M = dy.numel() // N
-            if ctx.mode == "fp16x3" and M >= ops.LINEAR_TC_MIN_ROWS and N % 4 == 0 and weight.is_contiguous():
-                dx = ops.linear_dgrad_tc(dy, weight).view(x.shape)
+            if ctx.mode in ("fp16x3", "bf16") and M >= ops.LINEAR_TC_MIN_ROWS and N % 4 == 0 and weight.is_contiguous():
+                dx = ops.linear_dgrad_tc(dy, weight, ctx.mode).view(x.shape)
             else:
                 dx = ops.linear(dy, weight.detach().t().contiguous(), None, mode="fp32").view(x.shape)     # dX = dY W
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):

@@ -257,17 +257,19 @@ def _packed_linear_weight(weight, precision, transposed=False, reuse_scale=False
     return c[1]
 
 
-def linear_dgrad_tc(dy, weight):
-    """ dX = dY @ W on the tensor cores (fp16x3): dy (M, N), weight (N, K) -> (M, K); packs W^T like a Linear weight """
+def linear_dgrad_tc(dy, weight, mode="fp16x3"):
+    """ dX = dY @ W on the tensor cores (fp16x3, or one bf16 product with mode="bf16"): dy (M, N), weight (N, K) -> (M, K);
+    packs W^T like a Linear weight """
     lib = _lib.load()
     _req(dy, "dy"); _req(weight, "weight")
     N, K = weight.shape
     M = dy.numel() // N
-    w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, 3, transposed=True, reuse_scale=True)   # a (K, N) "weight"
+    prec = TC_PRECISION[mode]
+    w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, prec, transposed=True, reuse_scale=True)   # a (K, N) "weight"
     out = torch.empty(M, K, device=dy.device, dtype=torch.float32)
-    with _timed("linear_tc_p3", (M, K, N)):
+    with _timed("linear_tc_p%d" % prec, (M, K, N)):
         st = lib.ps_linear_tc(_ptr(dy.view(M, N)), N, _ptr(w_tc), float(w_scale), Kp, Npad, None, None, None, 0.0,
-                              None, 0, 1, 0, _ptr(out), K, M, K, N, 0, 3, _stream())
+                              None, 0, 1, 0, _ptr(out), K, M, K, N, 0, prec, _stream())
     _lib.check(st, "ps_linear_tc")
     return out
 

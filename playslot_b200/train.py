@@ -163,7 +163,8 @@ class GraphedTrainStep:
     """
     `train_step` for a fixed batch shape captured in ONE CUDA graph (forward, backward, clip, Adam, EMA-VQ update): at the
     reference's batch size (8 videos per GPU) the ~3000 launches of a step are host-bound when issued from Python.
-    Single process only (the gradient all-reduce of multi-GPU training stays on the eager path).  The InvDyn noise is drawn
+    With torch.distributed initialised the NCCL gradient all-reduce and the EMA-VQ statistic all-reduce are part of the graph
+    (every rank must build and call this object in lock step).  The InvDyn noise is drawn
     on the host with the reference's RNG call and uploaded into a static buffer before every replay, like
     pipeline.GraphedSeedRollout.  The optimizer must be built with capturable=True.
     linear_mode="fp16x3" runs the forward and data-gradient GEMMs of the predictor's Linear layers on the tensor cores
@@ -172,11 +173,12 @@ class GraphedTrainStep:
 
     def __init__(self, savi, predictor, optimizer, batch, num_seed, num_preds, resolution=(64, 64), clip_gradient=0.05, warmup=3,
                  bucket=None, linear_mode="fp32"):
-        # Single process only: capturing the NCCL all-reduces of a multi-GPU step with it hung in our 2-GPU trial, so sharded
-        # training keeps the eager train_step (with its GradientBucket).
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise NotImplementedError("GraphedTrainStep covers single-GPU training; use train_step with a GradientBucket")
-        self.bucket = None
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        # Multi-GPU: the gradient all-reduce (one flat bucket the .grad tensors alias) and the EMA-VQ statistic all-reduce are
+        # captured INSIDE the graph.  NCCL capture needs (a) a communicator that has already run on this device -- the
+        # warm-up steps below do that -- and (b) capture_error_mode="thread_local", because the NCCL watchdog thread polls CUDA
+        # events while the capture is open.
+        self.bucket = bucket if bucket is not None else (GradientBucket(predictor.parameters()) if self.world > 1 else None)
         self.savi, self.predictor, self.optimizer = savi, predictor, optimizer
         self.num_seed, self.num_preds = num_seed, num_preds
         T = num_seed + num_preds
@@ -194,11 +196,15 @@ class GraphedTrainStep:
         predictor.train()
 
         from . import autograd as AG
-        if linear_mode not in ("fp32", "fp16x3"):
-            raise ValueError(f"linear_mode={linear_mode!r}; expected 'fp32' or 'fp16x3'")
+        if linear_mode not in ("fp32", "fp16x3", "bf16"):
+            raise ValueError(f"linear_mode={linear_mode!r}; expected 'fp32', 'fp16x3' or 'bf16'")
+        self.linear_mode = linear_mode
 
         def body():
-            optimizer.zero_grad(set_to_none=True)
+            if self.bucket is not None:
+                self.bucket.attach()                                               # zeroed flat bucket, .grad = views
+            else:
+                optimizer.zero_grad(set_to_none=True)
             old_mode, AG.TRAIN_LINEAR_MODE = AG.TRAIN_LINEAR_MODE, linear_mode     # arithmetic of the differentiable Linears
             try:
                 loss, terms, _ = forward_loss(savi, predictor, self.video, num_seed, num_preds)
@@ -206,7 +212,7 @@ class GraphedTrainStep:
             finally:
                 AG.TRAIN_LINEAR_MODE = old_mode
             if self.bucket is not None:
-                self.bucket.all_reduce_mean()
+                self.bucket.all_reduce_mean(local_count=batch)
             if clip_gradient is not None:
                 torch.nn.utils.clip_grad_norm_(predictor.parameters(), clip_gradient)
             optimizer.step()
@@ -225,13 +231,22 @@ class GraphedTrainStep:
                     body()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()
             self.graph = torch.cuda.CUDAGraph()
-            optimizer.zero_grad(set_to_none=True)
-            with torch.cuda.graph(self.graph):
+            if self.bucket is None:
+                optimizer.zero_grad(set_to_none=True)
+            kw = {"capture_error_mode": "thread_local"} if self.world > 1 else {}
+            from . import ops as _ops
+            n0 = _ops.launch_count()
+            with torch.cuda.graph(self.graph, **kw):
                 self.loss, self.terms = body()
+            self.launches_per_replay = _ops.launch_count() - n0       # playslot_b200 kernels inside the graph
         finally:
             la._static_noise = None
             _restore_training_state(predictor, optimizer, snap)
+            if self.bucket is not None:
+                self.bucket.flat.zero_()
 
     def draw_noise(self):
         return torch.randn(self.noise_shape, dtype=torch.float32)
