@@ -125,9 +125,14 @@ def run_train(args):
                                   "the backward (nothing left to overlap), so this is its exposed time"},
             "trainable_params": n_params, "loss_first_last": [losses[0], losses[-1]],
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() after graph-captured collectives blocks in the NCCL watchdog shutdown (measured: the process hangs
+        # until killed); the results are out, leave without the teardown
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_train_reference(args):

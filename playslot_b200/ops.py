@@ -221,9 +221,11 @@ def pack_linear_weight_tc(w, precision, scale=None):
     Kp, Npad = (K + 63) // 64 * 64, (N + 127) // 128 * 128
     wt = torch.zeros(Npad, Kp, device=w.device, dtype=torch.float32)
     wt[:N, :K] = w.detach().float()
+    if precision == 1:
+        scale = 1.0                                   # bf16 has the exponent range of fp32: no scaling (and no host sync)
     if scale is None:
         amax = float(wt.abs().max())
-        scale = 1.0 if amax == 0.0 or precision == 1 else 2.0 ** (-round(math.log2(amax)))
+        scale = 1.0 if amax == 0.0 else 2.0 ** (-round(math.log2(amax)))
     wt = wt * scale
     if precision == 1:
         hi = wt.to(torch.bfloat16).view(torch.int16)

@@ -360,41 +360,36 @@ class FixedRandnLocal:
 
 def test_training_step_bf16_mode_stated_tolerance(train_linear_mode_guard):
     """ the 16-bit tensor-core training mode of BASELINE.json configs[3] (Linear forward / data-gradient GEMMs: one bf16 product,
-    fp32 accumulate, fp32 master weights, fp32 weight gradients and InvDyn tail; decoder convolutions: one fp16 product) against the
-    reference's fp32 training step.  Stated tolerances: loss terms 2e-2, d loss / d pred_slots 5e-2, parameter-gradient norms 1e-1
-    (measured: see DESIGN.md section 4) """
-    from playslot_b200 import train
-    train_linear_mode_guard.TRAIN_LINEAR_MODE = "bf16"
-    fx, ssd, psd, video, noise = _load_train_case("buttonpress")
-    scfg, pcfg = fx["savi_cfg"], fx["predictor_cfg"]
-    ns, npred, B = fx["num_seed"], fx["num_preds"], fx["B"]
-    savi = make_savi(scfg, ssd, DEV)
-    savi.conv_mode = "fp16"
+    fp32 accumulate, fp32 master weights, fp32 weight gradients and InvDyn tail; decoder convolutions: one fp16 product) against
+    the fp32 training step (itself pinned to the reference by test_training_step_matches_reference_golden), on a batch large enough
+    for every Linear to take the tensor-core path (>= 128 rows).  Stated tolerances: loss 2e-2, gradient norms 1e-1, gradient
+    direction (cosine over all parameters) >= 0.98 """
+    from playslot_b200 import configs, train
+    import copy
+    cfg = configs.experiment("ButtonPress")
+    torch.manual_seed(0)
+    savi, pred_a = configs.build_models(cfg, DEV)
     for p in savi.parameters():
         p.requires_grad_(False)
-    pred = make_predictor(fx["predictor_name"], pcfg, psd, DEV).train()
-    sh = fx["slot_history"].to(DEV)
-    with FixedRandn(noise):
-        pred_slots, out = pred(slots=sh, num_seed=ns, num_preds=npred)
-    check("pred_slots (bf16)", pred_slots, fx["pred_slots"], 3e-2)
-    pred_slots.retain_grad()
-    S, D = pred_slots.shape[-2:]
-    n = pred_slots.shape[1]
-    pred_imgs, _ = savi.decode(pred_slots.reshape(B * n, S, D))
-    pred_imgs = pred_imgs.view(B, n, *pred_imgs.shape[1:])
-    T = ns + npred
-    loss, terms = train.predictor_losses(pred_slots, sh[:, 1:T], pred_imgs, video[:, 1:T].to(DEV), out["vq_losses"])
-    for k, ref in (("pred_img_mse", fx["pred_img_mse"]), ("pred_slot_mse", fx["pred_slot_mse"])):
-        assert abs(float(terms[k]) - ref) <= 2e-2 * abs(ref), f"{k}: {float(terms[k])} vs {ref}"
-    loss.backward()
-    check("d loss / d pred_slots (bf16)", pred_slots.grad, fx["d_pred_slots"], 5e-2)
-    named = dict(pred.named_parameters())
-    big = max(v for v in fx["grad_norms"].values() if v)
-    worst = 0.0
-    for k, ref_norm in fx["grad_norms"].items():
-        if ref_norm is None or ref_norm < 1e-3 * big:
-            continue
-        got = float(named[k].grad.double().norm())
-        worst = max(worst, abs(got - ref_norm) / ref_norm)
-        assert abs(got - ref_norm) <= 1e-1 * ref_norm, f"{k}: grad norm {got} vs {ref_norm}"
-    print(f"bf16 training mode: worst relative gradient-norm error {worst:.3e}")
+    pred_b = copy.deepcopy(pred_a)
+    B, ns, npred = 16, 6, 4
+    gen = torch.Generator().manual_seed(21)
+    video = torch.rand(B, ns + npred, 3, 64, 64, generator=gen).to(DEV)
+    noise = torch.randn(B, ns + npred - 1, cfg["predictor"]["predictor_params"]["action_dim"], generator=gen)
+    res = {}
+    for name, pred, lin, conv in (("fp32", pred_a, "fp32", "fp16x3"), ("bf16", pred_b, "bf16", "fp16")):
+        train_linear_mode_guard.TRAIN_LINEAR_MODE = lin
+        savi.conv_mode = conv
+        pred.train()
+        with FixedRandn(noise):
+            loss, terms, _ = train.forward_loss(savi, pred, video, ns, npred)
+        loss.backward()
+        res[name] = (float(loss), {k: p.grad.detach().double().flatten() for k, p in pred.named_parameters() if p.grad is not None})
+    la, ga = res["fp32"]
+    lb, gb = res["bf16"]
+    assert abs(la - lb) <= 2e-2 * abs(la), f"loss {lb} (bf16 mode) vs {la} (fp32)"
+    va, vb = torch.cat([ga[k] for k in ga]), torch.cat([gb[k] for k in ga])
+    cos = float((va @ vb) / (va.norm() * vb.norm()))
+    worst = max(abs(float(gb[k].norm() - ga[k].norm())) / float(ga[k].norm()) for k in ga if float(ga[k].norm()) > 1e-3 * float(va.norm()))
+    print(f"bf16 training mode: loss {lb:.6f} vs {la:.6f}, gradient cosine {cos:.5f}, worst gradient-norm error {worst:.3e}")
+    assert cos >= 0.98 and worst <= 1e-1, (cos, worst)
