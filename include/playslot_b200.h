@@ -95,6 +95,10 @@ int ps_conv2d(const float* x, const float* w_packed, const float* bias, const fl
 /* ps_conv2d with Cout == 64 writing the padded NHWC split planes of ps_conv5x5_tc directly (first encoder convolution). */
 int ps_conv2d_split(const float* x, const float* w_packed, const float* bias, void* act_out, int n_img, int Cin, int H, int W,
                     int ksize, int relu, int precision, void* stream);
+/* ps_conv2d_split on uint8 images (0..255): x / 255 -- the ToTensor normalisation of the reference's data pipeline
+ * (src/data/load_data.py:86-91, consumed at src/05_evaluate_PlaySlot.py:75) -- fused into the first encoder convolution */
+int ps_conv2d_split_u8(const unsigned char* x8, const float* w_packed, const float* bias, void* act_out, int n_img, int Cin,
+                       int H, int W, int ksize, int relu, int precision, void* stream);
 
 /* ---- SlotAttention (src/models/BlocksUtils/attention.py:76-119) ---------------------------------------- */
 
@@ -270,6 +274,19 @@ int ps_dec_expand_bwd(const float* g_tokens, float* dG, const float* g_scale, in
  * proto = z + (z_q - z), exact codewords z_q, int64 indices, per-vector mean_A (z_q - z)^2. */
 int ps_vq_lookup(const float* z, const float* codebook, float* proto_out, float* zq_out, long long* idx_out,
                  float* loss_out, int n, int A, int K, void* stream);
+
+/* ---- fused loss / metric tail ------------------------------------------------------------------------- */
+
+/* out[f] = sum_e (pred[f][e] - target[f][e])^2 per frame (optionally both clamped to [0, 1]), one pass, deterministic.
+ * Replaces nn.MSELoss of PredImgMSELoss / PredSlotMSELoss (src/lib/loss.py:201-238) in the training step and the per-frame
+ * PSNR input of the evaluation (src/05_evaluate_PlaySlot.py:98-108 -> lib/metrics.py:225-235 -> piqa.psnr), which the
+ * reference computes on the CPU after copying every predicted frame to the host.  Strides in elements. */
+int ps_frame_sq_err(const float* pred, const float* target, float* out, long long n_videos, int frames_per_video, long long elems,
+                    long long pred_video_stride, long long pred_frame_stride, long long tgt_video_stride, long long tgt_frame_stride,
+                    int clamp01, void* stream);
+/* d_pred = 2 * scale * g[0] * (pred - target): backward of scale * sum (pred - target)^2 (loss.backward() through nn.MSELoss) */
+int ps_mse_bwd(const float* pred, const float* target, const float* g, float scale, float* d_pred, long long n_videos,
+               int frames_per_video, long long elems, long long tgt_video_stride, long long tgt_frame_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@ SIGNATURES = {
     "ps_mha": (c_i, [c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_conv2d": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_conv2d_split": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "ps_conv2d_split_u8": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_sa_partial_floats": (c_i, [c_i]),
     "ps_sa_main": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),
     "ps_sa_main_tc": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),
@@ -55,6 +56,8 @@ SIGNATURES = {
     "ps_dec_expand_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_dec_composite_tc": (c_i, [c_f, c_f, c_fl, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_nchw_to_split": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
+    "ps_frame_sq_err": (c_i, [c_f, c_f, c_f, ctypes.c_longlong, c_i] + [ctypes.c_longlong] * 5 + [c_i, c_f]),
+    "ps_mse_bwd": (c_i, [c_f, c_f, c_f, c_fl, c_f, ctypes.c_longlong, c_i, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_f]),
 }
 
 _lib = None

@@ -187,3 +187,28 @@ def invdyn_tail(mv, noise, codebook, per_slot):
         return out
     dist, z, proto, var, idx, quant, commit = _InvDynTail.apply(mv, noise, codebook, per_slot)
     return {"action_dist": dist, "z": z, "proto": proto, "variability": var, "idx": idx, "quant": quant, "commit": commit}
+
+
+class _MSELoss(torch.autograd.Function):
+    """ nn.MSELoss(pred, target) (mean over all elements; PredImgMSELoss / PredSlotMSELoss, src/lib/loss.py:201-238) as one
+    reduction pass and one backward pass; the target may be a time slice of the clip (read in place), no gradient w.r.t. it """
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred = _c(pred)
+        sq = ops.frame_sq_err(pred, target)
+        ctx.save_for_backward(pred, target)
+        ctx.scale = 1.0 / pred.numel()
+        return sq.sum() * ctx.scale
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        return ops.mse_bwd(pred, target, _c(g.reshape(1)), ctx.scale), None
+
+
+def mse_loss(pred, target):
+    """ (B, F, ...) tensors -> scalar mean squared error, differentiable w.r.t. pred """
+    if not _needs_grad(pred):
+        return ops.frame_sq_err(_c(pred), target).sum() / pred.numel()
+    return _MSELoss.apply(pred, target)

@@ -524,6 +524,7 @@ extern "C" int ps_mha_planes(const float* qkv, int ld, const float* res, void* o
 // ------------------------------------------------------------------------------------------------
 struct ConvParams {
     const float* x;        // [n][Cin][H][W]
+    const uint8_t* x8;     // uint8 images [n][Cin][H][W] instead of x: value / 255 (torchvision ToTensor, data/load_data.py) on the fly
     const float* wp;       // packed [Cin][KS*KS][Cout]
     const float* bias;     // [Cout] or null
     const float* addend;   // NHWC addend [H*W][Cout] (only with out_nhwc) or null
@@ -553,7 +554,8 @@ __global__ __launch_bounds__(256) void conv2d_kernel(ConvParams p) {
     const int ty0 = (blockIdx.x / tiles_x) * CV_T, tx0 = (blockIdx.x % tiles_x) * CV_T;
     const int img = blockIdx.y;
     const int py = lane >> 1, px0 = (lane & 1) * 8;
-    const float* xin = p.x + (size_t)img * p.Cin * p.H * p.W;
+    const float* xin = p.x ? p.x + (size_t)img * p.Cin * p.H * p.W : nullptr;
+    const uint8_t* xin8 = p.x8 ? p.x8 + (size_t)img * p.Cin * p.H * p.W : nullptr;
 
     float acc[8][COUT_T];
 #pragma unroll
@@ -570,8 +572,10 @@ __global__ __launch_bounds__(256) void conv2d_kernel(ConvParams p) {
             const int hy = r / CV_HS, hx = r - hy * CV_HS;
             const int gy = ty0 + hy - PAD, gx = tx0 + hx - PAD;
             float v = 0.f;
-            if (hx < HH && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
-                v = xin[((size_t)(c0 + ci) * p.H + gy) * p.W + gx];
+            if (hx < HH && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+                const size_t o = ((size_t)(c0 + ci) * p.H + gy) * p.W + gx;
+                v = xin8 ? __fdiv_rn((float)xin8[o], 255.0f) : xin[o];       // IEEE division: bit-equal to ToTensor's x.div(255)
+            }
             s_in[idx] = v;
         }
         // stage the weights of these channels: contiguous in the packed layout
@@ -693,7 +697,7 @@ extern "C" int ps_conv2d(const float* x, const float* w_packed, const float* bia
     PS_REQUIRE(ps_aligned16(x) && ps_aligned16(w_packed) && ps_aligned16(y), "ps_conv2d: pointers must be 16-byte aligned");
     PS_REQUIRE(!addend_nhwc || out_nhwc, "ps_conv2d: the addend is only supported with NHWC output");
     ConvParams p;
-    p.x = x; p.wp = w_packed; p.bias = bias; p.addend = addend_nhwc; p.y = y;
+    p.x = x; p.x8 = nullptr; p.wp = w_packed; p.bias = bias; p.addend = addend_nhwc; p.y = y;
     p.n = n_img; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu; p.out_nhwc = out_nhwc ? 1 : 0;
     p.split_hi = nullptr; p.split_lo = nullptr; p.split_bf16 = 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -707,17 +711,35 @@ extern "C" int ps_conv2d(const float* x, const float* w_packed, const float* bia
 
 // ps_conv2d writing the zero-bordered NHWC split planes consumed by ps_conv5x5_tc (Cout == 64): the first encoder
 // convolution feeds the tensor-core layers without an fp32 NCHW round trip.
+static int conv2d_split_run(const float* x, const uint8_t* x8, const float* w_packed, const float* bias, void* act_out, int n_img, int Cin,
+                            int H, int W, int ksize, int relu, int precision, void* stream);
+
 extern "C" int ps_conv2d_split(const float* x, const float* w_packed, const float* bias, void* act_out, int n_img, int Cin,
                                int H, int W, int ksize, int relu, int precision, void* stream) {
-    PS_REQUIRE(x && w_packed && act_out, "ps_conv2d_split: null pointer");
+    PS_REQUIRE(x, "ps_conv2d_split: null pointer");
+    return conv2d_split_run(x, nullptr, w_packed, bias, act_out, n_img, Cin, H, W, ksize, relu, precision, stream);
+}
+
+// the same with uint8 input images (0..255): the ToTensor normalisation x / 255 of the reference's data pipeline
+// (src/data/load_data.py:86-91 DataLoader -> .to(device), 05_evaluate_PlaySlot.py:75) is applied while the halo tile is staged,
+// so a clip travels over PCIe / through HBM as 1 byte per value instead of 4
+extern "C" int ps_conv2d_split_u8(const unsigned char* x8, const float* w_packed, const float* bias, void* act_out, int n_img, int Cin,
+                                  int H, int W, int ksize, int relu, int precision, void* stream) {
+    PS_REQUIRE(x8, "ps_conv2d_split_u8: null pointer");
+    return conv2d_split_run(nullptr, x8, w_packed, bias, act_out, n_img, Cin, H, W, ksize, relu, precision, stream);
+}
+
+static int conv2d_split_run(const float* x, const uint8_t* x8, const float* w_packed, const float* bias, void* act_out, int n_img, int Cin,
+                            int H, int W, int ksize, int relu, int precision, void* stream) {
+    PS_REQUIRE(w_packed && act_out, "ps_conv2d_split: null pointer");
     PS_REQUIRE(precision >= 1 && precision <= 3, "ps_conv2d_split: precision must be 1, 2 or 3");
     PS_REQUIRE(n_img >= 0 && Cin > 0, "ps_conv2d_split: bad shape");
     if (n_img == 0) return PS_OK;
     PS_REQUIRE(H % CV_T == 0 && W % CV_T == 0, "ps_conv2d_split: H and W must be multiples of %d (got %dx%d)", CV_T, H, W);
     PS_REQUIRE(n_img <= 65535, "ps_conv2d_split: at most 65535 images per launch (got %d)", n_img);
-    PS_REQUIRE(ps_aligned16(x) && ps_aligned16(w_packed) && ps_aligned16(act_out), "ps_conv2d_split: pointers must be 16-byte aligned");
+    PS_REQUIRE((!x || ps_aligned16(x)) && ps_aligned16(w_packed) && ps_aligned16(act_out), "ps_conv2d_split: pointers must be 16-byte aligned");
     ConvParams p;
-    p.x = x; p.wp = w_packed; p.bias = bias; p.addend = nullptr; p.y = nullptr;
+    p.x = x; p.x8 = x8; p.wp = w_packed; p.bias = bias; p.addend = nullptr; p.y = nullptr;
     p.n = n_img; p.Cin = Cin; p.Cout = 64; p.H = H; p.W = W; p.relu = relu; p.out_nhwc = 2;
     const long long P = (long long)n_img * (H + 4) * (W + 4);
     p.split_hi = reinterpret_cast<uint16_t*>(act_out);

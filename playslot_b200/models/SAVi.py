@@ -179,7 +179,14 @@ class SAVi(nn.Module):
         SlotAttention's "tc" mode instead """
         require_cuda(x, "SAVi.encode")
         no_grad_only("SAVi.encode", x, self.encoder_mlp[1].weight)
-        x = f32c(x)
+        # uint8 frames (0..255): the ToTensor normalisation x / 255 of the reference's DataLoader (data/load_data.py:86-91) is fused
+        # into the first convolution when it runs as the split-plane producer; otherwise normalise here (same IEEE division)
+        u8_fused = (x.dtype == torch.uint8 and x.shape[0] <= 65535 and x.shape[2] % 16 == 0 and x.shape[3] % 16 == 0
+                    and self._tc_applicable(self.encoder.encoder, skip_first=True, channels=self.enc_tc_channels))
+        if x.dtype == torch.uint8:
+            x = x.contiguous() if u8_fused else x.float().div(255)
+        if not u8_fused:
+            x = f32c(x)
         M, _, H, W = x.shape
         posemb = self.encoder_pos_embedding.table(channels_last=True)
         ln, fc1, fc2 = self.encoder_mlp[0], self.encoder_mlp[1], self.encoder_mlp[3]

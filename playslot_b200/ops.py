@@ -369,11 +369,20 @@ def conv2d(x, w_packed, bias, ksize, relu, out_nhwc=False, addend=None):
 
 
 def conv2d_split(x, w_packed, bias, ksize, relu, act_out, precision):
-    """ x (n, Cin, H, W) -> padded NHWC split planes (Cout == 64) in `act_out` """
+    """ x (n, Cin, H, W) fp32 -- or uint8 images 0..255, normalised by 1/255 inside the kernel -- -> padded NHWC split planes
+    (Cout == 64) in `act_out` """
     lib = _lib.load()
-    _req(x, "x"); _req(w_packed, "w_packed")
+    _req(w_packed, "w_packed")
     n, Cin, H, W = x.shape
     assert w_packed.shape[-1] == 64 and n <= 65535
+    if x.dtype == torch.uint8:
+        if not x.is_cuda or not x.is_contiguous():
+            raise ValueError("conv2d_split: uint8 images must be a contiguous CUDA tensor")
+        with _timed("conv2d_%dx%d_%dto64_split" % (ksize, ksize, Cin), (n, Cin, 64, H, W, ksize)):
+            st = lib.ps_conv2d_split_u8(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(act_out), n, Cin, H, W, ksize, int(relu), int(precision), _stream())
+        _lib.check(st, "ps_conv2d_split_u8")
+        return act_out
+    _req(x, "x")
     with _timed("conv2d_%dx%d_%dto64_split" % (ksize, ksize, Cin), (n, Cin, 64, H, W, ksize)):
         st = lib.ps_conv2d_split(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(act_out), n, Cin, H, W, ksize, int(relu), int(precision), _stream())
     _lib.check(st, "ps_conv2d_split")
@@ -790,3 +799,58 @@ def dec_expand_bwd(g_tokens, n_img, H, W, ksize, g_scale=None):
         st = lib.ps_dec_expand_bwd(_ptr(g_tokens), _ptr(dG), _ptr(g_scale), n_img, H, W, ksize, _stream())
     _lib.check(st, "ps_dec_expand_bwd")
     return dG
+
+
+# ------------------------------------------------------------------------------------------------ fused loss / metric tail
+
+def _frame_layout(t, name):
+    """ (B, F, ...) tensor whose frames (all trailing dimensions) are contiguous -> (B, F, elems, video stride, frame stride) """
+    _req_f32_cuda(t, name)
+    if t.dim() < 3:
+        raise ValueError(f"{name}: expected (B, F, ...), got {tuple(t.shape)}")
+    B, Fr = t.shape[0], t.shape[1]
+    elems = 1
+    for d in t.shape[2:]:
+        elems *= d
+    expect = 1
+    for d, st in zip(reversed(t.shape[2:]), reversed(t.stride()[2:])):
+        if d != 1 and st != expect:
+            raise ValueError(f"{name}: the trailing (per-frame) dimensions must be contiguous")
+        expect *= d
+    return B, Fr, elems, t.stride(0), t.stride(1)
+
+
+def _req_f32_cuda(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a tensor")
+    if not t.is_cuda:
+        raise _lib.PlaySlotKernelError(f"{name} lives on {t.device}: playslot_b200 runs on CUDA (sm_100a) only and has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+
+
+def frame_sq_err(pred, target, clamp01=False):
+    """ pred, target (B, F, ...) (time slices of a clip are read in place) -> (B, F) sums of squared differences per frame """
+    lib = _lib.load()
+    B, Fr, elems, pv, pf = _frame_layout(pred, "pred")
+    B2, F2, e2, tv, tf = _frame_layout(target, "target")
+    if (B, Fr, elems) != (B2, F2, e2):
+        raise ValueError(f"frame_sq_err: pred {tuple(pred.shape)} vs target {tuple(target.shape)}")
+    out = torch.empty(B, Fr, device=pred.device, dtype=torch.float32)
+    with _timed("frame_sq_err"):
+        st = lib.ps_frame_sq_err(_ptr(pred), _ptr(target), _ptr(out), B, Fr, elems, pv, pf, tv, tf, int(clamp01), _stream())
+    _lib.check(st, "ps_frame_sq_err")
+    return out
+
+
+def mse_bwd(pred, target, g, scale):
+    """ 2 * scale * g * (pred - target) for a contiguous pred (B, F, ...) and a target addressed like in frame_sq_err """
+    lib = _lib.load()
+    _req(pred, "pred")
+    B, Fr, elems, _, _ = _frame_layout(pred, "pred")
+    _, _, _, tv, tf = _frame_layout(target, "target")
+    d = torch.empty_like(pred)
+    with _timed("mse_bwd"):
+        st = lib.ps_mse_bwd(_ptr(pred), _ptr(target), _ptr(g), float(scale), _ptr(d), B, Fr, elems, tv, tf, _stream())
+    _lib.check(st, "ps_mse_bwd")
+    return d

@@ -143,7 +143,10 @@ class GraphedSeedRollout:
     replay, so results are identical to the eager path under the same seed.
     """
 
-    def __init__(self, savi, predictor, batch, num_seed, num_preds, resolution=(64, 64), num_samples=1, device="cuda", warmup=2):
+    def __init__(self, savi, predictor, batch, num_seed, num_preds, resolution=(64, 64), num_samples=1, device="cuda", warmup=2,
+                 video_dtype=torch.float32):
+        """ video_dtype=torch.uint8: the clip arrives as 0..255 bytes (a quarter of the PCIe / HBM traffic of fp32 frames); the
+        x / 255 normalisation of the reference's ToTensor runs inside the first encoder convolution """
         if num_samples != 1:
             raise NotImplementedError("the graphed path covers the posterior rollout (num_samples=1); prior samples draw "
                                       "random codebook indices on the host and use the eager path")
@@ -155,7 +158,7 @@ class GraphedSeedRollout:
         S, A = savi.num_slots, la.action_dim
         per_slot = type(la).__name__ == "VQSimpleMLPSlotLatentAction"
         self.noise_shape = (batch, T - 1, S, A) if per_slot else (batch, T - 1, A)
-        self.video = torch.zeros(batch, T, 3, H, W, device=device)
+        self.video = torch.zeros(batch, T, 3, H, W, device=device, dtype=video_dtype)
         self.noise = torch.zeros(self.noise_shape, device=device)
         self._noise_ring = PinnedRing(self.noise_shape)
         la._static_noise = self.noise

@@ -20,8 +20,10 @@ import torch.distributed as dist
 
 def predictor_losses(pred_slots, target_slots, pred_imgs, target_imgs, vq_losses, commit_weight=0.25):
     """ the three loss terms of the shipped PlaySlot configs; returns (total, dict of detached terms) """
-    img = torch.nn.functional.mse_loss(pred_imgs, target_imgs)
-    slot = torch.nn.functional.mse_loss(pred_slots, target_slots)
+    from . import autograd as AG
+    # one fused reduction pass per term (csrc/metrics.cu); the targets are time slices of the clip / slot history, read in place
+    img = AG.mse_loss(pred_imgs, target_imgs)
+    slot = AG.mse_loss(pred_slots, target_slots)
     quant, commit = vq_losses["quant_loss"].mean(), vq_losses["commit_loss"].mean()
     total = img + slot + quant + commit_weight * commit
     return total, {"pred_img_mse": img.detach(), "pred_slot_mse": slot.detach(), "quant": quant.detach(), "commit": commit.detach()}

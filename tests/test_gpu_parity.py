@@ -697,3 +697,81 @@ def test_config5_highres_many_slots_vs_oracle():
     check("recon", recon, r_recon)
     check("masks", masks, r_masks)
     check("recons", recons, r_recons)
+
+
+# ----------------------------------------------------------------------------------------------- input pipeline / metric tail
+
+@pytest.mark.parametrize("case", ["gridshapes5", "buttonpress"])
+def test_uint8_video_equals_normalised_float(case):
+    """ uint8 frames with the ToTensor normalisation (x / 255, data/load_data.py:86-91) fused into the first encoder
+    convolution give bit-identical slots to feeding the normalised fp32 frames; also through the CUDA-graph pipeline """
+    from playslot_b200.pipeline import GraphedSeedRollout
+    fx, ssd, psd, video, noise, init_noise = load_case(case)
+    savi = make_savi(fx["savi_cfg"], ssd, DEV)
+    pred = make_predictor(fx["predictor_name"], fx["predictor_cfg"], psd, DEV)
+    B, ns, npred = fx["B"], fx["num_seed"], fx["num_preds"]
+    v8 = (video * 255).round().to(torch.uint8)
+    vf = v8.float().div(255)
+    runs = []
+    for v in (v8, vf):
+        with torch.no_grad():
+            if init_noise is not None:
+                with FixedRandn(init_noise):
+                    runs.append(savi(v.to(DEV), num_imgs=ns + npred, decode=False)["slot_history"])
+            else:
+                runs.append(savi(v.to(DEV), num_imgs=ns + npred, decode=False)["slot_history"])
+    assert torch.equal(runs[0], runs[1]), "uint8 path differs from the normalised fp32 path"
+    with torch.no_grad():
+        check("encode(uint8) vs oracle", savi.encode(v8[:, 0].to(DEV)), O.encode(ssd, vf[:, 0]))
+    if init_noise is None:
+        g8 = GraphedSeedRollout(savi, pred, B, ns, npred, video_dtype=torch.uint8)
+        gf = GraphedSeedRollout(savi, pred, B, ns, npred)
+        a = g8(v8.pin_memory(), noise=noise)["pred_imgs"].clone()
+        b = gf(vf.to(DEV), noise=noise)["pred_imgs"]
+        assert torch.equal(a, b)
+
+
+def test_frame_metrics_and_fused_mse_loss():
+    """ per-frame squared error / PSNR on the device (piqa.psnr definition) and the fused MSE loss with its
+    backward, against plain torch on the same tensors; targets are time slices read in place """
+    from playslot_b200 import metrics, ops, autograd as AG
+    B, T, ns, npred = 3, 9, 4, 5
+    video = torch.rand(B, T, 3, 64, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    pred = (video[:, ns:ns + npred] + 0.1 * g(B, npred, 3, 64, 64, seed=2).to(DEV)).contiguous()
+    tgt = video[:, ns:ns + npred]                                        # non-contiguous slice of the clip
+    sq = ops.frame_sq_err(pred, tgt)
+    check("frame_sq_err", sq, ((pred - tgt) ** 2).flatten(2).sum(-1), 1e-5)
+    p = metrics.psnr(pred, tgt)
+    pc, tc_ = pred.clamp(0, 1), tgt.clamp(0, 1)
+    ref = 10 * torch.log10(1.0 / (((pc - tc_) ** 2).flatten(2).mean(-1) + 1e-8))
+    check("psnr", p, ref, 1e-5)
+    # fused MSE loss: value and gradient
+    x = pred.clone().requires_grad_(True)
+    loss = AG.mse_loss(x, tgt)
+    (loss * 3.0).backward()
+    xr = pred.clone().requires_grad_(True)
+    lr = F.mse_loss(xr, tgt)
+    (lr * 3.0).backward()
+    assert abs(float(loss) - float(lr)) <= 1e-6 * abs(float(lr))
+    check("d mse / d pred", x.grad, xr.grad, 1e-6)
+    # slots-shaped (B, F, S, D)
+    s1, s2 = g(4, 7, 6, 128, seed=3).to(DEV), g(4, 9, 6, 128, seed=4).to(DEV)
+    check("slot mse", AG.mse_loss(s1, s2[:, 1:8]).reshape(1), F.mse_loss(s1, s2[:, 1:8]).reshape(1), 1e-6)
+
+
+def test_evaluate_rollout_metrics_on_device():
+    """ forward_eval of 05_evaluate_PlaySlot.py:66-108 with the PSNR tail on the GPU == PSNR computed from the frames on the host """
+    from playslot_b200 import metrics
+    from playslot_b200.pipeline import seed_rollout
+    fx, ssd, psd, video, noise, init_noise = load_case("buttonpress")
+    savi = make_savi(fx["savi_cfg"], ssd, DEV)
+    pred = make_predictor(fx["predictor_name"], fx["predictor_cfg"], psd, DEV)
+    ns, npred = fx["num_seed"], fx["num_preds"]
+    with FixedRandn(noise):
+        ev = metrics.evaluate_rollout(savi, pred, video.to(DEV), ns, npred)
+    with FixedRandn(noise):
+        res = seed_rollout(savi, pred, video.to(DEV), ns, npred)
+    imgs = res["pred_imgs"][:, 0].cpu().clamp(0, 1)
+    tgt = video[:, ns:ns + npred].clamp(0, 1)
+    ref = 10 * torch.log10(1.0 / (((imgs - tgt) ** 2).flatten(2).mean(-1) + 1e-8))
+    check("psnr (device tail vs host)", ev["psnr"], ref, 1e-5)
