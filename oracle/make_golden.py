@@ -255,10 +255,88 @@ def run_prior_cases(setup_predictor):
     return res
 
 
+def closed_loop_policy(slots_t, Wp):
+    """ deterministic stand-in for the behaviour model of 11_evaluate_behavior_on_simulation.py:151 (models.Downstream is outside
+    the hot path): latent action = tanh(mean over slots (or per slot) of slots_t @ Wp) """
+    if Wp.dim() == 3:                                  # per-slot latent actions (SlotLatentPredictor)
+        return torch.tanh(torch.einsum("bsd,sda->bsa", slots_t, Wp))
+    return torch.tanh(slots_t.mean(dim=1) @ Wp)
+
+
+def run_closed_loop_cases(setup_model, setup_predictor):
+    """ the latent-imagination loop of 11_evaluate_behavior_on_simulation.py:128-183 with the reference modules: SAVi on the first
+    frame (decode=True), then per step policy -> InvDyn.decompose_action_latent -> cOCVP.enforce_window -> forward_single ->
+    savi.decode(pred_slots[:, 0]); 11 steps, so the 8-frame window slides """
+    res = {}
+    for exp, wseed in (("BlockPush", 51), ("GridShapes5Objs", 52)):
+        j = json.load(open(os.path.join(REF, "experiments", exp, "predictors", "PlaySlot", "experiment_params.json")))
+        scfg = copy.deepcopy(j["model"]["model_params"])
+        pcfg = copy.deepcopy(j["predictor"]["predictor_params"])
+        savi = setup_model(copy.deepcopy(j["model"])).eval()
+        pred = setup_predictor(copy.deepcopy(j)).eval()
+        sman, pman = manifest_of(savi), manifest_of(pred)
+        ssd = synth_state_dict(sman, wseed)
+        psd = synth_state_dict(pman, wseed + 100)
+        psd["dynamics_model.pos_emb.pe"] = pred.state_dict()["dynamics_model.pos_emb.pe"].clone()
+        savi.load_state_dict(ssd, strict=True)
+        pred.load_state_dict(psd, strict=True)
+        S, D, A = scfg["num_slots"], scfg["slot_dim"], pcfg["action_dim"]
+        per_slot = pcfg["LatentAction"]["model_name"] == "VQSimpleMLPSlotLatentAction"
+        B, steps = 2, 11
+        g = torch.Generator().manual_seed(wseed + 7)
+        init_img = torch.rand(B, 3, 64, 64, generator=g)
+        Wp = torch.randn((S, D, A) if per_slot else (D, A), generator=g) / D ** 0.5
+        init_noise = synth_noise((B, S, D), wseed + 1) if scfg["initializer"] == "LearnedRandom" else None
+        InvDyn, cOCVP = pred.latent_action, pred.dynamics_model
+        with torch.no_grad():
+            real_randn = torch.randn
+            if init_noise is not None:
+                torch.randn = lambda *a, **k: init_noise.clone()
+            try:
+                out = savi(init_img.unsqueeze(1), num_imgs=1, decode=True)
+            finally:
+                torch.randn = real_randn
+            cur_slots = out["slot_history"]
+            all_pred_slots, protos_hist, vars_hist, idx_hist = [cur_slots], [], [], []
+            imgs, masks = [out["recons_imgs"][:, 0]], [out["masks"][:, 0]]
+            for i in range(steps):
+                # the reference indexes the (window-cropped) slot tensor with the step counter (`cur_slots[:, i:i+1]`), which is the
+                # newest frame until the window is full; the stand-in policy reads the newest frame throughout
+                latent = closed_loop_policy(all_pred_slots[-1][:, 0] if all_pred_slots[-1].dim() == 4 else all_pred_slots[-1], Wp)
+                proto, var = InvDyn.decompose_action_latent(latent)
+                protos_hist.append(proto)
+                vars_hist.append(var)
+                cp, cv = torch.stack(protos_hist, dim=1), torch.stack(vars_hist, dim=1)
+                cur_slots, cp, cv = cOCVP.enforce_window(slots=cur_slots, action_protos=cp, action_vars=cv)
+                if len(cp.shape) == 3:
+                    cp = cp.unsqueeze(2).expand(-1, -1, S, -1)
+                    cv = cv.unsqueeze(2).expand(-1, -1, S, -1)
+                ps = cOCVP.forward_single(slots=cur_slots, action_protos=cp, action_vars=cv)[:, -1:]
+                all_pred_slots.append(ps)
+                cur_slots = torch.cat(all_pred_slots, dim=1)
+                img, (_, msk) = savi.decode(ps[:, 0])
+                imgs.append(img)
+                masks.append(msk)
+        res[exp] = {"savi_cfg": scfg, "predictor_cfg": pcfg, "predictor_name": j["predictor"]["predictor_name"],
+                    "savi_manifest": sman, "predictor_manifest": pman, "weight_seed": wseed, "input_seed": wseed + 7,
+                    "B": B, "steps": steps, "per_slot": per_slot,
+                    "pred_slots": torch.cat(all_pred_slots, dim=1).clone(), "protos": torch.stack(protos_hist, dim=1).clone(),
+                    "vars": torch.stack(vars_hist, dim=1).clone(),
+                    "imgs_last3": torch.stack(imgs[-3:], dim=1).clone(), "masks_last": masks[-1].clone(),
+                    "init_recon": imgs[0].clone()}
+    return res
+
+
 def main():
     setup_model, setup_predictor = _import_reference()
     outdir = os.path.join(REPO, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    if os.environ.get("GOLDEN_ONLY_LOOP"):
+        cl = run_closed_loop_cases(setup_model, setup_predictor)
+        path = os.path.join(outdir, "closed_loop.pt")
+        torch.save(cl, path)
+        print(f"closed_loop: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+        return
     if os.environ.get("GOLDEN_ONLY_PRIOR"):
         pr = run_prior_cases(setup_predictor)
         path = os.path.join(outdir, "prior_samples.pt")
@@ -285,6 +363,10 @@ def main():
     path = os.path.join(outdir, "prior_samples.pt")
     torch.save(pr, path)
     print(f"prior_samples: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+    cl = run_closed_loop_cases(setup_model, setup_predictor)
+    path = os.path.join(outdir, "closed_loop.pt")
+    torch.save(cl, path)
+    print(f"closed_loop: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
     sa = run_slot_attention_cases(setup_model)
     path = os.path.join(outdir, "slot_attention.pt")
     torch.save(sa, path)

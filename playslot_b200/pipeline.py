@@ -267,3 +267,102 @@ class HostPipeline:
         self.h2d.synchronize()
         torch.cuda.current_stream().synchronize()
         self.d2h.synchronize()
+
+
+class ClosedLoopStepper:
+    """
+    Latent imagination, one frame at a time -- the loop of src/11_evaluate_behavior_on_simulation.py:128-183 around an external
+    behaviour model:
+
+        stepper = ClosedLoopStepper(savi, predictor, batch)
+        first = stepper.reset(init_img)                      # savi(init_img.unsqueeze(1), num_imgs=1, decode=True)
+        for i in range(n):
+            latent = policy(stepper.slots[:, -1:])[:, 0]     # (B, A) or (B, S, A), by the caller
+            out = stepper.step(latent)                       # decompose_action_latent -> enforce_window -> forward_single -> decode
+
+    Single-step latency is what matters for planning: with graphs=True every window length (1 .. context_length frames) gets
+    its own CUDA graph (captured lazily at first use) of decompose + cOCVP step + decode of the predicted frame, so a step is
+    two small device copies and one graph replay.  Same kernels as the eager calls: results are bit-identical.
+    """
+
+    def __init__(self, savi, predictor, batch, graphs=True):
+        self.savi, self.predictor = savi, predictor
+        self.inv, self.dyn = predictor.latent_action, predictor.dynamics_model
+        self.B, self.S, self.D = batch, savi.num_slots, savi.slot_dim
+        self.A = self.inv.action_dim
+        self.ctx = self.dyn.context_length
+        self.per_slot = type(self.inv).__name__ == "VQSimpleMLPSlotLatentAction"
+        self.graphs_enabled = graphs
+        self._graphs = {}
+        self.slots = None
+        self._protos, self._vars = [], []
+
+    @torch.no_grad()
+    def reset(self, init_img, **init_kwargs):
+        """ init_img (B, 3, H, W) -> dict(slots (B, 1, S, D), recons_imgs, recons_objs, masks) of the first frame """
+        out = self.savi(init_img.unsqueeze(1), num_imgs=1, decode=True, **init_kwargs)
+        self.slots = out["slot_history"]
+        self._protos, self._vars = [], []
+        return {"slots": self.slots, "recons_imgs": out["recons_imgs"][:, 0], "recons_objs": out["recons_objs"][:, 0], "masks": out["masks"][:, 0]}
+
+    def _body(self, latent, slots_win, protos_prev, vars_prev):
+        """ decompose the new latent action, append it to the (window-cropped) history, predict and decode the next frame """
+        proto, var = self.inv.decompose_action_latent(latent)
+        protos = torch.cat([protos_prev, proto.unsqueeze(1)], dim=1) if protos_prev is not None else proto.unsqueeze(1)
+        vars_ = torch.cat([vars_prev, var.unsqueeze(1)], dim=1) if vars_prev is not None else var.unsqueeze(1)
+        cp, cv = protos, vars_
+        if cp.dim() == 3:                                    # single-action model: one action per frame, shared by the slots
+            cp = cp.unsqueeze(2).expand(-1, -1, self.S, -1)
+            cv = cv.unsqueeze(2).expand(-1, -1, self.S, -1)
+        nxt = self.dyn.forward_single(slots=slots_win, action_protos=cp, action_vars=cv)[:, -1:]
+        img, (objs, masks) = self.savi.decode(nxt[:, 0])
+        return proto, var, nxt, img, objs, masks
+
+    @torch.no_grad()
+    def step(self, latent_action):
+        """ latent_action (B, A) [or (B, S, A) for the per-slot model] -> dict(pred_slots (B, 1, S, D), pred_img, pred_objs, pred_masks) """
+        assert self.slots is not None, "call reset(init_img) first"
+        # window bookkeeping as upstream: keep the last `ctx` frames of slots and of the action history (incl. the new action)
+        slots_win = self.slots[:, -self.ctx:]
+        keep = self.ctx - 1
+        protos_prev = torch.stack(self._protos[-keep:], dim=1) if (self._protos and keep > 0) else None
+        vars_prev = torch.stack(self._vars[-keep:], dim=1) if (self._vars and keep > 0) else None
+        # the reference crops slots and actions to the same length: frames and actions pair up from the newest backwards
+        Fr = slots_win.shape[1]
+        if protos_prev is not None and protos_prev.shape[1] > Fr - 1:
+            protos_prev, vars_prev = protos_prev[:, -(Fr - 1):] if Fr > 1 else None, vars_prev[:, -(Fr - 1):] if Fr > 1 else None
+        latent_action = latent_action.contiguous().float()
+        if not self.graphs_enabled:
+            proto, var, nxt, img, objs, masks = self._body(latent_action, slots_win.contiguous(), protos_prev, vars_prev)
+        else:
+            g = self._graphs.get(Fr)
+            if g is None:
+                g = self._capture(Fr, latent_action, slots_win, protos_prev, vars_prev)
+                self._graphs[Fr] = g
+            g["latent"].copy_(latent_action)
+            g["slots"].copy_(slots_win)
+            if protos_prev is not None:
+                g["protos"].copy_(protos_prev)
+                g["vars"].copy_(vars_prev)
+            g["graph"].replay()
+            proto, var, nxt, img, objs, masks = (t.clone() for t in g["out"])
+        self._protos.append(proto)
+        self._vars.append(var)
+        self.slots = torch.cat([self.slots, nxt], dim=1)
+        return {"pred_slots": nxt, "pred_img": img, "pred_objs": objs, "pred_masks": masks, "action_proto": proto, "action_var": var}
+
+    def _capture(self, Fr, latent, slots_win, protos_prev, vars_prev):
+        st = {"latent": latent.clone(), "slots": slots_win.contiguous().clone(),
+              "protos": None if protos_prev is None else protos_prev.clone(), "vars": None if vars_prev is None else vars_prev.clone()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._body(st["latent"], st["slots"], st["protos"], st["vars"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["out"] = self._body(st["latent"], st["slots"], st["protos"], st["vars"])
+        st["graph"] = graph
+        return st

@@ -775,3 +775,46 @@ def test_evaluate_rollout_metrics_on_device():
     tgt = video[:, ns:ns + npred].clamp(0, 1)
     ref = 10 * torch.log10(1.0 / (((imgs - tgt) ** 2).flatten(2).mean(-1) + 1e-8))
     check("psnr (device tail vs host)", ev["psnr"], ref, 1e-5)
+
+
+@pytest.mark.parametrize("exp", ["BlockPush", "GridShapes5Objs"])
+@pytest.mark.parametrize("graphs", [False, True])
+def test_closed_loop_matches_reference_golden(exp, graphs):
+    """ the latent-imagination loop of 11_evaluate_behavior_on_simulation.py:128-183 (SAVi on one frame ->
+    [policy -> decompose_action_latent -> enforce_window -> forward_single -> decode] x 11, the window slides) against the real
+    reference driven by the same deterministic stand-in policy; eager launches and one CUDA graph per window length """
+    from playslot_b200.pipeline import ClosedLoopStepper
+    fx = torch.load(os.path.join(GOLDEN_DIR, "closed_loop.pt"), weights_only=False)[exp]
+    ssd = synth_state_dict(fx["savi_manifest"], fx["weight_seed"])
+    psd = synth_state_dict(fx["predictor_manifest"], fx["weight_seed"] + 100)
+    savi = make_savi(fx["savi_cfg"], ssd, DEV)
+    pred = make_predictor(fx["predictor_name"], fx["predictor_cfg"], psd, DEV)
+    S, D, A = fx["savi_cfg"]["num_slots"], fx["savi_cfg"]["slot_dim"], fx["predictor_cfg"]["action_dim"]
+    B, steps = fx["B"], fx["steps"]
+    gen = torch.Generator().manual_seed(fx["input_seed"])
+    init_img = torch.rand(B, 3, 64, 64, generator=gen)
+    Wp = (torch.randn((S, D, A) if fx["per_slot"] else (D, A), generator=gen) / D ** 0.5).to(DEV)
+    from synth import synth_noise
+    init_noise = synth_noise((B, S, D), fx["weight_seed"] + 1) if fx["savi_cfg"]["initializer"] == "LearnedRandom" else None
+
+    def policy(slots_t):
+        if Wp.dim() == 3:
+            return torch.tanh(torch.einsum("bsd,sda->bsa", slots_t, Wp))
+        return torch.tanh(slots_t.mean(dim=1) @ Wp)
+
+    stepper = ClosedLoopStepper(savi, pred, B, graphs=graphs)
+    if init_noise is not None:
+        with FixedRandn(init_noise):
+            first = stepper.reset(init_img.to(DEV))
+    else:
+        first = stepper.reset(init_img.to(DEV))
+    check("first-frame reconstruction", first["recons_imgs"], fx["init_recon"])
+    imgs, last = [first["recons_imgs"]], None
+    for i in range(steps):
+        last = stepper.step(policy(stepper.slots[:, -1]))
+        imgs.append(last["pred_img"])
+    check("imagined slots (11 closed-loop steps)", stepper.slots, fx["pred_slots"])
+    check("action prototypes", torch.stack(stepper._protos, dim=1), fx["protos"])
+    check("action variability", torch.stack(stepper._vars, dim=1), fx["vars"], 1e-4 if fx["vars"].abs().max() > 0 else 1.0)
+    check("imagined frames (last 3)", torch.stack(imgs[-3:], dim=1), fx["imgs_last3"])
+    check("masks of the last frame", last["pred_masks"], fx["masks_last"])
