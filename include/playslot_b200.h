@@ -288,6 +288,33 @@ int ps_frame_sq_err(const float* pred, const float* target, float* out, long lon
 int ps_mse_bwd(const float* pred, const float* target, const float* g, float scale, float* d_pred, long long n_videos,
                int frames_per_video, long long elems, long long tgt_video_stride, long long tgt_frame_stride, void* stream);
 
+/* ---- SAVi training (src/02_train_savi.py:21-70): backward pieces of SlotAttention, encoder and decoder --------------------- */
+
+/* Attention core of one SlotAttention iteration (src/models/BlocksUtils/attention.py:97-110) on folded operands:
+ * A (B,S,128) = D^-1/2 * q W_k, xn (B,N,128) = norm_input(inputs)  ->  t (B,S,128) = sum_n w[s][n] xn[n] with
+ * a = softmax_s(A xn^T) + eps, w = a / sum_n a;  Z (B,S) = sum_n a;  masks (B,S,N) = a (or null).
+ * Workspaces: part_t (B, chunks, S, 128), part_z (B, chunks, S), part_dA (B, chunks, S, 128), chunks = ps_sa_core_chunks(N). */
+int ps_sa_core_chunks(int N);
+int ps_sa_core_fwd(const float* A, const float* xn, float* t, float* Z, float* masks, float* part_t, float* part_z,
+                   int B, int S, int N, float eps, void* stream);
+int ps_sa_core_bwd(const float* A, const float* xn, const float* t, const float* Z, const float* dt, float* dA, float* dxn,
+                   float* part_dA, int B, int S, int N, float eps, int accumulate, void* stream);
+/* element-wise part of nn.GRUCell (attention.py:112-115): gi = W_ih u + b_ih, gh = W_hh h + b_hh (M, 3D) -> h' (M, D); gates (M, 3D) saved */
+int ps_gru_gates_fwd(const float* gi, const float* gh, const float* h, float* hout, float* gates, long long M, int D, void* stream);
+int ps_gru_gates_bwd(const float* dhout, const float* gates, const float* gh, const float* h, float* dgi, float* dgh, float* dh,
+                     long long M, int D, void* stream);
+/* weight / bias gradients of the convolutions (ConvBlocks of encoders.py:46-104 / decoders.py:45-113) from the padded NHWC split
+ * planes the tcgen05 convolutions read and write; outputs accumulate (+=) and must be zeroed by the caller */
+int ps_conv5x5_planes_wgrad(const void* dy_planes, const void* x_planes, float* dW, int n_img, int H, int W, int dy_precision,
+                            int x_precision, float scale, void* stream);
+int ps_planes_colsum(const void* planes, float* out, int n_img, int H, int W, int precision, float scale, void* stream);
+int ps_conv_first_wgrad(const void* dh_planes, const float* x, const unsigned char* x8, float* dW, int n_img, int Cin, int H, int W,
+                        int ksize, int precision, float scale, void* stream);
+int ps_conv3x3_final_wgrad(const float* g_o, const float* h, float* dW, float* db, int n_img, int H, int W, void* stream);
+int ps_colsum(const float* X, float* out, long long M, long long N, float scale, void* stream);
+int ps_nhwc_to_split_scaled(const float* tokens, int ld, const float* scale, void* planes, int n_img, int H, int W, int precision,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,5 +111,55 @@ def main():
               f"{nz}/{len(grad_norms)} params with gradient, {len(grads_full)} stored in full, {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+SAVI_CASES = {
+    # name: (experiment, B, T, weight seed)   -- SAVi training step of src/02_train_savi.py:21-70
+    "savi_blockpush":   ("BlockPush",       2, 3, 61),
+    "savi_gridshapes5": ("GridShapes5Objs", 2, 2, 62),
+}
+
+
+def main_savi():
+    """ reference SAVi training step: model(videos) with decode, MSE(recons_imgs, videos), backward; stores the loss, the gradient
+    norm of every parameter and the full gradient of the small ones """
+    os.chdir(REF)
+    sys.path.insert(0, os.path.join(REF, "src"))
+    from lib.setup_model import setup_model
+    for name, (exp, B, T, wseed) in SAVI_CASES.items():
+        j = json.load(open(os.path.join(REF, "experiments", exp, "predictors", "PlaySlot", "experiment_params.json")))
+        scfg = copy.deepcopy(j["model"]["model_params"])
+        savi = setup_model(copy.deepcopy(j["model"])).train()
+        sman = {k: list(v.shape) for k, v in savi.state_dict().items()}
+        savi.load_state_dict(synth_state_dict(sman, wseed), strict=True)
+        H, W = scfg["encoder"]["encoder_params"]["resolution"]
+        S, D = scfg["num_slots"], scfg["slot_dim"]
+        video = synth_video(B, T, H, W, wseed)
+        init_noise = synth_noise((B, S, D), wseed + 1) if scfg["initializer"] == "LearnedRandom" else None
+        real_randn = torch.randn
+        if init_noise is not None:
+            torch.randn = lambda *a, **k: init_noise.clone()
+        try:
+            out = savi(video, num_imgs=T)
+        finally:
+            torch.randn = real_randn
+        loss = torch.nn.functional.mse_loss(out["recons_imgs"], video.clamp(0, 1))
+        loss.backward()
+        grad_norms, grads_full = {}, {}
+        for k, p_ in savi.named_parameters():
+            grad_norms[k] = None if p_.grad is None else float(p_.grad.double().norm())
+            if p_.grad is not None and p_.numel() <= 8192:
+                grads_full[k] = p_.grad.clone()
+        fx = {"case": name, "experiment": exp, "B": B, "T": T, "weight_seed": wseed, "savi_cfg": scfg, "savi_manifest": sman,
+              "loss": float(loss), "slot_history": out["slot_history"].detach().clone(),
+              "recon_last": out["recons_imgs"][:, -1].detach().clone(), "masks_last": out["masks"][:, -1].detach().clone(),
+              "grad_norms": grad_norms, "grads_full": grads_full}
+        path = os.path.join(REPO, "tests", "golden", f"train_{name}.pt")
+        torch.save(fx, path)
+        print(f"{name}: loss {float(loss):.6f}, {sum(1 for v in grad_norms.values() if v)}/{len(grad_norms)} params with gradient, "
+              f"{len(grads_full)} stored in full, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--savi" in sys.argv:
+        main_savi()
+    else:
+        main()

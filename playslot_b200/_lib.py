@@ -56,6 +56,17 @@ SIGNATURES = {
     "ps_dec_expand_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_dec_composite_tc": (c_i, [c_f, c_f, c_fl, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_nchw_to_split": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
+    "ps_sa_core_chunks": (c_i, [c_i]),
+    "ps_sa_core_fwd": (c_i, [c_f] * 7 + [c_i, c_i, c_i, c_fl, c_f]),
+    "ps_sa_core_bwd": (c_i, [c_f] * 8 + [c_i, c_i, c_i, c_fl, c_i, c_f]),
+    "ps_gru_gates_fwd": (c_i, [c_f] * 5 + [ctypes.c_longlong, c_i, c_f]),
+    "ps_gru_gates_bwd": (c_i, [c_f] * 7 + [ctypes.c_longlong, c_i, c_f]),
+    "ps_conv5x5_planes_wgrad": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
+    "ps_planes_colsum": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
+    "ps_conv_first_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
+    "ps_conv3x3_final_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "ps_colsum": (c_i, [c_f, c_f, ctypes.c_longlong, ctypes.c_longlong, c_fl, c_f]),
+    "ps_nhwc_to_split_scaled": (c_i, [c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_frame_sq_err": (c_i, [c_f, c_f, c_f, ctypes.c_longlong, c_i] + [ctypes.c_longlong] * 5 + [c_i, c_f]),
     "ps_mse_bwd": (c_i, [c_f, c_f, c_f, c_fl, c_f, ctypes.c_longlong, c_i, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_f]),
 }

@@ -114,6 +114,15 @@ class SlotAttention(nn.Module):
             x = None
         else:
             require_cuda(inputs, "SlotAttention")
+            if AG.needs_grad(inputs, slots, self.to_q.weight, self.norm_input.weight):
+                # SAVi training (02_train_savi.py): differentiable iterations (savi_autograd.slot_attention_train)
+                from ... import savi_autograd as SG
+                n_it = self.num_iters_first if step == 0 else self.num_iters
+                if n_it <= 0:
+                    return slots
+                out, masks = SG.slot_attention_train(self, f32c(inputs), f32c(slots), n_it)
+                self.attention_masks = masks
+                return out
             x = f32c(inputs)
             B, N, _ = x.shape
         no_grad_only("SlotAttention", slots, self.to_q.weight, *([] if x is None else [x]))

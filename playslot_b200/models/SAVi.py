@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .. import autograd as AG
 from ._common import DerivedWeights, require_cuda, no_grad_only, f32c
 from .BlocksUtils.attention import SlotAttention
 from .BlocksUtils.initializers import get_initializer
@@ -121,7 +122,8 @@ class SAVi(nn.Module):
         stacks of empty tensors, as in the reference (SAVi.py:135-204).
         """
         require_cuda(x, "SAVi.forward")
-        no_grad_only("SAVi.forward", x, self.slot_attention.to_q.weight)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(x, num_imgs, decode, **kwargs)          # SAVi training (02_train_savi.py:21-70)
         B = x.shape[0]
         predicted = self.initializer(batch_size=B, **kwargs)
         predicted = f32c(predicted.detach())
@@ -138,6 +140,37 @@ class SAVi(nn.Module):
             else:
                 feats = next(f[t - t0] for t0, _, f in feats_all if t0 <= t < t0 + f.shape[0])
             slots = self.slot_attention(inputs=feats, slots=predicted, step=t)
+            if decode:
+                recon, (recons, masks) = self.decode(slots)
+            else:
+                recon, recons, masks = torch.tensor([]), torch.tensor([]), torch.tensor([])
+            predicted = self.transition_module(slots)
+            slot_history.append(slots)
+            recons_h.append(recon)
+            objs_h.append(recons)
+            masks_h.append(masks)
+        return {
+            "recons_imgs": torch.stack(recons_h, dim=1),
+            "recons_objs": torch.stack(objs_h, dim=1),
+            "masks": torch.stack(masks_h, dim=1),
+            "slot_history": torch.stack(slot_history, dim=1),
+        }
+
+    def _forward_train(self, x, num_imgs, decode, **kwargs):
+        """ differentiable forward (every parameter receives a gradient): same recurrence as `forward`, composed from the
+        autograd front-ends in playslot_b200.autograd / savi_autograd (fp32 feature tokens instead of the fused plane hand-over) """
+        from .. import savi_autograd as SG
+        B, _, C, H, W = x.shape
+        N = H * W
+        predicted = self.initializer(batch_size=B, **kwargs).float()
+        frames = x[:, :num_imgs].transpose(0, 1).reshape(num_imgs * B, C, H, W)
+        tokens = SG.encoder_tokens_train(self, frames)                                # (T*B, N, C)
+        ln, fc1, fc2 = self.encoder_mlp[0], self.encoder_mlp[1], self.encoder_mlp[3]
+        hdn = AG.linear(tokens, fc1.weight, fc1.bias, ln=(ln.weight, ln.bias, ln.eps), act=ops.ACT_RELU)
+        feats = AG.linear(hdn, fc2.weight, fc2.bias).view(num_imgs, B, N, -1)
+        slot_history, recons_h, objs_h, masks_h = [], [], [], []
+        for t in range(num_imgs):
+            slots = self.slot_attention(inputs=feats[t], slots=predicted, step=t)
             if decode:
                 recon, (recons, masks) = self.decode(slots)
             else:
@@ -349,10 +382,14 @@ class SAVi(nn.Module):
         (SAVi.py:220-234).  Differentiable w.r.t. `slots` (data gradient only: the training script keeps SAVi frozen).
         """
         require_cuda(slots, "SAVi.decode")
+        if torch.is_grad_enabled() and (self.decoder.final_conv().weight.requires_grad
+                                        or self.decoder_pos_embedding.projection.weight.requires_grad):
+            # SAVi training: gradients w.r.t. the slots and the decoder's parameters
+            from .. import savi_autograd as SG
+            recon, recons, masks = SG.decode_train(self, slots)
+            return recon, (recons, masks)
         if torch.is_grad_enabled() and slots.requires_grad:
-            no_grad_only("SAVi.decode (decoder weight gradients; SAVi training is not part of this path)",
-                         self.decoder.final_conv().weight, self.decoder_pos_embedding.projection.weight)
-            recon, recons, masks = _DecodeFn.apply(f32c(slots), self)
+            recon, recons, masks = _DecodeFn.apply(f32c(slots), self)         # predictor training: frozen decoder, data gradient
             return recon, (recons, masks)
         recon, recons, masks, _ = self._decode_impl(f32c(slots.detach()), keep=False)
         return recon, (recons, masks)
@@ -420,10 +457,11 @@ class SAVi(nn.Module):
         prec = ops.TC_PRECISION[self.conv_mode]
         cache = self._tc_w.setdefault((id(block), prec, "flip"), DerivedWeights())
         w = block.conv.weight
-        return cache.get([w], lambda: ops.pack_conv_weight_tc(w.detach().flip(2, 3).transpose(0, 1).contiguous(), prec))
+        return cache.get([w], lambda: ops.pack_conv_weight_tc(self._pad64(w.detach()).flip(2, 3).transpose(0, 1).contiguous(), prec))
 
-    def _decode_backward(self, saved, recons, masks, g_recon, g_recons, g_masks):
-        """ d loss / d slots through compositing, the 3x3 and the three 5x5 convolutions and the collapsed first one """
+    def _decode_backward(self, saved, recons, masks, g_recon, g_recons, g_masks, weight_grads=False, slots=None):
+        """ d loss / d slots through compositing, the 3x3 and the three 5x5 convolutions and the collapsed first one; with
+        weight_grads also the gradients of every decoder parameter (returned as (d_slots, dict)) """
         M, S = recons.shape[:2]
         H, W = self.decoder_resolution
         blocks = self.decoder.conv_blocks()
@@ -435,6 +473,12 @@ class SAVi(nn.Module):
         prec = ops.TC_PRECISION[self.conv_mode]
         cg = lambda g, m0, m1: None if g is None else f32c(g[m0:m1])
         out = torch.empty(M, S, self.slot_dim, device=recons.device, dtype=torch.float32)
+        wg = None
+        if weight_grads:
+            dev = recons.device
+            wg = {"wsum": torch.zeros_like(wsum), "P_hwc": torch.zeros(H * W, 64, device=dev),
+                  "conv": [[torch.zeros(64, 64, 5, 5, device=dev), torch.zeros(64, device=dev)] for _ in range(3)],
+                  "final": [torch.zeros(4, 64, 3, 3, device=dev), torch.zeros(4, device=dev)]}
         for m0, m1, acts, h in saved:
             n_img = (m1 - m0) * S
             g_o = ops.dec_composite_bwd(f32c(recons[m0:m1]), f32c(masks[m0:m1]), cg(g_recon, m0, m1), cg(g_recons, m0, m1), cg(g_masks, m0, m1))
@@ -445,13 +489,36 @@ class SAVi(nn.Module):
             amax = g_o.abs().max().clamp_min(1e-30)
             g_scale = torch.exp2(-torch.floor(torch.log2(amax))).reshape(1)
             ops.dec_final_dgrad(g_o, wfin, h, ga, prec, g_scale)                                   # through conv3x3 and relu(h4)
+            inv = 1.0 / g_scale
+            if wg is not None:
+                dwf, dbf = ops.conv3x3_final_wgrad(g_o, h)
+                wg["final"][0] += dwf; wg["final"][1] += dbf
+                wg["conv"][2][0] += ops.conv5x5_planes_wgrad(ga, acts[2], n_img, H, W, prec, prec) * inv     # block 3: h3 -> h4
+                wg["conv"][2][1] += ops.planes_colsum(ga, n_img, H, W, prec) * inv
             ops.conv5x5_tc_dgrad(ga, self._tc_weight_flipped(blocks[3]), acts[2], n_img, H, W, prec, act_out=gb)
+            if wg is not None:
+                wg["conv"][1][0] += ops.conv5x5_planes_wgrad(gb, acts[1], n_img, H, W, prec, prec) * inv     # block 2: h2 -> h3
+                wg["conv"][1][1] += ops.planes_colsum(gb, n_img, H, W, prec) * inv
             ops.conv5x5_tc_dgrad(gb, self._tc_weight_flipped(blocks[2]), acts[1], n_img, H, W, prec, act_out=ga)
+            if wg is not None:
+                wg["conv"][0][0] += ops.conv5x5_planes_wgrad(ga, acts[0], n_img, H, W, prec, prec) * inv     # block 1: h1 -> h2
+                wg["conv"][0][1] += ops.planes_colsum(ga, n_img, H, W, prec) * inv
             tokens = torch.empty(n_img, H * W, 64, device=recons.device, dtype=torch.float32)
             ops.conv5x5_tc_dgrad(ga, self._tc_weight_flipped(blocks[1]), acts[0], n_img, H, W, prec, out_tokens=tokens)
             dG = ops.dec_expand_bwd(tokens, n_img, H, W, k, g_scale)
             out[m0:m1] = ops.linear(dG, wsum_t, mode="fp32").view(m1 - m0, S, self.slot_dim)
-        return out
+            if wg is not None:
+                # collapsed first convolution: G = slots @ wsum^T (+ P broadcast): d wsum = dG^T slots, d P = sum over images of d h1
+                dws, _ = ops.linear_wgrad(dG, f32c(slots[m0:m1].reshape(n_img, self.slot_dim)), want_bias=False)
+                wg["wsum"] += dws
+                wg["P_hwc"] += ops.colsum(tokens.view(n_img, H * W * 64)).view(H * W, 64) * inv
+        if wg is None:
+            return out
+        params = []
+        for dw, db in wg["conv"]:
+            params += [dw, db]
+        params += wg["final"]
+        return out, {"wsum": wg["wsum"], "P_hwc": wg["P_hwc"], "params": params}
 
     def _final_packed(self, conv):
         if not hasattr(self, "_fin_cache"):

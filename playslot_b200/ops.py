@@ -854,3 +854,130 @@ def mse_bwd(pred, target, g, scale):
         st = lib.ps_mse_bwd(_ptr(pred), _ptr(target), _ptr(g), float(scale), _ptr(d), B, Fr, elems, tv, tf, _stream())
     _lib.check(st, "ps_mse_bwd")
     return d
+
+
+# ------------------------------------------------------------------------------------------------ SAVi training kernels
+
+def sa_core_fwd(A, xn, eps, want_masks=True):
+    """ A (B,S,128) folded queries, xn (B,N,128) normalised features -> (t (B,S,128), Z (B,S), masks (B,S,N) or None) """
+    lib = _lib.load()
+    _req(A, "A"); _req(xn, "xn")
+    B, S, D = A.shape
+    N = xn.shape[1]
+    assert D == 128 and xn.shape == (B, N, 128), "sa_core: 128 features"
+    ch = int(lib.ps_sa_core_chunks(N))
+    dev = A.device
+    t = torch.empty(B, S, D, device=dev, dtype=torch.float32)
+    Z = torch.empty(B, S, device=dev, dtype=torch.float32)
+    masks = torch.empty(B, S, N, device=dev, dtype=torch.float32) if want_masks else None
+    pt = torch.empty(B, ch, S, D, device=dev, dtype=torch.float32)
+    pz = torch.empty(B, ch, S, device=dev, dtype=torch.float32)
+    with _timed("sa_core_fwd"):
+        st = lib.ps_sa_core_fwd(_ptr(A), _ptr(xn), _ptr(t), _ptr(Z), _ptr(masks), _ptr(pt), _ptr(pz), B, S, N, float(eps), _stream())
+    _lib.check(st, "ps_sa_core_fwd")
+    return t, Z, masks
+
+
+def sa_core_bwd(A, xn, t, Z, dt, eps, dxn=None):
+    """ -> (dA (B,S,128), dxn (B,N,128)); with `dxn` given the feature gradient is accumulated into it """
+    lib = _lib.load()
+    B, S, D = A.shape
+    N = xn.shape[1]
+    ch = int(lib.ps_sa_core_chunks(N))
+    dev = A.device
+    dA = torch.empty(B, S, D, device=dev, dtype=torch.float32)
+    acc = dxn is not None
+    if dxn is None:
+        dxn = torch.empty_like(xn)
+    pd = torch.empty(B, ch, S, D, device=dev, dtype=torch.float32)
+    with _timed("sa_core_bwd"):
+        st = lib.ps_sa_core_bwd(_ptr(A), _ptr(xn), _ptr(t), _ptr(Z), _ptr(_req(dt, "dt")), _ptr(dA), _ptr(dxn), _ptr(pd), B, S, N, float(eps),
+                                int(acc), _stream())
+    _lib.check(st, "ps_sa_core_bwd")
+    return dA, dxn
+
+
+def gru_gates_fwd(gi, gh, h):
+    lib = _lib.load()
+    _req(gi, "gi"); _req(gh, "gh"); _req(h, "h")
+    D = h.shape[-1]
+    M = h.numel() // D
+    out = torch.empty_like(h)
+    gates = torch.empty_like(gi)
+    st = lib.ps_gru_gates_fwd(_ptr(gi), _ptr(gh), _ptr(h), _ptr(out), _ptr(gates), M, D, _stream())
+    _lib.check(st, "ps_gru_gates_fwd")
+    return out, gates
+
+
+def gru_gates_bwd(dhout, gates, gh, h):
+    lib = _lib.load()
+    D = h.shape[-1]
+    M = h.numel() // D
+    dgi, dgh, dh = torch.empty_like(gates), torch.empty_like(gates), torch.empty_like(h)
+    st = lib.ps_gru_gates_bwd(_ptr(_req(dhout, "dhout")), _ptr(gates), _ptr(gh), _ptr(h), _ptr(dgi), _ptr(dgh), _ptr(dh), M, D, _stream())
+    _lib.check(st, "ps_gru_gates_bwd")
+    return dgi, dgh, dh
+
+
+def conv5x5_planes_wgrad(dy_planes, x_planes, n_img, H, W, dy_precision, x_precision, scale=1.0):
+    """ -> dW (64 cout, 64 cin, 5, 5) = scale * correlation of the gradient planes with the activation planes """
+    lib = _lib.load()
+    dW = torch.zeros(25, 64, 64, device=dy_planes.device, dtype=torch.float32)
+    with _timed("conv5x5_wgrad", (n_img, 64, 64, H, W, 5)):
+        st = lib.ps_conv5x5_planes_wgrad(_ptr(dy_planes), _ptr(x_planes), _ptr(dW), n_img, H, W, int(dy_precision), int(x_precision),
+                                         float(scale), _stream())
+    _lib.check(st, "ps_conv5x5_planes_wgrad")
+    return dW.view(5, 5, 64, 64).permute(2, 3, 0, 1).contiguous()
+
+
+def planes_colsum(planes, n_img, H, W, precision, scale=1.0):
+    lib = _lib.load()
+    out = torch.zeros(64, device=planes.device, dtype=torch.float32)
+    st = lib.ps_planes_colsum(_ptr(planes), _ptr(out), n_img, H, W, int(precision), float(scale), _stream())
+    _lib.check(st, "ps_planes_colsum")
+    return out
+
+
+def conv_first_wgrad(dh_planes, x, n_img, H, W, ksize, precision, scale=1.0):
+    """ x (n, Cin, H, W) fp32 or uint8 -> dW (64, Cin, k, k) """
+    lib = _lib.load()
+    Cin = x.shape[1]
+    dW = torch.zeros(64, Cin, ksize, ksize, device=x.device, dtype=torch.float32)
+    u8 = x.dtype == torch.uint8
+    st = lib.ps_conv_first_wgrad(_ptr(dh_planes), None if u8 else _ptr(x), _ptr(x) if u8 else None, _ptr(dW), n_img, Cin, H, W, ksize,
+                                 int(precision), float(scale), _stream())
+    _lib.check(st, "ps_conv_first_wgrad")
+    return dW
+
+
+def conv3x3_final_wgrad(g_o, h):
+    """ g_o (n, 4, H, W), h (n, 64, H, W) -> (dW (4, 64, 3, 3), db (4,)) """
+    lib = _lib.load()
+    _req(g_o, "g_o"); _req(h, "h")
+    n, _, H, W = h.shape
+    dW = torch.zeros(4, 64, 3, 3, device=h.device, dtype=torch.float32)
+    db = torch.zeros(4, device=h.device, dtype=torch.float32)
+    with _timed("conv3x3_final_wgrad"):
+        st = lib.ps_conv3x3_final_wgrad(_ptr(g_o), _ptr(h), _ptr(dW), _ptr(db), n, H, W, _stream())
+    _lib.check(st, "ps_conv3x3_final_wgrad")
+    return dW, db
+
+
+def colsum(x2d, scale=1.0):
+    """ (M, N) -> (N,) column sums times scale """
+    lib = _lib.load()
+    _req(x2d, "x")
+    M, N = x2d.shape
+    out = torch.empty(N, device=x2d.device, dtype=torch.float32)
+    st = lib.ps_colsum(_ptr(x2d), _ptr(out), M, N, float(scale), _stream())
+    _lib.check(st, "ps_colsum")
+    return out
+
+
+def nhwc_to_split_scaled(tokens, planes, n_img, H, W, precision, scale=None):
+    """ tokens (n_img, H*W, ld >= 64) fp32 * scale[0] -> padded split planes (pre-zeroed borders) """
+    lib = _lib.load()
+    _req(tokens, "tokens")
+    st = lib.ps_nhwc_to_split_scaled(_ptr(tokens), tokens.shape[-1], _ptr(scale), _ptr(planes), n_img, H, W, int(precision), _stream())
+    _lib.check(st, "ps_nhwc_to_split_scaled")
+    return planes

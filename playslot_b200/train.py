@@ -264,3 +264,32 @@ class GraphedTrainStep:
         from . import ops
         ops.bump_weight_generation()
         return self.loss, self.terms
+
+
+# ------------------------------------------------------------------------------------------------ SAVi training (02_train_savi.py)
+
+def savi_forward_loss(savi, videos, **init_kwargs):
+    """ `Trainer.forward_loss_metric` of src/02_train_savi.py:21-70: model(videos) with decode, MSE(recons_imgs, videos.clamp(0, 1)) """
+    from . import autograd as AG
+    out = savi(videos, num_imgs=videos.shape[1], **init_kwargs)
+    target = videos if videos.dtype == torch.float32 else videos.float().div(255)
+    loss = AG.mse_loss(out["recons_imgs"], target.clamp(0, 1))
+    return loss, out
+
+
+def savi_train_step(savi, optimizer, videos, bucket=None, clip_gradient=0.05, **init_kwargs):
+    """ one optimisation step of the decomposition model on this rank's shard (gradient all-reduce through `bucket` when
+    torch.distributed is initialised), as base/baseTrainer.py drives 02_train_savi.py; returns (loss value tensor, model output) """
+    savi.train()
+    if bucket is not None:
+        bucket.attach()
+    else:
+        optimizer.zero_grad(set_to_none=True)
+    loss, out = savi_forward_loss(savi, videos, **init_kwargs)
+    loss.backward()
+    if bucket is not None:
+        bucket.all_reduce_mean(local_count=videos.shape[0])
+    if clip_gradient is not None:
+        torch.nn.utils.clip_grad_norm_(savi.parameters(), clip_gradient)
+    optimizer.step()
+    return loss.detach(), out
