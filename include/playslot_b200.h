@@ -307,6 +307,10 @@ int ps_gru_gates_bwd(const float* dhout, const float* gates, const float* gh, co
  * planes the tcgen05 convolutions read and write; outputs accumulate (+=) and must be zeroed by the caller */
 int ps_conv5x5_planes_wgrad(const void* dy_planes, const void* x_planes, float* dW, int n_img, int H, int W, int dy_precision,
                             int x_precision, float scale, void* stream);
+/* the same on tcgen05 (both tensors precision 3 = fp16 hi + lo planes; images up to 68 pixels wide): MN-major operands straight
+ * from the position-major planes, TMEM accumulation over a chunk of positions, 7 tap groups x position chunks */
+int ps_conv5x5_planes_wgrad_tc(const void* dy_planes, const void* x_planes, float* dW, int n_img, int H, int W, int precision,
+                               float scale, void* stream);
 int ps_planes_colsum(const void* planes, float* out, int n_img, int H, int W, int precision, float scale, void* stream);
 int ps_conv_first_wgrad(const void* dh_planes, const float* x, const unsigned char* x8, float* dW, int n_img, int Cin, int H, int W,
                         int ksize, int precision, float scale, void* stream);

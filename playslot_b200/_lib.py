@@ -62,6 +62,7 @@ SIGNATURES = {
     "ps_gru_gates_fwd": (c_i, [c_f] * 5 + [ctypes.c_longlong, c_i, c_f]),
     "ps_gru_gates_bwd": (c_i, [c_f] * 7 + [ctypes.c_longlong, c_i, c_f]),
     "ps_conv5x5_planes_wgrad": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
+    "ps_conv5x5_planes_wgrad_tc": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "ps_planes_colsum": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "ps_conv_first_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "ps_conv3x3_final_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f]),

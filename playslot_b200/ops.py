@@ -919,10 +919,19 @@ def gru_gates_bwd(dhout, gates, gh, h):
     return dgi, dgh, dh
 
 
-def conv5x5_planes_wgrad(dy_planes, x_planes, n_img, H, W, dy_precision, x_precision, scale=1.0):
+WGRAD_IMPL = os.environ.get("PLAYSLOT_WGRAD_IMPL", "tc")      # "tc": tcgen05 kernel where it applies; "ffma": CUDA-core kernel
+
+
+def conv5x5_planes_wgrad(dy_planes, x_planes, n_img, H, W, dy_precision, x_precision, scale=1.0, impl=None):
     """ -> dW (64 cout, 64 cin, 5, 5) = scale * correlation of the gradient planes with the activation planes """
     lib = _lib.load()
     dW = torch.zeros(25, 64, 64, device=dy_planes.device, dtype=torch.float32)
+    impl = impl or WGRAD_IMPL
+    if impl == "tc" and dy_precision == 3 and x_precision == 3 and W <= 68:
+        with _timed("conv5x5_wgrad_tc", (n_img, 64, 64, H, W, 5)):
+            st = lib.ps_conv5x5_planes_wgrad_tc(_ptr(dy_planes), _ptr(x_planes), _ptr(dW), n_img, H, W, 3, float(scale), _stream())
+        _lib.check(st, "ps_conv5x5_planes_wgrad_tc")
+        return dW.view(5, 5, 64, 64).permute(2, 3, 0, 1).contiguous()
     with _timed("conv5x5_wgrad", (n_img, 64, 64, H, W, 5)):
         st = lib.ps_conv5x5_planes_wgrad(_ptr(dy_planes), _ptr(x_planes), _ptr(dW), n_img, H, W, int(dy_precision), int(x_precision),
                                          float(scale), _stream())

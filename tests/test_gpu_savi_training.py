@@ -91,12 +91,14 @@ def test_conv_weight_gradients(n, H, W):
     x = F.relu(g(n, 64, H, W, seed=1))
     dy = g(n, 64, H, W, seed=2)
     xp, dyp = _to_planes(x), _to_planes(dy)
-    dW = ops.conv5x5_planes_wgrad(dyp, xp, n, H, W, 3, 3)
+    dW = ops.conv5x5_planes_wgrad(dyp, xp, n, H, W, 3, 3, impl="ffma")
+    dW_tc = ops.conv5x5_planes_wgrad(dyp, xp, n, H, W, 3, 3, impl="tc")
     db = ops.planes_colsum(dyp, n, H, W, 3)
     w = torch.zeros(64, 64, 5, 5, dtype=torch.float64, requires_grad=True)
     b = torch.zeros(64, dtype=torch.float64, requires_grad=True)
     (F.conv2d(x.double(), w, b, padding=2) * dy.double()).sum().backward()
     check("dW 5x5", dW, w.grad.float(), 2e-5)
+    check("dW 5x5 (tcgen05)", dW_tc, w.grad.float(), 2e-5)
     check("db", db, b.grad.float(), 2e-5)
     # first convolution, fp32 and uint8 images
     img = torch.rand(n, 3, H, W, generator=torch.Generator().manual_seed(3))
