@@ -275,6 +275,26 @@ int ps_dec_expand_bwd(const float* g_tokens, float* dG, const float* g_scale, in
 int ps_vq_lookup(const float* z, const float* codebook, float* proto_out, float* zq_out, long long* idx_out,
                  float* loss_out, int n, int A, int K, void* stream);
 
+/* ---- fused transformer stack --------------------------------------------------------------------------- */
+
+/* X (n_seq * L, 128) fp32, in place: n_layers pre-LN blocks  y = x + MHSA(LN(x)) W_o^T + b_o;  x = y + W_2 GELU(W_1 LN(y) + b_1) + b_2
+ * in ONE launch (4-CTA clusters, tcgen05, activations on chip).  Replaces the per-block chains of TransformerDecoder /
+ * TransformerEncoderBlock (src/models/BlocksUtils/attention.py:425-565, MetaAttention :204-316, model_blocks.MLP :278-309) as
+ * stacked by the cOCVP predictor (Predictors/DynamicsModels.py:457-516) and SAVi's transition module (transition_models.py:19-53),
+ * for embed_dim 128, 4 or 8 heads of width <= 64, MLP hidden 512, <= 128 tokens per sequence.  spf > 0: block-causal mask over
+ * frames of spf tokens (model_utils.py:115-124).  Weight packing: see csrc/tblock_tc.cu / ops.pack_tblock_stack. */
+int ps_tblock_stack(float* X, int n_seq, int L, int spf, int n_layers, int heads, float qscale, float eps1, float eps2,
+                    const void* WA, const void* WB, const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b,
+                    const float* b_o, const float* b1, const float* b2, const float* inv_scale, float* workspace, void* stream);
+/* floats of scratch (the clusters' partial sums travel through L2) ps_tblock_stack needs for n_seq sequences of L tokens */
+long long ps_tblock_stack_workspace_floats(int n_seq, int L);
+
+/* development variant: dbg (device, >= 4096 u64) receives %globaltimer stamps of CTA 0 at the phase boundaries of its row warps */
+int ps_tblock_stack_dbg(float* X, int n_seq, int L, int spf, int n_layers, int heads, float qscale, float eps1, float eps2,
+                        const void* WA, const void* WB, const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b,
+                        const float* b_o, const float* b1, const float* b2, const float* inv_scale, float* workspace,
+                        unsigned long long* dbg, void* stream);
+
 /* ---- fused loss / metric tail ------------------------------------------------------------------------- */
 
 /* out[f] = sum_e (pred[f][e] - target[f][e])^2 per frame (optionally both clamped to [0, 1]), one pass, deterministic.

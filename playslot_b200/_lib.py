@@ -68,6 +68,9 @@ SIGNATURES = {
     "ps_conv3x3_final_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "ps_colsum": (c_i, [c_f, c_f, ctypes.c_longlong, ctypes.c_longlong, c_fl, c_f]),
     "ps_nhwc_to_split_scaled": (c_i, [c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
+    "ps_tblock_stack": (c_i, [c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_fl] + [c_f] * 10 + [c_f, c_f]),
+    "ps_tblock_stack_workspace_floats": (ctypes.c_longlong, [c_i, c_i]),
+    "ps_tblock_stack_dbg": (c_i, [c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_fl] + [c_f] * 10 + [c_f, c_f, c_f]),
     "ps_frame_sq_err": (c_i, [c_f, c_f, c_f, ctypes.c_longlong, c_i] + [ctypes.c_longlong] * 5 + [c_i, c_f]),
     "ps_mse_bwd": (c_i, [c_f, c_f, c_f, c_fl, c_f, ctypes.c_longlong, c_i, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_f]),
 }

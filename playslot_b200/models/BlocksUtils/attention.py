@@ -334,6 +334,22 @@ class MultiHeadCrossAttention(MetaAttention):
 # TRANSFORMER BLOCKS #
 ######################
 
+def run_block_stack(blocks, x, slots_per_frame=0, cache=None):
+    """ x (B, L, E) through a list of pre-LN blocks.  Inference with embed_dim 128 / MLP 512 / <= 128 tokens: ONE fused launch for
+    the whole stack (csrc/tblock_tc.cu, 4-CTA clusters, activations on chip); otherwise block by block (4-5 launches each).
+    `cache`: a DerivedWeights holding the packed operands of the stack """
+    blocks = list(blocks)
+    B, L, E = x.shape
+    params = [p for b in blocks for p in b.parameters()]
+    if ops.tblock_stack_applicable(blocks, L) and not AG.needs_grad(x, *params):
+        cache = cache if cache is not None else blocks[0].__dict__.setdefault("_stack_cache", DerivedWeights())
+        pack = cache.get(params, lambda: ops.pack_tblock_stack(blocks))
+        return ops.tblock_stack(x.reshape(B * L, E), pack, B, L, slots_per_frame).view(B, L, E)
+    for blk in blocks:
+        x = blk.run(x, slots_per_frame=slots_per_frame)
+    return x
+
+
 class TransformerBlock(nn.Module):
     """ Common base (attention.py:380-421): owns `ln_mlp` (eps 1e-6) and `mlp` """
 
@@ -374,7 +390,7 @@ class TransformerEncoderBlock(TransformerBlock):
         assert inputs.ndim == 3
         require_cuda(inputs, "TransformerEncoderBlock")
         x = f32c(inputs)
-        return self.run(x, self.attn.spf_of(mask, x.shape[1]))
+        return run_block_stack([self], x, self.attn.spf_of(mask, x.shape[1]))
 
 
 class TransformerDecoder(TransformerBlock):
@@ -403,4 +419,4 @@ class TransformerDecoder(TransformerBlock):
         require_cuda(queries, "TransformerDecoder")
         x = f32c(queries)
         spf = slots_per_frame if slots_per_frame is not None else self.attn.spf_of(self_attn_mask, x.shape[1])
-        return self.run(x, spf)
+        return run_block_stack([self], x, spf)

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from ... import autograd as AG
 from .._common import DerivedWeights, require_cuda, f32c
-from ..BlocksUtils.attention import TransformerDecoder
+from ..BlocksUtils.attention import TransformerDecoder, run_block_stack
 from ..BlocksUtils.model_blocks import SlotPositionalEncoding
 from ..BlocksUtils.model_utils import build_slot_causal_mask
 
@@ -159,8 +159,7 @@ class MarkovTransformerDynamicsModel(BaseSlotDynamicsModel):
         slots, action_protos, action_vars = self._check_inputs(slots, action_protos, action_vars)
         B, Fr, S, D = slots.shape
         t = self._embed(slots, action_protos, action_vars).view(B * Fr, S, -1)
-        for blk in self.dynamics_model:
-            t = blk.run(t)
+        t = run_block_stack(self.dynamics_model, t)
         out = self._head(t).view(B, Fr, S, D)
         return out + slots if self.residual else out
 
@@ -221,8 +220,7 @@ class SlotGPTDymamicsModel(BaseSlotDynamicsModel):
             # (B, F, S, E) tensor, device RNG, like the reference on CUDA
             t = self.pos_emb.dropout(t.view(B, Fr, S, -1))
         t = t.reshape(B, Fr * S, -1)
-        for blk in self.dynamics_model:
-            t = blk.run(t, slots_per_frame=S)
+        t = run_block_stack(self.dynamics_model, t, slots_per_frame=S)     # one fused launch for the L layers when applicable
         out = self._head(t).view(B, Fr, S, D)
         return out + slots if self.residual else out
 

@@ -990,3 +990,91 @@ def nhwc_to_split_scaled(tokens, planes, n_img, H, W, precision, scale=None):
     st = lib.ps_nhwc_to_split_scaled(_ptr(tokens), tokens.shape[-1], _ptr(scale), _ptr(planes), n_img, H, W, int(precision), _stream())
     _lib.check(st, "ps_nhwc_to_split_scaled")
     return planes
+
+
+# ------------------------------------------------------------------------------------------------ fused transformer stack
+
+FUSED_TBLOCK = os.environ.get("PLAYSLOT_FUSED_TBLOCK", "1") != "0"
+
+
+def _pow2_scale_of(t):
+    amax = float(t.abs().max())
+    return 1.0 if amax == 0.0 else 2.0 ** (-round(math.log2(amax)))
+
+
+def _split_fp16(w):
+    h = w.to(torch.float16)
+    lo = ((w - h.float()) * TC_LO_SCALE).to(torch.float16)
+    return torch.stack([h, lo], dim=0)
+
+
+def tblock_stack_applicable(blocks, L):
+    """ can this list of pre-LN transformer blocks run as ONE fused launch (csrc/tblock_tc.cu)? """
+    if not FUSED_TBLOCK or _LINEAR_MODE != "fp16x3" or not blocks or L > 128:
+        return False
+    b0 = blocks[0]
+    for b in blocks:
+        a = b.attn
+        if (b.embed_dim != 128 or b.mlp_size != 512 or a.num_heads not in (4, 8) or a.head_dim > 64 or a.num_heads != b0.attn.num_heads
+                or a.head_dim != b0.attn.head_dim or getattr(b, "use_cross_attn", False) or b.mlp._act != ACT_GELU
+                or (not a.has_out_proj() and a.inner_dim != 128)):
+            return False
+    return True
+
+
+def pack_tblock_stack(blocks):
+    """ packed operands of ps_tblock_stack for a list of blocks (attention.py TransformerEncoderBlock / TransformerDecoder mirrors) """
+    a0 = blocks[0].attn
+    H, dh = a0.num_heads, a0.head_dim
+    dev = a0.q.weight.device
+    WA, WB, inv, vecs = [], [], [], {k: [] for k in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "b_o", "b1", "b2")}
+    for b in blocks:
+        a = b.attn
+        q, k, v = a.q.weight.detach().float(), a.k.weight.detach().float(), a.v.weight.detach().float()       # (H*dh, 128)
+        fc1, fc2 = b.mlp.mlp[0], b.mlp.mlp[2]
+        if a.has_out_proj():
+            wo, bo = a.out_proj[0].weight.detach().float(), a.out_proj[0].bias.detach().float()             # (128, H*dh)
+        else:
+            wo, bo = torch.eye(128, device=dev), torch.zeros(128, device=dev)                                   # heads are concatenated
+        s_qkv = _pow2_scale_of(torch.cat([q, k, v]))
+        s_1, s_o, s_2 = _pow2_scale_of(fc1.weight.detach()), _pow2_scale_of(wo), _pow2_scale_of(fc2.weight.detach())
+        rows = []
+        for h in range(H):
+            for w in (q, k, v):
+                blk = torch.zeros(64, 128, device=dev)
+                blk[:dh] = w[h * dh:(h + 1) * dh] * s_qkv
+                rows.append(blk)
+        rows.append(fc1.weight.detach().float() * s_1)
+        WA.append(_split_fp16(torch.cat(rows, dim=0)))                                                        # (2, H*192 + 512, 128)
+        cols = []
+        for h in range(H):
+            blk = torch.zeros(128, 64, device=dev)
+            blk[:, :dh] = wo[:, h * dh:(h + 1) * dh] * s_o
+            cols.append(blk)
+        cols.append(fc2.weight.detach().float() * s_2)
+        WB.append(_split_fp16(torch.cat(cols, dim=1)))                                                        # (2, 128, H*64 + 512)
+        inv.append(torch.tensor([1.0 / s_qkv, 1.0 / s_1, 1.0 / s_o, 1.0 / s_2], device=dev))
+        vecs["ln1_g"].append(b.ln_att.weight.detach().float()); vecs["ln1_b"].append(b.ln_att.bias.detach().float())
+        vecs["ln2_g"].append(b.ln_mlp.weight.detach().float()); vecs["ln2_b"].append(b.ln_mlp.bias.detach().float())
+        vecs["b_o"].append(bo); vecs["b1"].append(fc1.bias.detach().float()); vecs["b2"].append(fc2.bias.detach().float())
+    out = {k: torch.stack(v).contiguous() for k, v in vecs.items()}
+    out.update(WA=torch.stack(WA).view(torch.int16).contiguous(), WB=torch.stack(WB).view(torch.int16).contiguous(),
+               inv_scale=torch.stack(inv).contiguous(), heads=H, qscale=dh ** -0.5, n_layers=len(blocks),
+               eps1=blocks[0].ln_att.eps, eps2=blocks[0].ln_mlp.eps)
+    return out
+
+
+def tblock_stack(x, pack, n_seq, L, spf):
+    """ x (n_seq * L, 128) -> the stack's output (new tensor) """
+    lib = _lib.load()
+    _req(x, "x")
+    assert x.numel() == n_seq * L * 128
+    y = x.clone()
+    ws = torch.empty(int(lib.ps_tblock_stack_workspace_floats(int(n_seq), int(L))), device=x.device, dtype=torch.float32)
+    with _timed("tblock_stack", (n_seq, L, pack["n_layers"])):
+        st = lib.ps_tblock_stack(_ptr(y), int(n_seq), int(L), int(spf), pack["n_layers"], pack["heads"], float(pack["qscale"]),
+                                 float(pack["eps1"]), float(pack["eps2"]), _ptr(pack["WA"]), _ptr(pack["WB"]), _ptr(pack["ln1_g"]),
+                                 _ptr(pack["ln1_b"]), _ptr(pack["ln2_g"]), _ptr(pack["ln2_b"]), _ptr(pack["b_o"]), _ptr(pack["b1"]),
+                                 _ptr(pack["b2"]), _ptr(pack["inv_scale"]), _ptr(ws), _stream())
+    _lib.check(st, "ps_tblock_stack")
+    return y

@@ -818,3 +818,42 @@ def test_closed_loop_matches_reference_golden(exp, graphs):
     check("action variability", torch.stack(stepper._vars, dim=1), fx["vars"], 1e-4 if fx["vars"].abs().max() > 0 else 1.0)
     check("imagined frames (last 3)", torch.stack(imgs[-3:], dim=1), fx["imgs_last3"])
     check("masks of the last frame", last["pred_masks"], fx["masks_last"])
+
+
+# ----------------------------------------------------------------------------------------------- fused transformer stack
+
+@pytest.mark.parametrize("n_layers,H,dh,proj,spf,L,n_seq", [(1, 8, 64, True, 6, 48, 4), (2, 8, 64, True, 6, 36, 7), (1, 4, 32, False, 0, 6, 64),
+                                                          (3, 8, 64, True, 8, 64, 5), (8, 8, 64, True, 6, 48, 64), (1, 4, 32, False, 0, 16, 9),
+                                                          (2, 8, 64, True, 0, 128, 2), (1, 8, 64, True, 1, 5, 3)])
+def test_fused_transformer_stack_vs_oracle(n_layers, H, dh, proj, spf, L, n_seq, linear_mode_guard):
+    """ ps_tblock_stack (one launch for a whole stack of pre-LN blocks, 4-CTA clusters) against the fp64 oracle block by block """
+    from playslot_b200 import ops
+    from playslot_b200.models.BlocksUtils.attention import TransformerDecoder, TransformerEncoderBlock
+    linear_mode_guard.set_linear_mode("fp16x3")
+    torch.manual_seed(n_layers * 100 + L)
+    if proj:
+        blocks = [TransformerDecoder(embed_dim=128, head_dim=dh, num_heads=H, mlp_size=512, project_out=True) for _ in range(n_layers)]
+    else:
+        blocks = [TransformerEncoderBlock(embed_dim=128, head_dim=dh, num_heads=H, mlp_size=512) for _ in range(n_layers)]
+    for b in blocks:
+        for name, prm in b.named_parameters():
+            with torch.no_grad():
+                if prm.dim() == 1:
+                    prm.copy_(torch.randn_like(prm) * 0.1 + (1.0 if "ln_" in name and name.endswith("weight") else 0.0))
+                else:
+                    prm.copy_(torch.randn_like(prm) * prm.shape[1] ** -0.5)
+    x = g(n_seq, L, 128, seed=7)
+    ref = x.double()
+    mask = None
+    if spf > 0:
+        fr = torch.arange(L) // spf
+        mask = (fr[None, :] <= fr[:, None]).to(torch.float64)
+    for b in blocks:
+        sd = {"blk." + k: v.detach().double() for k, v in b.state_dict().items()}
+        ref = O.transformer_block(sd, "blk", ref, H, dh, mask)
+    blocks = [b.to(DEV).eval() for b in blocks]
+    assert ops.tblock_stack_applicable(blocks, L)
+    pack = ops.pack_tblock_stack(blocks)
+    with torch.no_grad():
+        y = ops.tblock_stack(x.to(DEV).view(n_seq * L, 128), pack, n_seq, L, spf).view(n_seq, L, 128)
+    check("fused stack", y, ref.float())
