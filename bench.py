@@ -339,8 +339,102 @@ def slot_attention_config2(pk):
                     res["iteration_kernel" + ("_with_masks" if with_masks else "")] = {
                         "kernel": "sa_main_tc2", "us": us, "algorithmic_MB": kb / 1e6, "achieved_GBs": kb / us / 1e3,
                         "frac": kb / us / 1e3 / pk["hbm_gbs"]}
+            if reference_available():
+                # the same call on the UNMODIFIED reference module (oracle/_ref), eager PyTorch-CUDA with default flags, same weights
+                try:
+                    from oracle.install_ref import load_reference
+                    load_reference()
+                    from models.BlocksUtils.attention import SlotAttention as RefSlotAttention
+                    r = RefSlotAttention(128, 128, S, 3, 1, 256).eval().cuda()
+                    r.load_state_dict(m.state_dict())
+                    for _ in range(3):
+                        ref_out = r(feats, slots, step=0)
+                    ours_out = m(feats, slots, step=0)
+                    tr = []
+                    for _ in range(10):
+                        flush.zero_()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        r(feats, slots, step=0)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        tr.append(e0.elapsed_time(e1))
+                    tr.sort()
+                    res["reference_torch_cuda_ms"] = tr[len(tr) // 2]
+                    res["vs_reference_torch_cuda"] = tr[len(tr) // 2] / ms
+                    res["max_rel_err_vs_reference_torch_cuda"] = float((ours_out - ref_out).abs().max() / ref_out.abs().max())
+                    del r
+                except Exception as e:                          # the baseline leg never takes the bench line down
+                    res["reference_torch_cuda_ms"] = None
+                    res["reference_error"] = repr(e)[:200]
         out[f"S{S}"] = res
+    # "encode-only" variant of configs[1]: savi.encode(x) of one frame batch = CNN encoder + position embedding +
+    # encoder MLP + the 3-iteration SlotAttention, BlockPush (8 slots) and ButtonPress (4 slots) shapes, 64 frames of 64 x 64
+    try:
+        out["encode_only"] = encode_only_sweep(flush)
+    except Exception as e:
+        out["encode_only"] = {"error": repr(e)[:300]}
     return out
+
+
+@torch.no_grad()
+def encode_only_sweep(flush):
+    import contextlib
+    import copy
+    from playslot_b200 import configs
+    res = {}
+    for exp in ("BlockPush", "ButtonPress"):
+        cfg = configs.experiment(exp)
+        torch.manual_seed(0)
+        savi, _ = configs.build_models(cfg, "cuda")
+        savi.eval()
+        x = torch.rand(64, 3, 64, 64, device="cuda")
+        S = cfg["model"]["model_params"]["num_slots"]
+
+        def ours():
+            return savi_encode(savi, x)
+        for _ in range(3):
+            o = ours()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ours(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        entry = {"slots": S, "frames": 64, "ours_ms": ts[len(ts) // 2], "ours_frames_per_s": 64 / ts[len(ts) // 2] * 1e3}
+        if reference_available():
+            from oracle.install_ref import load_reference
+            with contextlib.redirect_stdout(sys.stderr):
+                setup_model, _, experiment_json = load_reference()
+                rsavi = setup_model(copy.deepcopy(experiment_json(exp)["model"])).eval().cuda()
+            rsavi.load_state_dict(savi.state_dict())
+            for _ in range(3):
+                ro = savi_encode(rsavi, x)
+            tr = []
+            for _ in range(10):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); savi_encode(rsavi, x); e1.record()
+                torch.cuda.synchronize()
+                tr.append(e0.elapsed_time(e1))
+            tr.sort()
+            entry["reference_torch_cuda_ms"] = tr[len(tr) // 2]
+            entry["vs_reference_torch_cuda"] = tr[len(tr) // 2] / entry["ours_ms"]
+            entry["max_rel_err_vs_reference_torch_cuda"] = float((o - ro).abs().max() / ro.abs().max())
+            del rsavi
+        res[exp] = entry
+        del savi
+    torch.cuda.empty_cache()
+    return res
+
+
+def savi_encode(savi, x):
+    """ one frame batch through the public API, SAVi.forward with one frame and decode=False (SAVi.py:135-204): CNN encoder,
+    position embedding, encoder MLP, the 3 SlotAttention iterations of a first frame (and the transition block, negligible) --
+    the same call for our mirror and for the reference module """
+    return savi(x.unsqueeze(1), num_imgs=1, decode=False)["slot_history"]
 
 
 def run_ours(args):

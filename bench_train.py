@@ -125,6 +125,16 @@ def run_train(args):
                                   "the backward (nothing left to overlap), so this is its exposed time"},
             "trainable_params": n_params, "loss_first_last": [losses[0], losses[-1]],
         }
+        if world == 1 and not args.skip_extras:
+            try:
+                from oracle.install_ref import available
+                if available():
+                    tcb = torch_cuda_train_baseline(B)
+                    line["torch_cuda_baseline"] = tcb
+                    line["vs_torch_cuda"] = {"device_resident": value / tcb["value"], "e2e": line["e2e"]["value"] / tcb["value"],
+                                             "note": "our videos/s / the reference's PyTorch-CUDA training step, same GPU, same batch"}
+            except Exception as e:
+                line["torch_cuda_baseline"] = {"error": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         # destroy_process_group() after graph-captured collectives blocks in the NCCL watchdog shutdown (measured: the process hangs
@@ -135,36 +145,32 @@ def run_train(args):
         os._exit(0)
 
 
-def run_train_reference(args):
-    """ the unmodified reference's training step (modules + lib/loss.py from oracle/_ref) on the host cores, bounded sample """
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def reference_train_step(device, B):
+    """ step(seed) -> seconds: one training step of the UNMODIFIED reference (modules + lib/loss.py from oracle/_ref; frozen SAVi,
+    predictor forward, decode, PredImgMSE + PredSlotMSE + VQ losses, backward, clip, Adam -- 04_train_PlaySlot.py:32-122,
+    basePredictorTrainer.py:320-333) on `device`, eager PyTorch with default flags """
     import contextlib
     import copy
-    from oracle.install_ref import load_reference, available
-    if not available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref did not travel with the snapshot"}))
-        return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    B = args.ref_batch or 2
+    from oracle.install_ref import load_reference
     T = NUM_SEED + NUM_PREDS
     with contextlib.redirect_stdout(sys.stderr):
         setup_model, setup_predictor, experiment_json = load_reference()
         from lib.loss import PredImgMSELoss, PredSlotMSELoss, VQLoss
         j = experiment_json(EXPERIMENT)
         torch.manual_seed(0)
-        savi = setup_model(copy.deepcopy(j["model"])).eval()
-        pred = setup_predictor(copy.deepcopy(j)).train()
+        savi = setup_model(copy.deepcopy(j["model"])).eval().to(device)
+        pred = setup_predictor(copy.deepcopy(j)).train().to(device)
     for p in savi.parameters():
         p.requires_grad_(False)
     opt = torch.optim.Adam(pred.parameters(), lr=1e-4)
     l_img, l_slot, l_vq = PredImgMSELoss(), PredSlotMSELoss(), VQLoss(beta=0.25)
+    cuda = str(device).startswith("cuda")
 
     def step(seed):
         g = torch.Generator().manual_seed(seed)
-        video = torch.rand(B, T, 3, 64, 64, generator=g)
+        video = torch.rand(B, T, 3, 64, 64, generator=g).to(device)
+        if cuda:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         with torch.no_grad():
             sh = savi(video, num_imgs=T, decode=False)["slot_history"]
@@ -178,7 +184,37 @@ def run_train_reference(args):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(pred.parameters(), 0.05)
         opt.step()
+        if cuda:
+            torch.cuda.synchronize()
         return time.perf_counter() - t0
+    return step
+
+
+def torch_cuda_train_baseline(B, reps=10):
+    """ the reference's training step on the same GPU (the PyTorch-CUDA denominator of the training number) """
+    step = reference_train_step("cuda", B)
+    ts = sorted(step(300 + i) for i in range(2 + reps))[: reps]     # drop the two slowest (warm-up: cuDNN autotune, allocator)
+    ms = 1e3 * ts[len(ts) // 2]
+    torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_min": 1e3 * ts[0], "ms_max": 1e3 * ts[-1], "timed_reps": reps,
+            "batch": B, "kind": "unmodified reference modules + lib/loss.py (oracle/_ref) on cuda:0: eager ATen / cuDNN / cuBLAS, "
+                                "default flags (TF32 convolutions), fp32; wall clock with synchronise, median"}
+
+
+def run_train_reference(args):
+    """ the unmodified reference's training step (modules + lib/loss.py from oracle/_ref) on the host cores, bounded sample """
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.install_ref import available
+    if not available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref did not travel with the snapshot"}))
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.ref_batch or 2
+    T = NUM_SEED + NUM_PREDS
+    step = reference_train_step("cpu", B)
 
     for i in range(args.warmup):
         step(100 + i)

@@ -144,6 +144,11 @@ int ps_sa_main_tc2(const void* planes, long long lo_offset_tokens, const float* 
 int ps_enc_mlp_planes(const float* x, int ldx, int K1, const float* ln_g, const float* ln_b, float ln_eps,
                       const void* w1_packed, float w1_scale, const float* b1, const void* w2_packed, float w2_scale,
                       const float* b2, float out_eps, void* planes, long long n_tokens, void* stream);
+/* The same for a 32-channel encoder convolved in channel pairs (two images share the 64 channels of ps_conv5x5_tc): input row
+ * (pair * pair_hw + position) * 2 + image, output planes in image order.  pair_hw = H * W of one image (0: plain). */
+int ps_enc_mlp_planes_paired(const float* x, int ldx, int K1, const float* ln_g, const float* ln_b, float ln_eps,
+                             const void* w1_packed, float w1_scale, const float* b1, const void* w2_packed, float w2_scale,
+                             const float* b2, float out_eps, void* planes, long long n_tokens, int pair_hw, void* stream);
 
 /* Per-slot update: reduce the partials, renormalise over locations (:109), to_v (:94), nn.GRUCell (:112-115),
  * residual MLP (:117), then (do_prep) the folded queries of the next iteration.  With do_update = 0 it only

@@ -32,6 +32,7 @@ SIGNATURES = {
     "ps_sa_main_tc": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),
     "ps_sa_prepare": (c_i, [c_f, c_f, ctypes.c_longlong, c_i, c_fl, c_f]),
     "ps_enc_mlp_planes": (c_i, [c_f, c_i, c_i, c_f, c_f, c_fl, c_f, c_fl, c_f, c_f, c_fl, c_f, c_fl, c_f, ctypes.c_longlong, c_f]),
+    "ps_enc_mlp_planes_paired": (c_i, [c_f, c_i, c_i, c_f, c_f, c_fl, c_f, c_fl, c_f, c_f, c_fl, c_f, c_fl, c_f, ctypes.c_longlong, c_i, c_f]),
     "ps_sa_tc2_chunks": (c_i, [c_i, c_i]),
     "ps_sa_main_tc2": (c_i, [c_f, ctypes.c_longlong, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "ps_sa_update": (c_i, [c_f, c_i, c_f, c_f] + [c_f] * 17 + [c_f, c_f, c_f] + [c_i, c_i, c_i, c_i, c_fl, c_fl, c_i, c_i, c_f]),

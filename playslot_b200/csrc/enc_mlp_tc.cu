@@ -52,6 +52,7 @@ struct EncMlpParams {
     uint16_t* out_hi; uint16_t* out_lo;
     long long M;
     int n_tiles;
+    int pair_hw;                  // > 0: input rows are (pair, position, image-in-pair); output row = (2 * pair + image) * pair_hw + position
 };
 
 __device__ __forceinline__ void em_split8(const float* v, uint4& hi, uint4& lo) {
@@ -314,8 +315,13 @@ enc_mlp_tc_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_consta
             const float rstd = 1.0f / sqrtf((s_sq[par][0][row] + s_sq[par][1][row]) * (1.0f / EM_D) + p.out_eps);
             const long long m = (long long)it * EM_BM + row;
             if (m < p.M) {
-                uint16_t* oh = p.out_hi + (size_t)m * EM_D + half * 64;
-                uint16_t* ol = p.out_lo + (size_t)m * EM_D + half * 64;
+                long long mo = m;
+                if (p.pair_hw > 0) {                               // un-interleave the two images of a channel pair (see ps_enc_mlp_planes_paired)
+                    const long long q = m >> 1, pr = q / p.pair_hw;
+                    mo = (2 * pr + (m & 1)) * p.pair_hw + (q - pr * p.pair_hw);
+                }
+                uint16_t* oh = p.out_hi + (size_t)mo * EM_D + half * 64;
+                uint16_t* ol = p.out_lo + (size_t)mo * EM_D + half * 64;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                      // 16 features -> one full 32-byte sector per plane
                     float f[16];
@@ -343,6 +349,18 @@ enc_mlp_tc_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_consta
 extern "C" int ps_enc_mlp_planes(const float* X, int ldx, int K1, const float* ln_g, const float* ln_b, float ln_eps,
                                  const void* w1_packed, float w1_scale, const float* b1, const void* w2_packed, float w2_scale,
                                  const float* b2, float out_eps, void* planes, long long n_tokens, void* stream) {
+    return ps_enc_mlp_planes_paired(X, ldx, K1, ln_g, ln_b, ln_eps, w1_packed, w1_scale, b1, w2_packed, w2_scale, b2, out_eps, planes,
+                                    n_tokens, 0, stream);
+}
+
+// The same for the tokens of a 32-channel encoder whose images were convolved in channel PAIRS (two images side by side in the
+// 64 channels of the tensor-core convolution, SAVi._encode_convs_tc): input row r = (pair * pair_hw + position) * 2 + image,
+// i.e. the two images' tokens alternate; the planes are written in image order, row (2 * pair + image) * pair_hw + position.
+extern "C" int ps_enc_mlp_planes_paired(const float* X, int ldx, int K1, const float* ln_g, const float* ln_b, float ln_eps,
+                                        const void* w1_packed, float w1_scale, const float* b1, const void* w2_packed, float w2_scale,
+                                        const float* b2, float out_eps, void* planes, long long n_tokens, int pair_hw, void* stream) {
+    PS_REQUIRE(pair_hw >= 0 && (pair_hw == 0 || n_tokens % (2ll * pair_hw) == 0),
+               "ps_enc_mlp_planes_paired: n_tokens must be a multiple of 2 * pair_hw (got %lld, %d)", n_tokens, pair_hw);
     PS_REQUIRE(X && ln_g && ln_b && w1_packed && w2_packed && planes, "ps_enc_mlp_planes: null pointer");
     PS_REQUIRE(K1 >= 16 && K1 <= 64 && K1 % 16 == 0, "ps_enc_mlp_planes: K1 must be 16, 32, 48 or 64 (got %d)", K1);
     PS_REQUIRE(ldx >= K1 && ldx % 4 == 0 && ps_aligned16(X) && ps_aligned16(ln_g) && ps_aligned16(ln_b) && ps_aligned16(planes),
@@ -354,7 +372,7 @@ extern "C" int ps_enc_mlp_planes(const float* X, int ldx, int K1, const float* l
     p.X = X; p.ldx = ldx; p.K1 = K1; p.ln_g = ln_g; p.ln_b = ln_b; p.ln_eps = ln_eps;
     p.b1 = b1; p.b2 = b2; p.s1 = 1.0f / w1_scale; p.s2 = 1.0f / w2_scale; p.out_eps = out_eps;
     p.out_hi = reinterpret_cast<uint16_t*>(planes); p.out_lo = p.out_hi + n_tokens * EM_D;
-    p.M = n_tokens; p.n_tiles = (int)((n_tokens + EM_BM - 1) / EM_BM);
+    p.M = n_tokens; p.n_tiles = (int)((n_tokens + EM_BM - 1) / EM_BM); p.pair_hw = pair_hw;
     CUtensorMap mW1, mW2;
     int r = tc::make_tmap_2d_bf16_sw128(&mW1, w1_packed, 256, 64, 256, 64);
     PS_REQUIRE(r == 0, "ps_enc_mlp_planes: cuTensorMapEncodeTiled(W1) failed (%d)", r);

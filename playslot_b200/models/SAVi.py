@@ -227,7 +227,16 @@ class SAVi(nn.Module):
         tc_convs = self._tc_applicable(self.encoder.encoder, skip_first=True, channels=self.enc_tc_channels)
         fused = (planes and ops.linear_mode() == "fp16x3" and self.mlp_encoder_dim == 128 and fc1.out_features == 128
                  and C <= 64 and C % 16 == 0 and M * H * W >= ops.LINEAR_TC_MIN_ROWS)
-        if tc_convs:
+        paired = tc_convs and self._pairable(x)
+        if paired:
+            # 32-channel encoder: two images share the 64 channels of the tensor-core convolution (block-diagonal weights)
+            tokens = self._encode_convs_tc_paired(x, posemb)                      # (ceil(M/2), H*W, 2 images, 32)
+            if fused:
+                planes = ops.enc_mlp_planes(tokens.view(-1, C), C, (ln.weight, ln.bias, ln.eps), (fc1.weight, fc1.bias),
+                                            (fc2.weight, fc2.bias), self.slot_attention.norm_input.eps, pair_hw=H * W)
+                return planes if M % 2 == 0 else planes[:, :M * H * W].contiguous()
+            tokens = tokens.permute(0, 2, 1, 3).reshape(-1, H * W, C)[:M].contiguous()
+        elif tc_convs:
             tokens = self._encode_convs_tc(x, posemb, keep_padded=fused)          # (M, H*W, 64 if fused else C)
         else:
             tokens = self.encoder.run(x, last_nhwc_addend=posemb)
@@ -308,6 +317,60 @@ class SAVi(nn.Module):
             out[:b.shape[0]] = b.detach()
             return out
         return cache.get([b], build)
+
+    PAIR_32CH = True                # 32-channel encoders: convolve two images per 64-channel plane (False: zero-pad each image to 64)
+
+    def _pairable(self, x):
+        blocks = list(self.encoder.encoder)
+        M, _, H, W = x.shape
+        return (self.PAIR_32CH and blocks[0].conv.out_channels == 32 and M >= 2 and (M + 1) // 2 <= 65535
+                and H % 16 == 0 and W % 16 == 0)
+
+    def _pair_weights(self, block, first):
+        """ block-diagonal 64-channel weights / duplicated bias of a 32-channel ConvBlock: image 2p of a pair lives in channels
+        0..31, image 2p+1 in channels 32..63 (the zero blocks contribute exact zeros, so both images see their own convolution) """
+        prec = ops.TC_PRECISION[self.conv_mode]
+        cache = self._tc_w.setdefault((id(block), "pair", first, prec), DerivedWeights())
+        c = block.conv
+
+        def build():
+            w = c.weight.detach()
+            co, ci = w.shape[0], w.shape[1]
+            wp = torch.zeros(2 * co, 2 * ci, *w.shape[2:], device=w.device, dtype=w.dtype)
+            wp[:co, :ci] = w
+            wp[co:, ci:] = w
+            bp = torch.cat([c.bias.detach(), c.bias.detach()]).contiguous()
+            return (ops.pack_conv_weight(wp) if first else ops.pack_conv_weight_tc(wp, prec)), bp
+        return cache.get([c.weight, c.bias], build)
+
+    def _encode_convs_tc_paired(self, x, posemb):
+        """ the encoder stack of a 32-channel configuration on image PAIRS: (M, 3, H, W) is read as (M/2, 6, H, W), every layer runs
+        with block-diagonal weights, and the tokens come back as (M/2, H*W, 2, 32) -- half the tensor-core work of padding each
+        image to 64 channels.  An odd batch gets one zero image appended. """
+        prec = ops.TC_PRECISION[self.conv_mode]
+        blocks = list(self.encoder.encoder)
+        M, Cin, H, W = x.shape
+        if M % 2:
+            x = torch.cat([x, torch.zeros_like(x[:1])], dim=0)
+        Mp = x.shape[0] // 2
+        xp = x.view(Mp, 2 * Cin, H, W)
+        a = self._tc_workspace("enc_a", Mp, H, W, x.device)
+        b = self._tc_workspace("enc_b", Mp, H, W, x.device)
+        w0, b0 = self._pair_weights(blocks[0], True)
+        ops.conv2d_split(xp, w0, b0, blocks[0].conv.kernel_size[0], blocks[0]._relu, a, prec)
+        for blk in blocks[1:-1]:
+            w, bias = self._pair_weights(blk, False)
+            ops.conv5x5_tc(a, w, bias, Mp, H, W, blk._relu, prec, act_out=b)
+            a, b = b, a
+        last = blocks[-1]
+        if not hasattr(self, "_posemb_pair"):
+            self._posemb_pair = DerivedWeights()
+        pe = self.encoder_pos_embedding.projection
+        posemb2 = self._posemb_pair.get([pe.weight, pe.bias], lambda: torch.cat([posemb, posemb], dim=-1).contiguous())
+        tokens = torch.empty(Mp, H * W, 64, device=x.device, dtype=torch.float32)
+        w, bias = self._pair_weights(last, False)
+        ops.conv5x5_tc(a, w, bias, Mp, H, W, last._relu, prec, out_tokens=tokens, addend=posemb2)
+        return tokens.view(Mp, H * W, 2, 32)
 
     def _encode_convs_tc(self, x, posemb, keep_padded=False):
         """ first conv (3 -> C) on the CUDA cores writing the split planes, the C -> C layers on tcgen05; tokens + posemb out.

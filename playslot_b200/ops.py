@@ -431,10 +431,11 @@ def sa_prepare(x, ln_eps=1e-5):
     return planes
 
 
-def enc_mlp_planes(tokens, K1, ln, fc1, fc2, out_eps):
+def enc_mlp_planes(tokens, K1, ln, fc1, fc2, out_eps, pair_hw=0):
     """ tokens (n_tok, ldx) fp32 (first K1 columns used), ln = (gamma, beta, eps) over K1, fc1 = (W1 (128,K1), b1),
     fc2 = (W2 (128,128), b2) -> planes int16 (2 [hi, lo], n_tok, 128) of norm_input-normalised encoder features: the
-    encoder MLP and sa_prepare in one tensor-core kernel """
+    encoder MLP and sa_prepare in one tensor-core kernel.  pair_hw > 0: the token rows are (pair, position, image-in-pair)
+    (channel-paired 32-channel encoder); the planes come out in image order """
     lib = _lib.load()
     _req(tokens, "tokens")
     n_tok, ldx = tokens.shape
@@ -443,9 +444,9 @@ def enc_mlp_planes(tokens, K1, ln, fc1, fc2, out_eps):
     assert (kp1, np1, kp2, np2) == (64, 128, 128, 128), "enc_mlp_planes: Linear(K1<=64, 128) -> Linear(128, 128) only"
     planes = torch.empty(2, n_tok, 128, device=tokens.device, dtype=torch.int16)
     with _timed("enc_mlp_planes", (n_tok, K1)):
-        st = lib.ps_enc_mlp_planes(_ptr(tokens), ldx, K1, _ptr(ln[0]), _ptr(ln[1]), float(ln[2]), _ptr(w1), float(s1), _ptr(fc1[1]),
-                                   _ptr(w2), float(s2), _ptr(fc2[1]), float(out_eps), _ptr(planes), n_tok, _stream())
-    _lib.check(st, "ps_enc_mlp_planes")
+        st = lib.ps_enc_mlp_planes_paired(_ptr(tokens), ldx, K1, _ptr(ln[0]), _ptr(ln[1]), float(ln[2]), _ptr(w1), float(s1), _ptr(fc1[1]),
+                                          _ptr(w2), float(s2), _ptr(fc2[1]), float(out_eps), _ptr(planes), n_tok, int(pair_hw), _stream())
+    _lib.check(st, "ps_enc_mlp_planes_paired")
     return planes
 
 

@@ -358,6 +358,35 @@ def test_encode_and_decode_vs_oracle(case, conv_mode):
     check("recon == sum(rgb*mask)", recon, (recons * masks).sum(dim=1), 1e-5)
 
 
+@pytest.mark.parametrize("n_frames", [6, 5, 1])
+def test_encode_32ch_channel_pairs(n_frames):
+    """ 32-channel encoders convolve two images per 64-channel plane (SAVi._encode_convs_tc_paired): tokens, the fused
+    plane hand-over to SlotAttention and the uint8 input path against the oracle and against the one-image-per-plane path,
+    for even / odd / single-image batches """
+    fx, ssd, psd, video, noise, init_noise = load_case("blockpush")
+    scfg = fx["savi_cfg"]
+    savi = make_savi(scfg, ssd, DEV)
+    frames = video.reshape(-1, *video.shape[2:])[:n_frames].contiguous()
+    x = frames.to(DEV)
+    ref = O.encode(ssd, frames)
+    with torch.no_grad():
+        assert savi._pairable(x) == (n_frames >= 2)
+        check("encode, paired", savi.encode(x), ref)
+        planes_p = savi.encode(x, planes=True)
+        u8 = (frames * 255).round().clamp(0, 255).to(torch.uint8)
+        tok_u8 = savi.encode(u8.to(DEV))
+        check("encode, paired, uint8", tok_u8, O.encode(ssd, u8.float().div(255)))
+        savi.PAIR_32CH = False
+        tok_1 = savi.encode(x)
+        planes_1 = savi.encode(x, planes=True)
+    check("encode, one image per plane", tok_1, ref)
+    assert planes_p.shape == planes_1.shape and planes_p.is_contiguous()
+    # fp16 hi planes of the two paths: same values up to the rounding of a different summation order inside the MMAs
+    hp = planes_p[0].view(torch.float16).float()
+    h1 = planes_1[0].view(torch.float16).float()
+    check("planes, paired vs single", hp, h1, 2e-3)
+
+
 # ----------------------------------------------------------------------------------------------- whole pipeline
 
 @pytest.mark.parametrize("mode,tol", [("bf16", 1e-1), ("fp16", 1e-2)])

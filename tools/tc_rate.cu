@@ -8,7 +8,7 @@
 #include <vector>
 #include "../playslot_b200/csrc/tc_common.cuh"
 
-struct Case { int n1, n2, a_off1, a_off2, b_off; };     // per k-step: MMA(N = n1, A rows from a_off1) [+ MMA(N = n2, A from plane 2 at a_off2)]
+struct Case { int n1, n2, a_off1, a_off2, b_off, m1, m2; };   // m1 / m2: M of the two MMAs (0 = 128)     // per k-step: MMA(N = n1, A rows from a_off1) [+ MMA(N = n2, A from plane 2 at a_off2)]
 
 __global__ void __launch_bounds__(128, 1) rate_kernel(Case c, int iters, long long* cycles) {
     extern __shared__ uint8_t smem_raw[];
@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(Case c, int iters, long lo
     tc::tc_fence_after();
     const uint32_t tm = tmem_base;
     if (warp == 0 && tc::elect_one()) {
-        const uint32_t id1 = tc::umma_idesc_f16(128, c.n1);
-        const uint32_t id2 = c.n2 ? tc::umma_idesc_f16(128, c.n2) : 0;
+        const uint32_t id1 = tc::umma_idesc_f16(c.m1 ? c.m1 : 128, c.n1);
+        const uint32_t id2 = c.n2 ? tc::umma_idesc_f16(c.m2 ? c.m2 : 128, c.n2) : 0;
         const uint64_t a0 = tc::umma_desc_sw128(tc::smem_u32(sA0), 1024, 0);
         const uint64_t a1 = tc::umma_desc_sw128(tc::smem_u32(sA1), 1024, 0);
         const uint64_t b0 = tc::umma_desc_sw128(tc::smem_u32(sB), 1024, 0);
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(Case c, int iters, long lo
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     tc::umma_bf16(tm + tile * 256, a0 + (uint64_t)(r1 * 8 + k * 2), bst + (uint64_t)(k * 2), id1, 1u);
-                    if (c.n2) tc::umma_bf16(tm + tile * 256 + 64, a1 + (uint64_t)(r2 * 8 + k * 2), bst + (uint64_t)(k * 2), id2, 1u);
+                    if (c.n2) tc::umma_bf16(tm + tile * 256 + (c.n2 > 192 ? 0 : 64), a1 + (uint64_t)(r2 * 8 + k * 2), bst + (uint64_t)(k * 2), id2, 1u);
                 }
             }
         }
@@ -67,6 +67,8 @@ int main() {
     const Case cases[] = {
         {64, 0, 0, 0, 0}, {64, 0, 1, 0, 0}, {128, 0, 0, 0, 0}, {128, 0, 1, 0, 0}, {128, 0, 4, 0, 0}, {256, 0, 0, 0, 0}, {256, 0, 1, 0, 0},
         {128, 64, 0, 0, 0}, {128, 64, 1, 1, 0}, {128, 64, 3, 3, 0}, {128, 128, 0, 0, 0}, {128, 128, 1, 1, 0}, {192, 0, 0, 0, 0}, {192, 0, 1, 0, 0},
+        // weights-stationary costing: what an M = 64 product costs next to an M = 128 one at N = 256 / 128
+        {256, 0, 0, 0, 0, 64, 0}, {128, 0, 0, 0, 0, 64, 0}, {256, 256, 0, 0, 0, 128, 64}, {128, 128, 0, 0, 0, 128, 64},
     };
     for (int grid : {1, 148}) {
         for (const Case& c : cases) {
@@ -80,8 +82,8 @@ int main() {
             cudaMemcpy(h.data(), d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
             long long mx = 0; for (long long v : h) mx = v > mx ? v : mx;
             const double ksteps = (double)iters * 8;
-            printf("grid %3d  N1 %3d N2 %3d  a_off %d/%d : %.1f clk per k-step (%.1f per MMA)\n", grid, c.n1, c.n2, c.a_off1, c.a_off2,
-                   mx / ksteps, mx / ksteps / (c.n2 ? 2 : 1));
+            printf("grid %3d  M1 %3d N1 %3d  M2 %3d N2 %3d  a_off %d/%d : %.1f clk per k-step (%.1f per MMA)\n", grid, c.m1 ? c.m1 : 128, c.n1,
+                   c.n2 ? (c.m2 ? c.m2 : 128) : 0, c.n2, c.a_off1, c.a_off2, mx / ksteps, mx / ksteps / (c.n2 ? 2 : 1));
         }
     }
     return 0;
