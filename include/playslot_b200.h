@@ -241,6 +241,8 @@ int ps_layernorm_bwd(const float* dy, const float* x, const float* mean, const f
 /* Weight gradient of nn.Linear: dW[N,K] = dY[M,N]^T X[M,K], db[N] = column sums of dY (db may be NULL); outputs overwritten.
  * The data gradient dX = dY W is ps_linear with the transposed weight. */
 int ps_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int N, int K, void* stream);
+/* dW += dY^T X, db += colsum(dY): accumulating variant (outputs are NOT cleared) for weights used several times in one backward */
+int ps_linear_wgrad_acc(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int N, int K, void* stream);
 
 /* activation forward on saved pre-activations / backward; act: 1 ReLU, 2 GELU (exact erf), 3 |x| */
 int ps_act_fwd(const float* z, float* y, long long n, int act, void* stream);

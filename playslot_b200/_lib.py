@@ -47,6 +47,7 @@ SIGNATURES = {
     "ps_layernorm_fwd": (c_i, [c_f, c_f, c_f, c_fl, c_f, c_f, c_f, c_i, c_i, c_f]),
     "ps_layernorm_bwd": (c_i, [c_f] * 8 + [c_i, c_i, c_f]),
     "ps_linear_wgrad": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "ps_linear_wgrad_acc": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_f]),
     "ps_act_fwd": (c_i, [c_f, c_f, ctypes.c_longlong, c_i, c_f]),
     "ps_act_bwd": (c_i, [c_f, c_f, c_f, ctypes.c_longlong, c_i, c_f]),
     "ps_mha_bwd": (c_i, [c_f, c_i, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),

@@ -25,6 +25,14 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _bucket_view(param):
+    """ the flat-bucket view train.GradientBucket.attach() installed as `param.grad` (a leaf Parameter still bound to it), or None """
+    v = getattr(param, "_ps_bucket_grad", None)
+    if v is None or not param.is_leaf or param.grad is None or param.grad.data_ptr() != v.data_ptr():
+        return None
+    return v
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
@@ -56,6 +64,7 @@ class _Linear(torch.autograd.Function):
         x = _c(x)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.bias = bias                 # the Parameter object (not a saved tensor): its bucket view receives the bias gradient
         ctx.mode = TRAIN_LINEAR_MODE
         w = weight if (ctx.mode != "fp32" and weight.is_contiguous()) else _c(weight.detach())     # the Parameter object carries the pack cache
         return ops.linear(x, w, None if bias is None else _c(bias.detach()), mode=ctx.mode, reuse_pack_scale=True)
@@ -73,7 +82,14 @@ class _Linear(torch.autograd.Function):
             else:
                 dx = ops.linear(dy, weight.detach().t().contiguous(), None, mode="fp32").view(x.shape)     # dX = dY W
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = ops.linear_wgrad(dy.view(-1, N), x.view(-1, K), want_bias=ctx.has_bias)
+            # Parameters whose .grad is a view of the training step's flat GradientBucket accumulate straight into it: a weight
+            # shared by the T roll-out steps would otherwise cost one autograd add kernel per use (~900 launches per step)
+            gw = _bucket_view(weight) if ctx.needs_input_grad[1] else None
+            gb = _bucket_view(ctx.bias) if ctx.has_bias else None
+            if gw is not None and (not ctx.has_bias or gb is not None):
+                ops.linear_wgrad_acc(dy.view(-1, N), x.view(-1, K), gw, gb)
+            else:
+                dw, db = ops.linear_wgrad(dy.view(-1, N), x.view(-1, K), want_bias=ctx.has_bias)
         return dx, dw, db
 
 

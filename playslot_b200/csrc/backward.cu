@@ -155,13 +155,31 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restri
     }
 }
 
+static int linear_wgrad_run(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int N, int K,
+                            bool accumulate, void* stream);
+
 extern "C" int ps_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int N, int K,
                                void* stream) {
+    return linear_wgrad_run(dY, lddy, X, ldx, dW, db, M, N, K, false, stream);
+}
+
+// dW += dY^T X, db += colsum(dY): the same kernel without clearing the outputs -- a weight that is used several times in one
+// backward pass (the 8 roll-out steps of the training script share every predictor weight) accumulates straight into its
+// gradient buffer instead of through one autograd add kernel per use
+extern "C" int ps_linear_wgrad_acc(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int N, int K,
+                                   void* stream) {
+    return linear_wgrad_run(dY, lddy, X, ldx, dW, db, M, N, K, true, stream);
+}
+
+static int linear_wgrad_run(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int N, int K,
+                            bool accumulate, void* stream) {
     PS_REQUIRE(dY && X && dW, "ps_linear_wgrad: null pointer");
     PS_REQUIRE(M >= 0 && N > 0 && K > 0, "ps_linear_wgrad: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
-    PS_CUDA(cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), st));
-    if (db) PS_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+    if (!accumulate) {
+        PS_CUDA(cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), st));
+        if (db) PS_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+    }
     if (M == 0) return PS_OK;
     const int tiles = ((N + WG_T - 1) / WG_T) * ((K + WG_T - 1) / WG_T);
     int splits = (2 * 148 + tiles - 1) / tiles;

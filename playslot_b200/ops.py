@@ -716,6 +716,18 @@ def linear_wgrad(dy, x, want_bias=True):
     return dW, db
 
 
+def linear_wgrad_acc(dy, x, dW, db=None):
+    """ dW (N, K) += dy^T x, db (N,) += colsum(dy): accumulate into existing gradient buffers """
+    lib = _lib.load()
+    _req(dy, "dy"); _req(x, "x"); _req(dW, "dW")
+    M, N = dy.shape
+    K = x.shape[1]
+    assert dW.shape == (N, K) and dW.is_contiguous() and (db is None or (db.shape == (N,) and db.is_contiguous()))
+    with _timed("linear_wgrad", (M, N, K)):
+        st = lib.ps_linear_wgrad_acc(_ptr(dy), N, _ptr(x), K, _ptr(dW), _ptr(db), M, N, K, _stream())
+    _lib.check(st, "ps_linear_wgrad_acc")
+
+
 def act_fwd(z, act):
     lib = _lib.load()
     _req(z, "z")

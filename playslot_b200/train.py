@@ -68,6 +68,7 @@ class GradientBucket:
         self.flat.zero_()
         for p, v in zip(self.params, self.views):
             p.grad = v
+            p._ps_bucket_grad = v        # autograd._Linear accumulates its weight / bias gradients straight into the view
 
     def _gather_detached(self):
         """ gradients that autograd rebound (set_to_none users): copy them in; the fast path never takes this branch """
@@ -180,7 +181,8 @@ class GraphedTrainStep:
         # captured INSIDE the graph.  NCCL capture needs (a) a communicator that has already run on this device -- the
         # warm-up steps below do that -- and (b) capture_error_mode="thread_local", because the NCCL watchdog thread polls CUDA
         # events while the capture is open.
-        self.bucket = bucket if bucket is not None else (GradientBucket(predictor.parameters()) if self.world > 1 else None)
+        # (single GPU too: the bucket views are what the Linear backward accumulates into without autograd add kernels)
+        self.bucket = bucket if bucket is not None else GradientBucket(predictor.parameters())
         self.savi, self.predictor, self.optimizer = savi, predictor, optimizer
         self.num_seed, self.num_preds = num_seed, num_preds
         T = num_seed + num_preds
