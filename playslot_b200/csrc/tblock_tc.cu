@@ -18,13 +18,10 @@
 // Arithmetic: the fp16x3 scheme of linear_tc.cu (x = hi + lo/2048; D0 += A_hi B_hi, D1 += A_hi B_lo + A_lo B_hi, y = D0 + D1/2048)
 // for EVERY contraction including q k^T and P v; softmax, LayerNorm, GELU, residuals in fp32.
 //
-// CTA = 512 threads = 16 "row" warps (row = 32 * (warp % 4) + lane, part = warp / 4: the TMEM lane quarter a warp may read is
-// warp % 4, the part selects 32 of a row's 128 columns).  The MMAs of a phase take ~0.15 us, the epilogues between them are
-// chains of dependent CUDA-core work (TMEM load -> scale / softmax / GELU -> fp16 split -> swizzled store), so the kernel's time
-// is thread-serial latency: four threads per row (was two: 37 -> 2x us per layer, tools/trace_tblock.py) halve every chain.
-// MMA and epilogue phases alternate strictly (operands ready -> MMAs -> accumulators ready -> epilogue -> ...) on two mbarriers,
-// so warp 0 issues the TMA loads and MMAs itself between its epilogue parts (no extra issuer warp: 512 threads x 128 registers
-// is the whole register file).
+// CTA = 256 threads = 8 "row" warps (row = 32 * (warp % 4) + lane, half = warp / 4: the TMEM lane quarter a warp may read is
+// warp % 4, the half selects 64 of a row's columns).  MMA and epilogue phases alternate strictly (operands ready -> MMAs ->
+// accumulators ready -> epilogue -> ...) on two mbarriers, so warp 0 issues the TMA loads and MMAs itself between its epilogue
+// parts (a ninth warp would put three warps on one scheduler and cap the kernel at 168 registers).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/playslot_b200.h"
@@ -35,8 +32,7 @@ namespace {
 constexpr int TB_E = 128;                    // embedding width
 constexpr int TB_M = 128;                    // rows per tile
 constexpr int TB_TILE = TB_M * 128;          // bytes of one [128 rows][64 K] 16-bit operand tile (16 KB)
-constexpr int TB_THREADS = 512;
-constexpr int TB_PARTS = 4;                  // threads per row (each owns 32 of the 128 columns)
+constexpr int TB_THREADS = 256;
 constexpr int TB_CLUSTER = 4;
 constexpr float TB_LO = 2048.0f;
 constexpr float TB_LO_INV = 1.0f / 2048.0f;
@@ -119,25 +115,6 @@ __device__ __forceinline__ void tb_ld32(uint32_t tl, int d0_col, int d1_col, flo
     for (int j = 0; j < 32; ++j) v[j] = fmaf(u[j], TB_LO_INV, v[j]);
 }
 
-__device__ __forceinline__ void tb_tmem_ld16_nowait(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tb_ld16(uint32_t tl, int d0_col, int d1_col, float* v) {
-    float u[16];
-    tb_tmem_ld16_nowait(tl + d0_col, v);
-    tb_tmem_ld16_nowait(tl + d1_col, u);
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaf(u[j], TB_LO_INV, v[j]);
-}
-
 __global__ void __cluster_dims__(TB_CLUSTER, 1, 1) __launch_bounds__(TB_THREADS, 1)
 tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_constant__ CUtensorMap mapA64,
                     const __grid_constant__ CUtensorMap mapB, const TbParams p) {
@@ -145,8 +122,8 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
     // starts at offset 0 of the CTA's shared window (1024-byte aligned, checked below); barriers and the small exchange buffer
     // live behind the tiles.
     extern __shared__ __align__(1024) uint8_t smem[];
-    float (*s_red)[TB_M] = reinterpret_cast<float (*)[TB_M]>(smem + TB_SMEM);            // [part][row] cross-part exchange
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TB_SMEM + TB_PARTS * TB_M * 4);
+    float (*s_red)[2][TB_M] = reinterpret_cast<float (*)[2][TB_M]>(smem + TB_SMEM);      // [buffer][half][row] cross-half exchange
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TB_SMEM + 2 * 2 * TB_M * 4);
     uint64_t& bar_opnd = bars[0]; uint64_t& bar_acc = bars[1]; uint64_t& bar_w0 = bars[2]; uint64_t& bar_w1 = bars[3]; uint64_t& bar_m = bars[4];
     uint32_t& tmem_base = *reinterpret_cast<uint32_t*>(bars + 5);
     if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();
@@ -159,7 +136,7 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
     const long long row0 = (long long)tile * p.G * p.L;                  // first global row
 
     if (tid == 0) {
-        tc::mbar_init(&bar_opnd, TB_THREADS / 32);      // one arrive per row warp
+        tc::mbar_init(&bar_opnd, 8);      // one arrive per row warp
         tc::mbar_init(&bar_acc, 1);
         tc::mbar_init(&bar_w0, 1);
         tc::mbar_init(&bar_w1, 1);
@@ -177,8 +154,8 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
     tc::pdl_wait();                                                      // X is produced by the previous kernel in the stream
 
     // ------------------------------------------------------------------ issuer role (warp 0; one elected lane issues TMA / MMA)
-    // The phases alternate strictly -- epilogue of all 16 warps -> MMAs -> epilogue ... -- so the MMAs are issued by warp 0 itself
-    // between two of its epilogue parts.
+    // The phases alternate strictly -- epilogue of all 8 warps -> MMAs -> epilogue ... -- so the MMAs are issued by warp 0 itself
+    // between two of its epilogue parts: no ninth warp (a third warp on one scheduler would cap the kernel at 168 registers).
     const bool issuer = warp == 0;
     const bool leader = issuer && tc::elect_one();
     const uint32_t sb = tc::smem_u32(smem);
@@ -230,10 +207,9 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
     };
     auto commit_acc = [&]() { if (leader) tc::umma_commit(&bar_acc); };
 
-    // ------------------------------------------------------------------ row role (all 16 warps)
-    const int q4 = warp & 3, part = warp >> 2;
+    // ------------------------------------------------------------------ row role (all 8 warps)
+    const int q4 = warp & 3, half = warp >> 2;
     const int row = q4 * 32 + lane;
-    const int kb_p = part >> 1, ch_p = (part & 1) * 4;  // this thread's 32 columns inside a [kb0 | kb1] K-major operand: K-block, first 16-byte chunk
     const uint32_t tl = tm + ((uint32_t)(q4 * 32) << 16);
     const bool row_ok = row < rows_valid;
     int n_stamp = 0;
@@ -251,57 +227,46 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bar_opnd);
     };
-    // The four threads of a row sit in the four warps of one TMEM lane quarter: they meet on the quarter's own named barrier
-    // (128 threads) and combine their partial values in a fixed order, so all four hold bit-identical results.  The exchange
-    // buffer is single (2 KB is all the shared memory left): the second barrier protects it against the next exchange.
-    auto qbar = [&]() { asm volatile("bar.sync %0, 128;\n" ::"r"(q4 + 1) : "memory"); };
-    auto row_sum = [&](float v) {
-        s_red[part][row] = v;
-        qbar();
-        const float t = (s_red[0][row] + s_red[1][row]) + (s_red[2][row] + s_red[3][row]);
-        qbar();
-        return t;
-    };
-    auto row_max = [&](float v) {
-        s_red[part][row] = v;
-        qbar();
-        const float t = fmaxf(fmaxf(s_red[0][row], s_red[1][row]), fmaxf(s_red[2][row], s_red[3][row]));
-        qbar();
-        return t;
-    };
-    // residual stream: this thread's 32 features of its row
-    float x[32];
+    // residual stream: this thread's 64 features of its row
+    float x[64];
     {
-        const float4* src = reinterpret_cast<const float4*>(p.X + (size_t)(row0 + row) * TB_E + part * 32);
+        const float4* src = reinterpret_cast<const float4*>(p.X + (size_t)(row0 + row) * TB_E + half * 64);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
             const float4 v = row_ok ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
             x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
         }
     }
-    // LayerNorm of the row -> the thread's 32 columns of the Ax operand (hi and lo tiles)
+    int red_buf = 0;
+    // LayerNorm of the row (two threads per row exchange partial sums) -> Ax K-block `half` (hi and lo tiles)
     auto layer_norm_to_ax = [&](const float* g, const float* b, float eps) {
         float sm_ = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sm_ += x[j];
-        const float mean = row_sum(sm_) * (1.0f / TB_E);
+        for (int j = 0; j < 64; ++j) sm_ += x[j];
+        s_red[red_buf][half][row] = sm_;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        const float mean = (s_red[red_buf][0][row] + s_red[red_buf][1][row]) * (1.0f / TB_E);
+        red_buf ^= 1;
         float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = x[j] - mean; ss = fmaf(d, d, ss); }
-        const float rstd = 1.0f / sqrtf(row_sum(ss) * (1.0f / TB_E) + eps);
-        uint8_t* hi_t = smem + TB_AX + kb_p * TB_TILE;
-        uint8_t* lo_t = smem + TB_AX + (2 + kb_p) * TB_TILE;
-        const float4* g4 = reinterpret_cast<const float4*>(g + part * 32);
-        const float4* b4 = reinterpret_cast<const float4*>(b + part * 32);
+        for (int j = 0; j < 64; ++j) { const float d = x[j] - mean; ss = fmaf(d, d, ss); }
+        s_red[red_buf][half][row] = ss;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        const float rstd = 1.0f / sqrtf((s_red[red_buf][0][row] + s_red[red_buf][1][row]) * (1.0f / TB_E) + eps);
+        red_buf ^= 1;
+        uint8_t* hi_t = smem + TB_AX + half * TB_TILE;
+        uint8_t* lo_t = smem + TB_AX + (2 + half) * TB_TILE;
+        const float4* g4 = reinterpret_cast<const float4*>(g + half * 64);
+        const float4* b4 = reinterpret_cast<const float4*>(b + half * 64);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 8; ++c) {
             const float4 ga = __ldg(g4 + 2 * c), gb = __ldg(g4 + 2 * c + 1), ba = __ldg(b4 + 2 * c), bb = __ldg(b4 + 2 * c + 1);
             float v[8];
             v[0] = fmaf((x[c * 8 + 0] - mean) * rstd, ga.x, ba.x); v[1] = fmaf((x[c * 8 + 1] - mean) * rstd, ga.y, ba.y);
             v[2] = fmaf((x[c * 8 + 2] - mean) * rstd, ga.z, ba.z); v[3] = fmaf((x[c * 8 + 3] - mean) * rstd, ga.w, ba.w);
             v[4] = fmaf((x[c * 8 + 4] - mean) * rstd, gb.x, bb.x); v[5] = fmaf((x[c * 8 + 5] - mean) * rstd, gb.y, bb.y);
             v[6] = fmaf((x[c * 8 + 6] - mean) * rstd, gb.z, bb.z); v[7] = fmaf((x[c * 8 + 7] - mean) * rstd, gb.w, bb.w);
-            tb_store8(hi_t, lo_t, row, ch_p + c, v);
+            tb_store8(hi_t, lo_t, row, c, v);
         }
     };
     // Cluster reduction through L2: every CTA stores its fp32 partial [feature][row] in a global scratch slot, ONE cluster barrier
@@ -318,20 +283,23 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
         float* slot = p.ws + ((size_t)(red_idx * (gridDim.x / TB_CLUSTER) + tile) * TB_CLUSTER) * (TB_M * TB_E);
         red_idx ^= 1;
         {
-            float* dst = slot + (size_t)crank * (TB_M * TB_E) + (size_t)(part * 32) * TB_M + row;
-            float v[32];
-            tb_ld32(tl, TM_Y + part * 32, TM_Y + 128 + part * 32, v);
+            float* dst = slot + (size_t)crank * (TB_M * TB_E) + (size_t)(half * 64) * TB_M + row;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                float v[32];
+                tb_ld32(tl, TM_Y + half * 64 + c0, TM_Y + 128 + half * 64 + c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) __stcg(dst + (size_t)j * TB_M, v[j] * inv_scale);
+                for (int j = 0; j < 32; ++j) __stcg(dst + (size_t)(c0 + j) * TB_M, v[j] * inv_scale);
+            }
         }
         tc::tc_fence_before();
         stamp();
         cluster_sync_all();
         stamp();
-        const float* src = slot + (size_t)(part * 32) * TB_M + row;
+        const float* src = slot + (size_t)(half * 64) * TB_M + row;
 #pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-            float acc = __ldg(bias + part * 32 + j);
+        for (int j = 0; j < 64; ++j) {
+            float acc = __ldg(bias + half * 64 + j);
 #pragma unroll
             for (int r = 0; r < TB_CLUSTER; ++r)                // rank order: identical sums in all four CTAs
                 acc += __ldcg(src + (size_t)r * (TB_M * TB_E) + (size_t)j * TB_M);
@@ -360,16 +328,19 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
             }
             wait_acc();
             if (issuer) load_v_o(layer, h);                // the projection MMAs have retired: W0 / W1 are free
-            {   // q / k epilogue: parts 0, 1 -> Q tile (scaled by 1/sqrt(d_h)), parts 2, 3 -> K tile
-                uint8_t* hi_t = smem + TB_QKP + kb_p * 2 * TB_TILE;
+            {   // q / k epilogue: half 0 -> Q tile (scaled by 1/sqrt(d_h)), half 1 -> K tile
+                uint8_t* hi_t = smem + TB_QKP + half * 2 * TB_TILE;
                 uint8_t* lo_t = hi_t + TB_TILE;
-                const float sc = kb_p == 0 ? is_qkv * p.qscale : is_qkv;
-                float v[32];
-                tb_ld32(tl, TM_X + part * 32, TM_X + 128 + part * 32, v);
+                const float sc = half == 0 ? is_qkv * p.qscale : is_qkv;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    float v[32];
+                    tb_ld32(tl, TM_X + half * 64 + c0, TM_X + 128 + half * 64 + c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= sc;
+                    for (int j = 0; j < 32; ++j) v[j] *= sc;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) tb_store8(hi_t, lo_t, row, ch_p + c, v + 8 * c);
+                    for (int c = 0; c < 4; ++c) tb_store8(hi_t, lo_t, row, (c0 >> 3) + c, v + 8 * c);
+                }
             }
             opnd_ready();
             // ---- v projection
@@ -385,13 +356,13 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
                 else load_a128_kb(layer, fc1_row, 0);
             }
             {   // v epilogue: transposed store, V^T[kb = row / 64] = [hi: 64 d rows | lo: 64 d rows] x 64 keys
-                float v[16];
-                tb_ld16(tl, TM_X + part * 16, TM_X + 64 + part * 16, v);
+                float v[32];
+                tb_ld32(tl, TM_X + half * 32, TM_X + 64 + half * 32, v);
                 uint8_t* vt = smem + TB_VO + (row >> 6) * TB_TILE;
                 const int kk = row & 63;                       // key index inside the K-block
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int d = part * 16 + j;
+                for (int j = 0; j < 32; ++j) {
+                    const int d = half * 32 + j;
                     const float val = v[j] * is_qkv;
                     const __half hv = __float2half_rn(val);
                     const __half lv = __float2half_rn((val - __half2float(hv)) * TB_LO);
@@ -413,37 +384,45 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
                 }
                 commit_acc();
             }
-            // ---- masked softmax over the keys of the row's own sequence: this thread's 32 keys [part * 32, +32).  The P tile
-            // holds exp(s - max) UN-normalised; 1 / sum is applied to O afterwards.
+            // ---- masked softmax over the keys of the row's own sequence: this thread's 64 keys [half * 64, +64).  The P tile
+            // holds exp(s - max) UN-normalised; 1 / sum is applied to O afterwards (the two halves' partial sums meet there).
             wait_acc();
-            float p_sum;
             {
                 const int seq = row / p.L, pos = row - seq * p.L;
                 const int frame = p.spf > 0 ? pos / p.spf : 0;
                 // valid keys: the same sequence, and (block-causal) frame(key) <= frame(row)
-                const int k_lo = seq * p.L - part * 32;                          // relative to this thread's first key
+                const int k_lo = seq * p.L - half * 64;                          // relative to this thread's first key
                 const int k_hi = row_ok ? (p.spf > 0 ? k_lo + (frame + 1) * p.spf : k_lo + p.L) : k_lo;     // exclusive
                 constexpr float LOG2E = 1.4426950408889634f;
-                float s0[32];
-                tb_ld32(tl, TM_X + part * 32, TM_X + 128 + part * 32, s0);
+                float s0[32], s1[32];
+                tb_ld32(tl, TM_X + half * 64, TM_X + 128 + half * 64, s0);
+                tb_ld32(tl, TM_X + half * 64 + 32, TM_X + 128 + half * 64 + 32, s1);
                 float mx = -3.0e38f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     s0[j] = (j >= k_lo && j < k_hi) ? s0[j] * LOG2E : -3.0e38f;
-                    mx = fmaxf(mx, s0[j]);
+                    s1[j] = (32 + j >= k_lo && 32 + j < k_hi) ? s1[j] * LOG2E : -3.0e38f;
+                    mx = fmaxf(mx, fmaxf(s0[j], s1[j]));
                 }
-                mx = row_max(mx);
+                s_red[red_buf][half][row] = mx;
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                mx = fmaxf(s_red[red_buf][0][row], s_red[red_buf][1][row]);
+                red_buf ^= 1;
                 float sum = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     s0[j] = s0[j] > -1.0e38f ? exp2f(s0[j] - mx) : 0.f;
-                    sum += s0[j];
+                    s1[j] = s1[j] > -1.0e38f ? exp2f(s1[j] - mx) : 0.f;
+                    sum += s0[j] + s1[j];
                 }
-                uint8_t* hi_t = smem + TB_QKP + kb_p * TB_TILE;
-                uint8_t* lo_t = smem + TB_QKP + (2 + kb_p) * TB_TILE;
+                s_red[red_buf][half][row] = sum;               // read in the O epilogue (ordered by the mbarrier hand-offs in between)
+                uint8_t* hi_t = smem + TB_QKP + half * TB_TILE;
+                uint8_t* lo_t = smem + TB_QKP + (2 + half) * TB_TILE;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) tb_store8(hi_t, lo_t, row, ch_p + c, s0 + c * 8);
-                p_sum = sum;
+                for (int c = 0; c < 4; ++c) {
+                    tb_store8(hi_t, lo_t, row, c, s0 + c * 8);
+                    tb_store8(hi_t, lo_t, row, 4 + c, s1 + c * 8);
+                }
             }
             opnd_ready();
             // ---- O = P v: A = P (two K-blocks of keys), B = V^T[kb] = [hi 64 | lo 64]
@@ -460,18 +439,19 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
                 }
                 commit_acc();
             }
-            p_sum = row_sum(p_sum);                        // the row's softmax denominator, exchanged while the P v MMAs run
             wait_acc();
-            {   // O epilogue: this thread's 16 head features / sum -> O tile (A operand of the output projection)
-                float v[16];
-                tb_ld16(tl, TM_X + part * 16, TM_X + 64 + part * 16, v);
-                const float inv = p_sum > 0.f ? 1.0f / p_sum : 0.f;
+            {   // O epilogue: this thread's 32 head features / sum -> O tile (A operand of the output projection)
+                float v[32];
+                tb_ld32(tl, TM_X + half * 32, TM_X + 64 + half * 32, v);
+                const float sum = s_red[red_buf][0][row] + s_red[red_buf][1][row];
+                red_buf ^= 1;
+                const float inv = sum > 0.f ? 1.0f / sum : 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] *= inv;
+                for (int j = 0; j < 32; ++j) v[j] *= inv;
                 uint8_t* hi_t = smem + TB_VO;
                 uint8_t* lo_t = smem + TB_VO + TB_TILE;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) tb_store8(hi_t, lo_t, row, part * 2 + c, v + 8 * c);
+                for (int c = 0; c < 4; ++c) tb_store8(hi_t, lo_t, row, half * 4 + c, v + 8 * c);
             }
             opnd_ready();
             // ---- Y (+)= O W_o[:, h]^T : A = O tile (TB_VO: hi | lo), B = W1 = [hi 128 | lo 128]
@@ -494,7 +474,7 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
                     if (lane == 0) tc::mbar_arrive(&bar_opnd);      // the next head's projection waits on bar_opnd like every MMA phase:
                 }
             }
-            if (!last) {                                   // ... all 16 warps arrive once (nothing to write), warp 0 did so above
+            if (!last) {                                   // ... all 8 warps arrive once (nothing to write), warp 0 did so above
                 __syncwarp();
                 if (!issuer && lane == 0) tc::mbar_arrive(&bar_opnd);
             }
@@ -511,20 +491,23 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
         }
         wait_acc();
         if (issuer) load_fc2(layer);                       // behind the GELU epilogue
-        {   // fc1 epilogue: + b_1, GELU -> A2 operand
-            uint8_t* hi_t = smem + TB_QKP + kb_p * TB_TILE;
-            uint8_t* lo_t = smem + TB_QKP + (2 + kb_p) * TB_TILE;
-            const float4* b1 = reinterpret_cast<const float4*>(p.b1 + layer * 512 + (int)crank * 128 + part * 32);
-            float v[32];
-            tb_ld32(tl, TM_X + part * 32, TM_X + 128 + part * 32, v);
+        {   // fc1 epilogue: + b_1, GELU -> A2 operand, K-block `half`
+            uint8_t* hi_t = smem + TB_QKP + half * TB_TILE;
+            uint8_t* lo_t = smem + TB_QKP + (2 + half) * TB_TILE;
+            const float4* b1 = reinterpret_cast<const float4*>(p.b1 + layer * 512 + (int)crank * 128 + half * 64);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                float v[32];
+                tb_ld32(tl, TM_X + half * 64 + c0, TM_X + 128 + half * 64 + c0, v);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 bb = __ldg(b1 + c);
-                v[4 * c] = tb_gelu(fmaf(v[4 * c], is_fc1, bb.x)); v[4 * c + 1] = tb_gelu(fmaf(v[4 * c + 1], is_fc1, bb.y));
-                v[4 * c + 2] = tb_gelu(fmaf(v[4 * c + 2], is_fc1, bb.z)); v[4 * c + 3] = tb_gelu(fmaf(v[4 * c + 3], is_fc1, bb.w));
+                for (int c = 0; c < 8; ++c) {
+                    const float4 bb = __ldg(b1 + (c0 >> 2) + c);
+                    v[4 * c] = tb_gelu(fmaf(v[4 * c], is_fc1, bb.x)); v[4 * c + 1] = tb_gelu(fmaf(v[4 * c + 1], is_fc1, bb.y));
+                    v[4 * c + 2] = tb_gelu(fmaf(v[4 * c + 2], is_fc1, bb.z)); v[4 * c + 3] = tb_gelu(fmaf(v[4 * c + 3], is_fc1, bb.w));
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tb_store8(hi_t, lo_t, row, (c0 >> 3) + c, v + 8 * c);
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tb_store8(hi_t, lo_t, row, ch_p + c, v + 8 * c);
         }
         opnd_ready();
         // ---- Y = A2 W_2[:, chunk]^T
@@ -548,9 +531,9 @@ tblock_stack_kernel(const __grid_constant__ CUtensorMap mapA128, const __grid_co
     }
     // write the tile back (rank 0 of the cluster: all four copies are identical)
     if (crank == 0 && row_ok) {
-        float4* dst = reinterpret_cast<float4*>(p.X + (size_t)(row0 + row) * TB_E + part * 32);
+        float4* dst = reinterpret_cast<float4*>(p.X + (size_t)(row0 + row) * TB_E + half * 64);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        for (int j = 0; j < 16; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
     }
     tc::pdl_trigger();
     tc::tc_fence_before();
@@ -614,7 +597,7 @@ extern "C" int ps_tblock_stack_dbg(float* X, int n_seq, int L, int spf, int n_la
     PS_REQUIRE(r == 0, "ps_tblock_stack: cuTensorMapEncodeTiled(WA, 64) failed (%d)", r);
     r = tc::make_tmap_2d_bf16_sw128(&mB, WB, (uint64_t)n_layers * 2 * TB_E, (uint64_t)(heads * 64 + 512), 128, 64);
     PS_REQUIRE(r == 0, "ps_tblock_stack: cuTensorMapEncodeTiled(WB) failed (%d)", r);
-    const size_t smem = TB_SMEM + TB_PARTS * TB_M * 4 + 64;
+    const size_t smem = TB_SMEM + 2 * 2 * TB_M * 4 + 64;
     static PsSmemConfig smem_cfg = {};
     PS_CUDA(ps_ensure_smem(tblock_stack_kernel, smem, smem_cfg));
     cudaLaunchConfig_t cfg = {};
