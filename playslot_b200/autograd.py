@@ -25,8 +25,29 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# Set (only) by the training steps of playslot_b200.train around their loss.backward(): the Linear backward may then add its
+# weight / bias gradients straight into the GradientBucket views.  Off everywhere else, so torch.autograd.grad(...) and
+# hand-written loops that expect the gradients to be RETURNED keep plain autograd semantics.
+ACCUMULATE_INTO_BUCKET = False
+
+
+class accumulate_into_bucket:
+    """ context manager: enable in-place accumulation of Linear weight gradients into the attached GradientBucket """
+
+    def __enter__(self):
+        global ACCUMULATE_INTO_BUCKET
+        self._old, ACCUMULATE_INTO_BUCKET = ACCUMULATE_INTO_BUCKET, True
+
+    def __exit__(self, *exc):
+        global ACCUMULATE_INTO_BUCKET
+        ACCUMULATE_INTO_BUCKET = self._old
+        return False
+
+
 def _bucket_view(param):
     """ the flat-bucket view train.GradientBucket.attach() installed as `param.grad` (a leaf Parameter still bound to it), or None """
+    if not ACCUMULATE_INTO_BUCKET:
+        return None
     v = getattr(param, "_ps_bucket_grad", None)
     if v is None or not param.is_leaf or param.grad is None or param.grad.data_ptr() != v.data_ptr():
         return None

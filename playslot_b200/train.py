@@ -109,7 +109,9 @@ def train_step(savi, predictor, optimizer, videos, num_seed, num_preds, bucket=N
     else:
         optimizer.zero_grad(set_to_none=True)
     loss, terms, _ = forward_loss(savi, predictor, videos, num_seed, num_preds, **init_kwargs)
-    loss.backward()
+    from . import autograd as AG
+    with AG.accumulate_into_bucket():           # (a no-op without an attached bucket)
+        loss.backward()
     if bucket is not None:
         bucket.all_reduce_mean(local_count=videos.shape[0])
     if clip_gradient is not None:
@@ -212,7 +214,8 @@ class GraphedTrainStep:
             old_mode, AG.TRAIN_LINEAR_MODE = AG.TRAIN_LINEAR_MODE, linear_mode     # arithmetic of the differentiable Linears
             try:
                 loss, terms, _ = forward_loss(savi, predictor, self.video, num_seed, num_preds)
-                loss.backward()
+                with AG.accumulate_into_bucket():
+                    loss.backward()
             finally:
                 AG.TRAIN_LINEAR_MODE = old_mode
             if self.bucket is not None:
@@ -288,7 +291,9 @@ def savi_train_step(savi, optimizer, videos, bucket=None, clip_gradient=0.05, **
     else:
         optimizer.zero_grad(set_to_none=True)
     loss, out = savi_forward_loss(savi, videos, **init_kwargs)
-    loss.backward()
+    from . import autograd as AG
+    with AG.accumulate_into_bucket():
+        loss.backward()
     if bucket is not None:
         bucket.all_reduce_mean(local_count=videos.shape[0])
     if clip_gradient is not None:
