@@ -205,9 +205,10 @@ struct MhaParams {
     uint16_t* out_lo;      // instead of fp32 `out`
     int n_seq, L, H, dh, spf;
     float scale;
+    int rows_per_chunk;    // row-streaming kernel: query rows per CTA (blockIdx.z selects the chunk; L when the grid has one chunk)
 };
 
-// One CTA per (sequence, head).  K and V are staged in shared memory; every warp processes FOUR query rows at a time so that
+// One CTA per (sequence, head, chunk of query rows).  K and V are staged in shared memory; every warp processes FOUR query rows at a time so that
 // each shared-memory read of a key / value element feeds four FMAs (the kernel is LDS-bound otherwise): the four queries are
 // stored interleaved [d][4] and the four probability rows [j][4], both read as one broadcast LDS.128.
 __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
@@ -220,7 +221,13 @@ __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
     float* Qs = Ps + 4 * L * 4;          // [4 warps][dh][4]
     const float* base = p.qkv + (size_t)seq * L * p.ld;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int idx = tid; idx < L * dh; idx += 128) {
+    // Long sequences on few (sequence, head) pairs -- the 160-token windows of the 16-slot configuration at 8 videos per GPU --
+    // split the query rows over blockIdx.z so that the launch fills the GPU.  With the block-causal mask the rows of a chunk only
+    // see the keys up to the chunk's last frame: the keys behind it would be filled with -1e9 and contribute exp(.) = 0 exactly,
+    // so they are neither staged nor visited (bit-identical results).
+    const int r_begin = blockIdx.z * p.rows_per_chunk, r_end = min(L, r_begin + p.rows_per_chunk);
+    const int Lk = p.spf > 0 ? min(L, ((r_end - 1) / p.spf + 1) * p.spf) : L;      // keys any row of this chunk attends to
+    for (int idx = tid; idx < Lk * dh; idx += 128) {
         const int j = idx / dh, d = idx - j * dh;
         Ks[j * (dh + 1) + d] = base[(size_t)j * p.ld + inner + h * dh + d];
         Vs[j * dh + d] = base[(size_t)j * p.ld + 2 * inner + h * dh + d];
@@ -228,15 +235,15 @@ __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
     __syncthreads();
     float* Pw = Ps + w * L * 4;
     float* Qw = Qs + w * dh * 4;
-    for (int i0 = w * 4; i0 < L; i0 += 16) {
+    for (int i0 = r_begin + w * 4; i0 < r_end; i0 += 16) {
         // the four query rows of this pass, interleaved; rows past the end are zero (their results are not stored)
         for (int idx = lane; idx < dh * 4; idx += 32) {
             const int d = idx >> 2, r = idx & 3;
-            Qw[idx] = (i0 + r < L) ? base[(size_t)(i0 + r) * p.ld + h * dh + d] : 0.f;
+            Qw[idx] = (i0 + r < r_end) ? base[(size_t)(i0 + r) * p.ld + h * dh + d] : 0.f;
         }
         __syncwarp();
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int j = lane; j < L; j += 32) {
+        for (int j = lane; j < Lk; j += 32) {
             const float* kr = Ks + j * (dh + 1);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
@@ -256,7 +263,7 @@ __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int r = 0; r < 4; ++r) mx[r] = warp_max(mx[r]);
-        for (int j = lane; j < L; j += 32) {
+        for (int j = lane; j < Lk; j += 32) {
             float4 e = *reinterpret_cast<const float4*>(Pw + j * 4);
             e.x = expf(e.x - mx[0]); e.y = expf(e.y - mx[1]); e.z = expf(e.z - mx[2]); e.w = expf(e.w - mx[3]);
             sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
@@ -269,7 +276,7 @@ __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
         for (int d = lane; d < dh; d += 32) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
-            for (int j = 0; j < L; ++j) {
+            for (int j = 0; j < Lk; ++j) {
                 const float v = Vs[j * dh + d];
                 const float4 pr = *reinterpret_cast<const float4*>(Pw + j * 4);
                 a0 = fmaf(pr.x * inv[0], v, a0); a1 = fmaf(pr.y * inv[1], v, a1);
@@ -278,7 +285,7 @@ __global__ __launch_bounds__(128) void mha_kernel(MhaParams p) {
             const float acc[4] = {a0, a1, a2, a3};
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                if (i0 + r < L) {
+                if (i0 + r < r_end) {
                     const size_t oi = ((size_t)seq * L + i0 + r) * p.ldo + h * dh + d;
                     p.out[oi] = p.res ? acc[r] + p.res[oi] : acc[r];
                 }
@@ -472,7 +479,7 @@ static int mha_run(const float* qkv, int ld, const float* res, float* out, void*
     p.qkv = qkv; p.ld = ld; p.res = res; p.out = out; p.ldo = ldo;
     p.out_hi = reinterpret_cast<uint16_t*>(out_planes);
     p.out_lo = p.out_hi ? p.out_hi + (size_t)plane_rows * ldo : nullptr; p.n_seq = n_seq; p.L = L; p.H = n_heads; p.dh = head_dim;
-    p.spf = slots_per_frame; p.scale = 1.0f / sqrtf((float)head_dim);
+    p.spf = slots_per_frame; p.scale = 1.0f / sqrtf((float)head_dim); p.rows_per_chunk = L;
     PS_REQUIRE(n_heads <= 65535, "ps_mha: too many heads");
     const bool vec = head_dim % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && ps_aligned16(qkv) && (out_planes ? ps_aligned16(out_planes) : ps_aligned16(out)) &&
                      (res == nullptr || ps_aligned16(res));
@@ -498,7 +505,17 @@ static int mha_run(const float* qkv, int ld, const float* res, float* out, void*
         PS_REQUIRE(smem <= 200 * 1024, "ps_mha: sequence of %d tokens x head_dim %d does not fit in shared memory", L, head_dim);
         static PsSmemConfig smem_cfg = {};
         if (smem > 48 * 1024) PS_CUDA(ps_ensure_smem(mha_kernel, smem, smem_cfg, 200 * 1024));
-        mha_kernel<<<dim3(n_seq, n_heads), 128, smem, (cudaStream_t)stream>>>(p);
+        // few (sequence, head) pairs with many rows each: split the query rows so that about two CTAs per SM exist
+        int chunks = 1;
+        const long long pairs = (long long)n_seq * n_heads;
+        if (L >= 32 && pairs < 148) {
+            chunks = (int)((2 * 148 + pairs - 1) / pairs);
+            if (chunks > (L + 15) / 16) chunks = (L + 15) / 16;
+            if (chunks < 1) chunks = 1;
+        }
+        p.rows_per_chunk = ((L + chunks - 1) / chunks + 3) / 4 * 4;
+        chunks = (L + p.rows_per_chunk - 1) / p.rows_per_chunk;
+        mha_kernel<<<dim3(n_seq, n_heads, chunks), 128, smem, (cudaStream_t)stream>>>(p);
     }
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();

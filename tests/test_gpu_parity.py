@@ -88,7 +88,8 @@ def test_linear(M, N, K, mode, lmode, tol, linear_mode_guard):
     check(f"linear[{mode}/{lmode}]", y, ref.float(), TOL)
 
 
-@pytest.mark.parametrize("n_seq,L,H,dh,spf", [(3, 9, 4, 64, 0), (2, 64, 8, 64, 8), (5, 8, 4, 32, 0), (2, 160, 8, 64, 16), (4, 30, 8, 64, 6)])
+@pytest.mark.parametrize("n_seq,L,H,dh,spf", [(3, 9, 4, 64, 0), (2, 64, 8, 64, 8), (5, 8, 4, 32, 0), (2, 160, 8, 64, 16), (4, 30, 8, 64, 6),
+                                                (8, 144, 8, 64, 16), (1, 160, 4, 32, 0), (3, 200, 2, 64, 8)])
 def test_mha(n_seq, L, H, dh, spf):
     from playslot_b200 import ops
     inner = H * dh
