@@ -218,8 +218,9 @@ int ps_conv5x5_tc(const void* act_in, const void* w_tc, const float* bias, float
 
 /* ps_dec_composite on the tensor cores: the 3x3 convolution as a 9-tap implicit GEMM over padded NHWC split planes
  * (act_in: the last 5x5 block's output for M*S slot images, precision 3), all S slots of a 128-position tile accumulated
- * side by side in TMEM, slot softmax and compositing in the epilogue.  w_tc: 16-bit [9 taps][16 rows: 4 hi, 4 zero, 4 lo,
- * 4 zero][64 cin] holding w * w_scale. */
+ * side by side in TMEM, slot softmax and compositing in the epilogue.  The three taps of a filter row share one MMA (their
+ * weights side by side in N); the epilogue adds the column-shifted partial sums of neighbouring positions.  w_tc: 16-bit
+ * [3 filter rows][32 rows: hi (kx0 o0-3 | kx1 o0-3 | kx2 o0-3 | 4 zero), lo (same)][64 cin] holding w * w_scale. */
 int ps_dec_composite_tc(const void* act_in, const void* w_tc, float w_scale, const float* bias, float* recon, float* recons,
                         float* masks, int M, int S, int H, int W, void* stream);
 

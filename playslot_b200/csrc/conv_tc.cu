@@ -579,10 +579,17 @@ extern "C" int ps_nchw_to_split(const float* x, void* act_out, int n_img, int H,
 // ================================================================================================
 // Final decoder stage on the tensor cores: Conv2d(64, 4, 3, padding=1) of every slot image + softmax of the alpha channel
 // over the slot axis + compositing (src/models/SAVi.py:226-234, EncodersDecoders/decoders.py:103-111).
-// Same padded-linear implicit GEMM as above with 9 taps; the 4 output channels are padded to 8, [w_hi | w_lo] form one
-// N = 16 operand, so slot s owns 16 TMEM columns (D0 | D1).  One work item = 128 positions of one frame: the S slot
-// images stream through a double-buffered activation region, their accumulators sit side by side in TMEM, and the
-// epilogue thread of a position sees all S slots: bias, slot softmax, recons / masks / recon written once.
+// Padded-linear implicit GEMM like above, but an MMA with 4 output channels reads a whole 4 KB activation operand for
+// 128 x 8 x 16 products: nine such taps made the kernel shared-memory-operand bound (72 MMAs = 288 KB of operand reads per slot
+// and tile, 2.4 ms per step).  The three taps of a filter ROW therefore share one MMA: their weights sit side by side in the B
+// operand (N = 32: [hi: kx0 o0-3 | kx1 | kx2 | pad ; lo: same]) and the A window is shifted by whole image rows only,
+//     Z_kx[q] = sum_ky W[ky][kx] . A[q + (ky - 1) Wp]                      (24 MMAs per slot and tile)
+//     out[p]  = Z_0[p - 1] + Z_1[p] + Z_2[p + 1]                           (epilogue: neighbouring TMEM lanes = neighbouring positions)
+// The horizontal shift happens between the epilogue threads: warp shuffles inside a warp, a 4 KB shared-memory exchange across
+// the three warp boundaries; rows 0 and 127 of a tile have no complete neighbourhood, so tiles advance by 126 positions.
+// One work item = one tile of one frame: the S slot images stream through a double-buffered activation region, their
+// accumulators (32 columns per slot) sit side by side in TMEM, and the epilogue thread of a position sees all S slots: bias,
+// slot softmax, recons / masks / recon written once.
 // ================================================================================================
 namespace {
 
@@ -596,20 +603,23 @@ struct CompTcParams {
     float out_scale;
 };
 
-constexpr int CT_WBYTES = 9 * 16 * ROWB;     // 9 taps x (8 hi + 8 lo rows) x 64 cin fp16
+constexpr int CT_WBYTES = 3 * 32 * ROWB;     // 3 filter rows x (16 hi + 16 lo rows) x 64 cin fp16
+constexpr int CT_STRIDE = TILE_M - 2;        // useful positions per tile
 
-template <int SPAD>      // slots padded to 8 or 16 (TMEM columns = 16 per slot)
+template <int SPAD>      // slots padded to 8 or 16 (TMEM columns = 32 per slot)
 __global__ void __launch_bounds__(192, 1)
 dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                         const __grid_constant__ CUtensorMap mapW, const CompTcParams p) {
-    constexpr uint32_t ACC_COLS = 16 * SPAD;
+    constexpr uint32_t ACC_COLS = 32 * SPAD;
+    constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;    // 16 slots fill the 512 TMEM columns once: no accumulator double buffer
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = p.a_rows * ROWB;
-    uint8_t* sW = smem;                                    // 18 KB
+    uint8_t* sW = smem;                                    // 12 KB
     uint8_t* sA0 = smem + ((CT_WBYTES + 1023) & ~1023);    // nbuf x [hi | lo] regions
     __shared__ uint64_t bar_w, bar_afull[2], bar_aempty[2], bar_accfull[2], bar_accempty[2];
     __shared__ uint32_t tmem_base;
+    __shared__ __align__(16) float s_edge[2][4][2][SPAD][4];             // [item parity][lane quarter][0: Z_0 of lane 31 | 1: Z_2 of lane 0][slot][o]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform (see conv5x5_tc_kernel)
     const int n_items = p.M * p.tiles_per_img;
@@ -623,7 +633,7 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
         }
         tc::fence_mbar_init();
     }
-    if (warp == 1) tc::tmem_alloc(&tmem_base, 2 * ACC_COLS);
+    if (warp == 1) tc::tmem_alloc(&tmem_base, NACC * ACC_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -637,7 +647,7 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
             int q = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int m = it / p.tiles_per_img, tile = it - m * p.tiles_per_img;
-                const int p0 = 2 * p.Wp + tile * TILE_M;
+                const int p0 = 2 * p.Wp + tile * CT_STRIDE - 1;               // position of the tile's row 0
                 for (int s = 0; s < S; ++s, ++q) {
                     const int buf = q % NBUF;
                     if (q >= NBUF) tc::mbar_wait(&bar_aempty[buf], ((q / NBUF) - 1) & 1);
@@ -656,34 +666,34 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
         // run-time buffer count); one elected lane issues -- same reasoning as in conv5x5_tc_kernel
         const bool leader = tc::elect_one();
         {
-            const uint32_t idesc16 = tc::umma_idesc_f16(TILE_M, 16), idesc8 = tc::umma_idesc_f16(TILE_M, 8);
+            const uint32_t idesc32 = tc::umma_idesc_f16(TILE_M, 32), idesc16 = tc::umma_idesc_f16(TILE_M, 16);
             const uint64_t dW = tc::umma_desc_sw128(tc::smem_u32(sW), 1024, 0);
             const uint64_t dA = tc::umma_desc_sw128(tc::smem_u32(sA0) + (uint32_t)p.halo * ROWB, 1024, 0);
             const uint64_t buf_units = (uint64_t)((2 * a_bytes) / 16), lo_units = (uint64_t)(a_bytes / 16);
-            const int row_step = (p.Wp - 3) * (ROWB / 16);
+            const int row_step = p.Wp * (ROWB / 16);
             tc::mbar_wait(&bar_w, 0);
             int buf = 0;
             uint32_t bph = 0;
             int i = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
-                const int ab = i & 1;
-                if (i >= 2) tc::mbar_wait(&bar_accempty[ab], ((i >> 1) - 1) & 1);
+                const int ab = NACC == 2 ? (i & 1) : 0;
+                if (i >= NACC) tc::mbar_wait(&bar_accempty[ab], (NACC == 2 ? ((i >> 1) - 1) : (i - 1)) & 1);
                 for (int s = 0; s < S; ++s) {
                     tc::mbar_wait(&bar_afull[buf], bph);
                     tc::tc_fence_after();
                     const uint64_t a_hi0 = dA + (uint64_t)buf * buf_units;
-                    const uint32_t acc = tm + ab * ACC_COLS + s * 16;
-                    int a_off = (-p.Wp - 1) * (ROWB / 16);                       // tap (0, 0) shift, 16-byte units
+                    const uint32_t acc = tm + ab * ACC_COLS + s * 32;
+                    int a_off = -row_step;                                       // filter row 0: one image row up, 16-byte units
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int ky = 0; ky < 3; ++ky) {
                         const uint64_t a_hi = a_hi0 + (uint64_t)(int64_t)a_off;
 #pragma unroll
                         for (int k = 0; k < C / 16; ++k) {
-                            const uint64_t bd = dW + (uint64_t)((tap * 16 * ROWB + k * 32) / 16);
-                            if (leader) tc::umma_bf16(acc, a_hi + (uint64_t)(k * 2), bd, idesc16, (tap | k) ? 1u : 0u);   // D0 | D1 += A_hi [w_hi | w_lo]
-                            if (leader) tc::umma_bf16(acc + 8, a_hi + lo_units + (uint64_t)(k * 2), bd, idesc8, 1u);        // D1 += A_lo w_hi
+                            const uint64_t bd = dW + (uint64_t)((ky * 32 * ROWB + k * 32) / 16);
+                            if (leader) tc::umma_bf16(acc, a_hi + (uint64_t)(k * 2), bd, idesc32, (ky | k) ? 1u : 0u);      // D0 | D1 += A_hi [w_hi | w_lo]
+                            if (leader) tc::umma_bf16(acc + 16, a_hi + lo_units + (uint64_t)(k * 2), bd, idesc16, 1u);       // D1 += A_lo w_hi
                         }
-                        a_off += (tap % 3 == 2) ? row_step + ROWB / 16 : ROWB / 16;
+                        a_off += row_step;
                     }
                     if (leader) tc::umma_commit(&bar_aempty[buf]);
                     if (++buf == NBUF) { buf = 0; bph ^= 1u; }
@@ -693,16 +703,18 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
         }
     } else {
         const int quad = warp & 3;
+        const int r = quad * 32 + lane;                    // row of the tile == TMEM lane
         const int HW = p.H * p.W;
         const float b0 = p.bias[0], b1 = p.bias[1], b2 = p.bias[2], b3 = p.bias[3];
         int i = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
-            const int ab = i & 1;
+            const int ab = NACC == 2 ? (i & 1) : 0;
+            const int par = i & 1;
             const int m = it / p.tiles_per_img, tile = it - m * p.tiles_per_img;
-            const int pp = 2 * p.Wp + tile * TILE_M + quad * 32 + lane;
+            const int pp = 2 * p.Wp + tile * CT_STRIDE - 1 + r;
             const int yp = pp / p.Wp, xp = pp - yp * p.Wp;
-            const bool interior = yp < p.H + 2 && xp >= 2 && xp < p.W + 2;
-            tc::mbar_wait(&bar_accfull[ab], (i >> 1) & 1);
+            const bool interior = r >= 1 && r <= CT_STRIDE && yp < p.H + 2 && xp >= 2 && xp < p.W + 2;
+            tc::mbar_wait(&bar_accfull[ab], (NACC == 2 ? (i >> 1) : i) & 1);
             __syncwarp();
             tc::tc_fence_after();
             float o[SPAD][4];
@@ -710,18 +722,48 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
 #pragma unroll
             for (int s = 0; s < SPAD; ++s) {
                 if (s < S) {
-                    float v[16];
-                    tc::tmem_ld_32x16(tb + s * 16, v);
-                    o[s][0] = fmaf(fmaf(v[8], 1.0f / LO_SCALE, v[0]), p.out_scale, b0);
-                    o[s][1] = fmaf(fmaf(v[9], 1.0f / LO_SCALE, v[1]), p.out_scale, b1);
-                    o[s][2] = fmaf(fmaf(v[10], 1.0f / LO_SCALE, v[2]), p.out_scale, b2);
-                    o[s][3] = fmaf(fmaf(v[11], 1.0f / LO_SCALE, v[3]), p.out_scale, b3);
+                    float v[32];
+                    tc::tmem_ld_32x32(tb + s * 32, v);
+                    float z[12];                               // z[kx * 4 + o] = Z_kx[this position][o]
+#pragma unroll
+                    for (int t = 0; t < 12; ++t) z[t] = fmaf(v[16 + t], 1.0f / LO_SCALE, v[t]);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float up = __shfl_up_sync(0xffffffffu, z[c], 1);          // Z_0 of the position to the left
+                        const float dn = __shfl_down_sync(0xffffffffu, z[8 + c], 1);    // Z_2 of the position to the right
+                        o[s][c] = z[4 + c] + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
+                    }
+                    if (lane == 31) *reinterpret_cast<float4*>(s_edge[par][quad][0][s]) = make_float4(z[0], z[1], z[2], z[3]);
+                    if (lane == 0) *reinterpret_cast<float4*>(s_edge[par][quad][1][s]) = make_float4(z[8], z[9], z[10], z[11]);
                 }
             }
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar_accempty[ab]);
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");       // the four epilogue warps: edge values are in shared memory
+            if (lane == 0 && quad > 0) {
+#pragma unroll
+                for (int s = 0; s < SPAD; ++s)
+                    if (s < S) {
+                        const float4 e = *reinterpret_cast<const float4*>(s_edge[par][quad - 1][0][s]);
+                        o[s][0] += e.x; o[s][1] += e.y; o[s][2] += e.z; o[s][3] += e.w;
+                    }
+            }
+            if (lane == 31 && quad < 3) {
+#pragma unroll
+                for (int s = 0; s < SPAD; ++s)
+                    if (s < S) {
+                        const float4 e = *reinterpret_cast<const float4*>(s_edge[par][quad + 1][1][s]);
+                        o[s][0] += e.x; o[s][1] += e.y; o[s][2] += e.z; o[s][3] += e.w;
+                    }
+            }
             if (!interior) continue;
+#pragma unroll
+            for (int s = 0; s < SPAD; ++s)
+                if (s < S) {
+                    o[s][0] = fmaf(o[s][0], p.out_scale, b0); o[s][1] = fmaf(o[s][1], p.out_scale, b1);
+                    o[s][2] = fmaf(o[s][2], p.out_scale, b2); o[s][3] = fmaf(o[s][3], p.out_scale, b3);
+                }
             float mx = -INFINITY;
 #pragma unroll
             for (int s = 0; s < SPAD; ++s)
@@ -751,7 +793,7 @@ dec_composite_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __gri
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tm, 2 * ACC_COLS);
+    if (warp == 1) tc::tmem_dealloc(tm, NACC * ACC_COLS);
 }
 
 template <int SPAD>
@@ -781,9 +823,9 @@ extern "C" int ps_dec_composite_tc(const void* act_in, const void* w_tc, float w
     CompTcParams p;
     p.bias = bias; p.recon = recon; p.recons = recons; p.masks = masks;
     p.M = M; p.S = S; p.H = H; p.W = W; p.Wp = Wp; p.Hp = Hp;
-    p.tiles_per_img = (H * Wp + TILE_M - 1) / TILE_M;
-    p.halo = Wp + 1;
-    p.a_rows = ((TILE_M + 2 * p.halo) + 63) / 64 * 64;
+    p.tiles_per_img = (H * Wp + CT_STRIDE - 1) / CT_STRIDE;
+    p.halo = Wp;                                   // whole image rows only: the +-1 column shift happens in the epilogue
+    p.a_rows = ((TILE_M + 2 * p.halo) + ABOX - 1) / ABOX * ABOX;
     const long long room = 227ll * 1024 - 1024 - ((CT_WBYTES + 1023) & ~1023);
     p.nbuf = (2ll * 2 * p.a_rows * ROWB <= room) ? 2 : 1;
     PS_REQUIRE(2ll * p.a_rows * ROWB <= room, "ps_dec_composite_tc: image width %d does not fit the shared-memory staging", W);
@@ -799,7 +841,7 @@ extern "C" int ps_dec_composite_tc(const void* act_in, const void* w_tc, float w
     PS_REQUIRE(r == 0, "ps_dec_composite_tc: cuTensorMapEncodeTiled(A_hi) failed (%d)", r);
     r = tc::make_tmap_2d_bf16_sw128(&mA_lo, in_hi + P * C, (uint64_t)P, C, ABOX, C);
     PS_REQUIRE(r == 0, "ps_dec_composite_tc: cuTensorMapEncodeTiled(A_lo) failed (%d)", r);
-    r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 9ull * 16, C, 9 * 16, C);
+    r = tc::make_tmap_2d_bf16_sw128(&mW, w_tc, 3ull * 32, C, 3 * 32, C);
     PS_REQUIRE(r == 0, "ps_dec_composite_tc: cuTensorMapEncodeTiled(W) failed (%d)", r);
     cudaStream_t st = (cudaStream_t)stream;
     return S <= 8 ? launch_comp_tc<8>(mA_hi, mA_lo, mW, p, st) : launch_comp_tc<16>(mA_hi, mA_lo, mW, p, st);

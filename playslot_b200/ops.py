@@ -528,18 +528,19 @@ def dec_composite(h, w_packed, bias, M, S):
 
 
 def pack_final_conv_tc(w):
-    """ final decoder conv weight (4, 64, 3, 3) -> (int16 (9 taps, 16 rows [4 hi | 4 zero | 4 lo | 4 zero], 64 cin), w_scale) """
+    """ final decoder conv weight (4, 64, 3, 3) -> (int16 (3 filter rows, 32 rows [hi: kx0 o0-3 | kx1 o0-3 | kx2 o0-3 | 4 zero; lo: same],
+    64 cin), w_scale): the three taps of a filter row form one N = 32 operand of ps_dec_composite_tc """
     Cout, Cin, K, _ = w.shape
     assert (Cout, Cin, K) == (4, 64, 3), "the tensor-core compositing kernel covers the 64 -> 4 channel 3x3 convolution"
-    wt = w.detach().float().permute(2, 3, 0, 1).reshape(9, 4, 64)
+    wt = w.detach().float().permute(2, 3, 0, 1).reshape(3, 12, 64)          # [ky][kx * 4 + o][cin]
     amax = float(wt.abs().max())
     scale = 1.0 if amax == 0.0 else 2.0 ** (-round(math.log2(amax)))
     wt = wt * scale
     h = wt.to(torch.float16)
     lo = ((wt - h.float()) * TC_LO_SCALE).to(torch.float16)
-    out = torch.zeros(9, 16, 64, device=w.device, dtype=torch.float16)
-    out[:, 0:4] = h
-    out[:, 8:12] = lo
+    out = torch.zeros(3, 32, 64, device=w.device, dtype=torch.float16)
+    out[:, 0:12] = h
+    out[:, 16:28] = lo
     return out.view(torch.int16).contiguous(), scale
 
 
