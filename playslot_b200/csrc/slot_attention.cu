@@ -514,63 +514,95 @@ struct SaUpd2Params {
     int do_update, do_prep;
 };
 
-// partial[(ks*N + o)*4 + r] = sum_{k in slice ks} Wt[k*ld + o] * in[k*4 + r]   for all (o, ks) tasks
-template <int KS>
+// partial[(ks*N + o)*R + r] = sum_{k in slice ks} Wt[k*ld + o] * in[k*R + r]   for all (o, ks) tasks
+template <int KS, int R>
 __device__ __forceinline__ void su2_matvec(const float* __restrict__ Wt, int ld, int K, int N, const float* in,
                                            float* part, int tid) {
     const int kper = K / KS;
     for (int task = tid; task < N * KS; task += SU2_THREADS) {
         const int o = task % N, ks = task / N;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
         for (int k0 = ks * kper; k0 < (ks + 1) * kper; k0 += 32) {
             float w[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) w[j] = __ldg(Wt + (size_t)(k0 + j) * ld + o);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float4 x = *reinterpret_cast<const float4*>(in + (k0 + j) * 4);
-                acc[0] = fmaf(w[j], x.x, acc[0]); acc[1] = fmaf(w[j], x.y, acc[1]);
-                acc[2] = fmaf(w[j], x.z, acc[2]); acc[3] = fmaf(w[j], x.w, acc[3]);
+#pragma unroll
+                for (int r4 = 0; r4 < R; r4 += 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(in + (k0 + j) * R + r4);
+                    acc[r4] = fmaf(w[j], x.x, acc[r4]); acc[r4 + 1] = fmaf(w[j], x.y, acc[r4 + 1]);
+                    acc[r4 + 2] = fmaf(w[j], x.z, acc[r4 + 2]); acc[r4 + 3] = fmaf(w[j], x.w, acc[r4 + 3]);
+                }
             }
         }
-        *reinterpret_cast<float4*>(part + (size_t)task * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+        for (int r4 = 0; r4 < R; r4 += 4)
+            *reinterpret_cast<float4*>(part + (size_t)task * R + r4) = make_float4(acc[r4], acc[r4 + 1], acc[r4 + 2], acc[r4 + 3]);
     }
 }
 
+template <int R>
 __device__ __forceinline__ float su2_sum(const float* part, int N, int KS, int o, int r) {
     float v = 0.f;
-    for (int ks = 0; ks < KS; ++ks) v += part[(size_t)(ks * N + o) * 4 + r];
+    for (int ks = 0; ks < KS; ++ks) v += part[(size_t)(ks * N + o) * R + r];
     return v;
 }
 
+// LayerNorm of the R rows stored as in[d*R + r] (d < 128) -> out (same layout); warps 0..R-1 work
+template <int R>
+__device__ __forceinline__ void su2_layernorm(const float* in, float* out, const float* g, const float* b,
+                                              float eps, int warp, int lane) {
+    if (warp < R) {
+        float v[4], s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] = in[(lane + 32 * i) * R + warp]; s += v[i]; }
+        const float mean = warp_sum(s) * (1.0f / SA_D);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float d = v[i] - mean; ss = fmaf(d, d, ss); }
+        const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / SA_D) + eps);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int d = lane + 32 * i;
+            out[d * R + warp] = (v[i] - mean) * rstd * g[d] + b[d];
+        }
+    }
+}
+
+// R slot rows of one frame per CTA (4, or 8 for the 5- and 6-slot configurations: see ps_sa_update2).
+template <int R>
 __global__ __launch_bounds__(SU2_THREADS) void sa_update2_kernel(SaUpd2Params p) {
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // PDL: the streaming pass that follows may start its feature loads (see slot_attention_tc.cu)
-    __shared__ __align__(16) float s_h[SA_D * 4];            // hidden state / new slots, [d][r]
-    __shared__ __align__(16) float s_u[SA_D * 4];            // normalised updates / LayerNorm outputs
-    __shared__ __align__(16) float s_hid[512 * 4];           // MLP hidden
-    __shared__ __align__(16) float s_p0[2 * 384 * 4];        // mat-vec partials
-    __shared__ __align__(16) float s_p1[2 * 384 * 4];
-    __shared__ float s_rs[4];
+    extern __shared__ __align__(16) float su2_smem[];
+    float* s_h = su2_smem;                        // [128][R] hidden state / new slots, [d][r]
+    float* s_u = s_h + SA_D * R;                  // [128][R] normalised updates / LayerNorm outputs
+    float* s_hid = s_u + SA_D * R;                // [512][R] MLP hidden
+    float* s_p0 = s_hid + 512 * R;                // [2 * 384][R] mat-vec partials
+    float* s_p1 = s_p0 + 2 * 384 * R;
+    __shared__ float s_rs[R];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y, r0 = blockIdx.x * 4;
+    const int b = blockIdx.y, r0 = blockIdx.x * R;
     const int S = p.S;
-    const int nr = min(4, S - r0);
+    const int nr = min(R, S - r0);
 
-    for (int idx = tid; idx < SA_D * 4; idx += SU2_THREADS) {
+    for (int idx = tid; idx < SA_D * R; idx += SU2_THREADS) {
         const int r = idx / SA_D, d = idx - r * SA_D;
-        s_h[d * 4 + r] = (r < nr) ? p.slots_in[((size_t)b * S + r0 + r) * SA_D + d] : 0.f;
+        s_h[d * R + r] = (r < nr) ? p.slots_in[((size_t)b * S + r0 + r) * SA_D + d] : 0.f;
     }
     if (p.do_update) {
         const int pstride = S * SA_D + S;
         const float* pb = p.partial + (size_t)b * p.CH * pstride;
-        if (tid < 4) {
+        if (tid < R) {
             float v = 0.f;
             if (tid < nr)
                 for (int c = 0; c < p.CH; ++c) v += pb[(size_t)c * pstride + S * SA_D + r0 + tid];
             s_rs[tid] = v;
         }
         __syncthreads();
-        for (int idx = tid; idx < SA_D * 4; idx += SU2_THREADS) {
+        for (int idx = tid; idx < SA_D * R; idx += SU2_THREADS) {
             const int r = idx / SA_D, c = idx - r * SA_D;
             float v = 0.f;
             if (r < nr) {
@@ -579,38 +611,38 @@ __global__ __launch_bounds__(SU2_THREADS) void sa_update2_kernel(SaUpd2Params p)
                 const float rs = s_rs[r];
                 v = (p.ln_in_g[c] * u + p.ln_in_b[c] * rs) / rs;
             }
-            s_u[c * 4 + r] = v;
+            s_u[c * R + r] = v;
         }
         __syncthreads();
         // GRU gates (gate order r, z, n): gi = W_iv u + b_ih, gh = W_hh h + b_hh
-        su2_matvec<2>(p.WivT, 3 * SA_D, SA_D, 3 * SA_D, s_u, s_p0, tid);
-        su2_matvec<2>(p.WhhT, 3 * SA_D, SA_D, 3 * SA_D, s_h, s_p1, tid);
+        su2_matvec<2, R>(p.WivT, 3 * SA_D, SA_D, 3 * SA_D, s_u, s_p0, tid);
+        su2_matvec<2, R>(p.WhhT, 3 * SA_D, SA_D, 3 * SA_D, s_h, s_p1, tid);
         __syncthreads();
-        if (tid < SA_D * 4) {
-            const int d = tid >> 2, r = tid & 3;
-            const float gir = su2_sum(s_p0, 384, 2, d, r) + p.b_ih[d], ghr = su2_sum(s_p1, 384, 2, d, r) + p.b_hh[d];
-            const float giz = su2_sum(s_p0, 384, 2, SA_D + d, r) + p.b_ih[SA_D + d], ghz = su2_sum(s_p1, 384, 2, SA_D + d, r) + p.b_hh[SA_D + d];
-            const float gin = su2_sum(s_p0, 384, 2, 2 * SA_D + d, r) + p.b_ih[2 * SA_D + d], ghn = su2_sum(s_p1, 384, 2, 2 * SA_D + d, r) + p.b_hh[2 * SA_D + d];
+        for (int idx = tid; idx < SA_D * R; idx += SU2_THREADS) {
+            const int d = idx / R, r = idx - d * R;
+            const float gir = su2_sum<R>(s_p0, 384, 2, d, r) + p.b_ih[d], ghr = su2_sum<R>(s_p1, 384, 2, d, r) + p.b_hh[d];
+            const float giz = su2_sum<R>(s_p0, 384, 2, SA_D + d, r) + p.b_ih[SA_D + d], ghz = su2_sum<R>(s_p1, 384, 2, SA_D + d, r) + p.b_hh[SA_D + d];
+            const float gin = su2_sum<R>(s_p0, 384, 2, 2 * SA_D + d, r) + p.b_ih[2 * SA_D + d], ghn = su2_sum<R>(s_p1, 384, 2, 2 * SA_D + d, r) + p.b_hh[2 * SA_D + d];
             const float rg = sigmoidf_(gir + ghr), zg = sigmoidf_(giz + ghz);
             const float ng = tanhf(gin + rg * ghn);
-            s_h[tid] = (1.0f - zg) * ng + zg * s_h[tid];
+            s_h[idx] = (1.0f - zg) * ng + zg * s_h[idx];
         }
         __syncthreads();
-        su_layernorm(s_h, s_u, p.ln_mlp_g, p.ln_mlp_b, p.ln_eps, warp, lane);
+        su2_layernorm<R>(s_h, s_u, p.ln_mlp_g, p.ln_mlp_b, p.ln_eps, warp, lane);
         __syncthreads();
-        su2_matvec<2>(p.W1T, p.Hm, SA_D, p.Hm, s_u, s_p0, tid);           // Hm <= 384: 2 x Hm x 4 floats fit s_p0
+        su2_matvec<2, R>(p.W1T, p.Hm, SA_D, p.Hm, s_u, s_p0, tid);           // Hm <= 384: 2 x Hm x R floats fit s_p0
         __syncthreads();
-        for (int idx = tid; idx < p.Hm * 4; idx += SU2_THREADS) {
-            const int o = idx >> 2, r = idx & 3;
-            s_hid[idx] = fmaxf(su2_sum(s_p0, p.Hm, 2, o, r) + p.b1[o], 0.f);
+        for (int idx = tid; idx < p.Hm * R; idx += SU2_THREADS) {
+            const int o = idx / R, r = idx - o * R;
+            s_hid[idx] = fmaxf(su2_sum<R>(s_p0, p.Hm, 2, o, r) + p.b1[o], 0.f);
         }
         __syncthreads();
-        su2_matvec<4>(p.W2T, SA_D, p.Hm, SA_D, s_hid, s_p1, tid);
+        su2_matvec<4, R>(p.W2T, SA_D, p.Hm, SA_D, s_hid, s_p1, tid);
         __syncthreads();
-        if (tid < SA_D * 4) {
-            const int d = tid >> 2, r = tid & 3;
-            const float v = s_h[tid] + su2_sum(s_p1, SA_D, 4, d, r) + p.b2[d];
-            s_h[tid] = v;
+        for (int idx = tid; idx < SA_D * R; idx += SU2_THREADS) {
+            const int d = idx / R, r = idx - d * R;
+            const float v = s_h[idx] + su2_sum<R>(s_p1, SA_D, 4, d, r) + p.b2[d];
+            s_h[idx] = v;
             if (r < nr) p.slots_out[((size_t)b * S + r0 + r) * SA_D + d] = v;
         }
         __syncthreads();
@@ -618,23 +650,35 @@ __global__ __launch_bounds__(SU2_THREADS) void sa_update2_kernel(SaUpd2Params p)
         __syncthreads();
     }
     if (p.do_prep) {
-        su_layernorm(s_h, s_u, p.ln_slot_g, p.ln_slot_b, p.ln_eps, warp, lane);
+        su2_layernorm<R>(s_h, s_u, p.ln_slot_g, p.ln_slot_b, p.ln_eps, warp, lane);
         __syncthreads();
-        su2_matvec<4>(p.MAT, SA_D, SA_D, SA_D, s_u, s_p0, tid);
+        su2_matvec<4, R>(p.MAT, SA_D, SA_D, SA_D, s_u, s_p0, tid);
         if (warp >= 16 && warp < 16 + nr) {                               // a0 = v0 . n, one warp per slot row
             const int r = warp - 16;
             float s0 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) s0 = fmaf(p.v0[lane + 32 * i], s_u[(lane + 32 * i) * 4 + r], s0);
+            for (int i = 0; i < 4; ++i) s0 = fmaf(p.v0[lane + 32 * i], s_u[(lane + 32 * i) * R + r], s0);
             s0 = warp_sum(s0);
             if (lane == 0) p.a0[b * S + r0 + r] = s0;
         }
         __syncthreads();
-        if (tid < SA_D * 4) {
-            const int c = tid >> 2, r = tid & 3;
-            if (r < nr) p.A[((size_t)b * S + r0 + r) * SA_D + c] = su2_sum(s_p0, SA_D, 4, c, r);
+        for (int idx = tid; idx < SA_D * R; idx += SU2_THREADS) {
+            const int c = idx / R, r = idx - c * R;
+            if (r < nr) p.A[((size_t)b * S + r0 + r) * SA_D + c] = su2_sum<R>(s_p0, SA_D, 4, c, r);
         }
     }
+}
+
+template <int R>
+static int launch_sa_update2(const SaUpd2Params& p, cudaStream_t st) {
+    const size_t smem = (size_t)(2 * SA_D * R + 512 * R + 2 * 2 * 384 * R) * sizeof(float);
+    static PsSmemConfig smem_cfg = {};
+    if (smem > 48 * 1024) PS_CUDA(ps_ensure_smem(sa_update2_kernel<R>, smem, smem_cfg));
+    dim3 grid((p.S + R - 1) / R, p.B);
+    sa_update2_kernel<R><<<grid, SU2_THREADS, smem, st>>>(p);
+    PS_COUNT_LAUNCH();
+    PS_LAUNCH_CHECK();
+    return PS_OK;
 }
 
 extern "C" int ps_sa_update2(const float* partial, int n_chunks, const float* slots_in, float* slots_out,
@@ -661,9 +705,9 @@ extern "C" int ps_sa_update2(const float* partial, int n_chunks, const float* sl
     p.ln_mlp_g = ln_mlp_g; p.ln_mlp_b = ln_mlp_b; p.W1T = W1T; p.b1 = b1; p.W2T = W2T; p.b2 = b2;
     p.ln_slot_g = ln_slot_g; p.ln_slot_b = ln_slot_b; p.MAT = MAT; p.v0 = v0; p.A = A; p.a0 = a0;
     p.B = B; p.S = S; p.Hm = mlp_hidden; p.ln_eps = ln_eps; p.do_update = do_update; p.do_prep = do_prep;
-    dim3 grid((S + 3) / 4, B);
-    sa_update2_kernel<<<grid, SU2_THREADS, 0, (cudaStream_t)stream>>>(p);
-    PS_COUNT_LAUNCH();
-    PS_LAUNCH_CHECK();
-    return PS_OK;
+    // 5 or 6 slots: one 8-row CTA per frame instead of a full 4-row CTA plus one that re-reads all the weights for 1 - 2 rows
+    // (GridShapes5Objs, 64 frames: 24 -> 20 us per launch).  With 8 slots two 4-row CTAs per frame are faster than one 8-row CTA
+    // (measured: 0.221 vs 0.231 ms for the 3-iteration forward) -- the kernel needs the parallelism as much as the L2 bytes.
+    if (S == 5 || S == 6) return launch_sa_update2<8>(p, (cudaStream_t)stream);
+    return launch_sa_update2<4>(p, (cudaStream_t)stream);
 }
