@@ -301,18 +301,23 @@ enc_mlp_tc_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_consta
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar_d2empty);           // accumulators are in registers
+            // norm_input statistics of the 128-feature row: this thread's half gives (sum, M2 about its own mean); the two halves are
+            // combined with the exact pairwise update (Chan et al.): one exchange and one barrier instead of a mean pass and a variance pass
             float s = 0.f;
 #pragma unroll
             for (int c = 0; c < 64; ++c) s += y[c];
-            s_sum[par][half][row] = s;
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");
-            const float mean = (s_sum[par][0][row] + s_sum[par][1][row]) * (1.0f / EM_D);
-            float ss = 0.f;
+            const float mh = s * (1.0f / 64.0f);
+            float m2 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 64; ++c) { y[c] -= mean; ss = fmaf(y[c], y[c], ss); }
-            s_sq[par][half][row] = ss;
+            for (int c = 0; c < 64; ++c) { const float d = y[c] - mh; m2 = fmaf(d, d, m2); }
+            s_sum[par][half][row] = s;
+            s_sq[par][half][row] = m2;
             asm volatile("bar.sync 1, 256;\n" ::: "memory");
-            const float rstd = 1.0f / sqrtf((s_sq[par][0][row] + s_sq[par][1][row]) * (1.0f / EM_D) + p.out_eps);
+            const float s0 = s_sum[par][0][row], s1 = s_sum[par][1][row];
+            const float mean = (s0 + s1) * (1.0f / EM_D);
+            const float dm = (s0 - s1) * (1.0f / 64.0f);
+            const float var = (s_sq[par][0][row] + s_sq[par][1][row] + dm * dm * 32.0f) * (1.0f / EM_D);
+            const float rstd = 1.0f / sqrtf(var + p.out_eps);
             const long long m = (long long)it * EM_BM + row;
             if (m < p.M) {
                 long long mo = m;
@@ -326,7 +331,7 @@ enc_mlp_tc_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_consta
                 for (int j = 0; j < 4; ++j) {                      // 16 features -> one full 32-byte sector per plane
                     float f[16];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) f[c] = y[16 * j + c] * rstd;
+                    for (int c = 0; c < 16; ++c) f[c] = (y[16 * j + c] - mean) * rstd;
                     uint4 h0, l0, h1, l1;
                     em_split8(f, h0, l0);
                     em_split8(f + 8, h1, l1);
