@@ -695,6 +695,26 @@ def test_host_pipeline_equals_blocking_calls():
         assert torch.equal(o, w), f"batch {i}: streamed result differs from the blocking call"
 
 
+@pytest.mark.parametrize("res,slots,M", [((32, 32), 6, 3), ((48, 80), 5, 2), ((96, 64), 3, 1)])
+def test_decode_other_resolutions_vs_oracle(res, slots, M):
+    """ the decoder kernels (collapsed first conv, tcgen05 5x5 layers, row-merged tcgen05 compositing with its 126-position tiles
+    and cross-warp edge exchange) on image sizes other than the shipped 64x64 / 128x128, against the CPU oracle """
+    from playslot_b200 import configs
+    cfg = configs.experiment("GridShapes5Objs", num_slots=slots, resolution=res)
+    scfg = cfg["model"]["model_params"]
+    savi_cpu, _ = configs.build_models(cfg, "cpu")
+    ssd = synth_state_dict({k: list(v.shape) for k, v in savi_cpu.state_dict().items()}, 77)
+    savi = make_savi(scfg, ssd, DEV)
+    sl = g(M, slots, 128, seed=res[0] + slots)
+    with torch.no_grad():
+        recon, (recons, masks) = savi.decode(sl.to(DEV))
+        r_recon, r_recons, r_masks = O.decode(ssd, scfg, sl)
+    assert recon.shape == (M, 3, *res) and masks.shape == (M, slots, 1, *res)
+    check("recon", recon, r_recon)
+    check("recons", recons, r_recons)
+    check("masks", masks, r_masks)
+
+
 def test_config5_highres_many_slots_vs_oracle():
     """ BASELINE.json configs[4] shapes: Sketchy hyper-parameters at 128x128, 16 slots, context 10 (N = 16384 feature tokens,
     160 predictor tokens): a short clip through encode -> SlotAttention -> InvDyn -> rollout -> decode against the CPU oracle """
