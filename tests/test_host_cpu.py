@@ -123,6 +123,35 @@ def test_border_class_tap_sums_match_direct_conv():
             assert torch.allclose(ws @ slot, full[:, y, x], atol=1e-4)
 
 
+def test_packed_operands_of_the_tensor_core_kernels():
+    """ host-side weight packing (pure tensor code, no kernel): the row-merged compositing operand [3 filter rows][hi 16 | lo 16][64]
+    of ps_dec_composite_tc reconstructs the 3x3 weight to 22 bits in the (kx, o) order the kernel's epilogue assumes, and the
+    block-diagonal pair weight of a 32-channel ConvBlock convolves the two images of a pair independently """
+    import torch.nn.functional as F
+    from playslot_b200 import ops, configs
+    torch.manual_seed(0)
+    w = torch.randn(4, 64, 3, 3) * 0.05
+    packed, scale = ops.pack_final_conv_tc(w)
+    assert packed.shape == (3, 32, 64) and packed.dtype == torch.int16
+    h = packed.view(torch.float16).float()
+    rec = (h[:, 0:12] + h[:, 16:28] / 2048.0) / scale                                   # [ky][kx * 4 + o][cin]
+    ref = w.permute(2, 3, 0, 1).reshape(3, 12, 64)
+    assert (rec - ref).abs().max() <= 2.0 ** -21 * ref.abs().max()
+    assert h[:, 12:16].abs().max() == 0 and h[:, 28:32].abs().max() == 0
+    # block-diagonal pairing
+    cfg = configs.experiment("BlockPush")
+    savi, _ = configs.build_models(cfg, "cpu")
+    blk = list(savi.encoder.encoder)[1]
+    c = blk.conv
+    co, ci = c.weight.shape[:2]
+    wp = torch.zeros(2 * co, 2 * ci, 5, 5)
+    wp[:co, :ci] = c.weight.detach(); wp[co:, ci:] = c.weight.detach()
+    x = torch.randn(2, ci, 16, 16)
+    y_pair = F.conv2d(x.reshape(1, 2 * ci, 16, 16), wp, torch.cat([c.bias, c.bias]).detach(), padding=2)
+    y_ref = F.conv2d(x, c.weight.detach(), c.bias.detach(), padding=2)
+    assert torch.allclose(y_pair.reshape(2, co, 16, 16), y_ref, atol=1e-5)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/experiments"), reason="reference tree not mounted")
 @pytest.mark.parametrize("name", ["BlockPush", "ButtonPress", "GridShapes5Objs", "Sketchy"])
 def test_restated_configs_equal_reference_json(name):
