@@ -274,6 +274,9 @@ int ps_dec_composite_bwd(const float* recons, const float* masks, const float* g
                          const float* g_masks, float* g_o, int M, int S, int H, int W, void* stream);
 int ps_dec_final_dgrad(const float* g_o, const float* w_packed, const float* h, void* act_out, const float* g_scale,
                        int n_img, int H, int W, int precision, void* stream);
+/* ps_dec_final_dgrad with the saved activation as padded split planes (the hi plane carries the sign of the ReLU input) */
+int ps_dec_final_dgrad_planes(const float* g_o, const float* w_packed, const void* h_planes, void* act_out, const float* g_scale,
+                              int n_img, int H, int W, int precision, void* stream);
 int ps_conv5x5_tc_dgrad(const void* g_in, const void* w_tc_flipped, float w_scale, const void* mask_act, void* act_out,
                         float* out_tokens, int n_img, int H, int W, int out_mode, int precision, void* stream);
 int ps_dec_expand_bwd(const float* g_tokens, float* dG, const float* g_scale, int n_img, int H, int W, int ksize, void* stream);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ps_invdyn_tail_bwd": (c_i, [c_f] * 11 + [c_i] * 6 + [c_fl, c_f]),
     "ps_dec_composite_bwd": (c_i, [c_f] * 6 + [c_i, c_i, c_i, c_i, c_f]),
     "ps_dec_final_dgrad": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
+    "ps_dec_final_dgrad_planes": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_conv5x5_tc_dgrad": (c_i, [c_f, c_f, c_fl, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "ps_dec_expand_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_dec_composite_tc": (c_i, [c_f, c_f, c_fl, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),

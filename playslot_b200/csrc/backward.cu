@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(256) dec_composite_bwd_kernel(const float* __r
 // dh[img][ci][y][x] = sum_{co<4,ky,kx} w[co][ci][ky][kx] * g_o[img][co][y+1-ky][x+1-kx], masked by relu'(h), written as
 // padded NHWC split (hi | lo) 16-bit planes.  w_packed is the forward packing [Cin=64][9][4].
 __global__ void __launch_bounds__(256) dec_final_dgrad_kernel(const float* __restrict__ g_o, const float* __restrict__ w_packed,
-                                                             const float* __restrict__ h, uint16_t* __restrict__ out_hi,
+                                                             const float* __restrict__ h, const uint16_t* __restrict__ h_hi,
+                                                             uint16_t* __restrict__ out_hi,
                                                              uint16_t* __restrict__ out_lo, const float* __restrict__ g_scale,
                                                              int n_img, int H, int W) {
     // One thread per pixel, all 64 input channels: the 36 incoming gradient values of the pixel's 3x3 neighbourhood live in
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(256) dec_final_dgrad_kernel(const float* __res
                 const float* gp = g_o + (size_t)img * 4 * HW + yy * W + xx;
                 go[ky * 3 + kx] = ok ? make_float4(gp[0], gp[HW], gp[2 * HW], gp[3 * HW]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        const float* hp = h + (size_t)img * 64 * HW + y * W + x;
+        const float* hp = h ? h + (size_t)img * 64 * HW + y * W + x : nullptr;
         const size_t o = (((size_t)img * Hp + y + 2) * Wp + x + 2) * 64;
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -488,7 +489,21 @@ __global__ void __launch_bounds__(256) dec_final_dgrad_kernel(const float* __res
                     acc = fmaf(w4.x, go[t].x, acc); acc = fmaf(w4.y, go[t].y, acc);
                     acc = fmaf(w4.z, go[t].z, acc); acc = fmaf(w4.w, go[t].w, acc);
                 }
-                v[j] = hp[(size_t)(c0 + j) * HW] > 0.f ? acc : 0.f;
+                v[j] = acc;
+                if (hp) v[j] = hp[(size_t)(c0 + j) * HW] > 0.f ? acc : 0.f;
+            }
+            if (!hp) {                 // saved activation as split planes (same position as the output row): pass where its hi part is positive
+                const uint4* mk = reinterpret_cast<const uint4*>(h_hi + o + c0);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint4 m4 = __ldg(mk + g);
+                    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if ((mw[j] & 0x7FFFu) == 0u || (mw[j] & 0x8000u)) v[g * 8 + 2 * j] = 0.f;
+                        if ((mw[j] & 0x7FFF0000u) == 0u || (mw[j] & 0x80000000u)) v[g * 8 + 2 * j + 1] = 0.f;
+                    }
+                }
             }
             uint32_t hw[8], lw[8];
 #pragma unroll
@@ -519,9 +534,26 @@ extern "C" int ps_dec_composite_bwd(const float* recons, const float* masks, con
     return PS_OK;
 }
 
+static int dec_final_dgrad_run(const float* g_o, const float* w_packed, const float* h, const void* h_planes, void* act_out,
+                               const float* g_scale, int n_img, int H, int W, int precision, void* stream);
+
 extern "C" int ps_dec_final_dgrad(const float* g_o, const float* w_packed, const float* h, void* act_out, const float* g_scale,
                                   int n_img, int H, int W, int precision, void* stream) {
-    PS_REQUIRE(g_o && w_packed && h && act_out, "ps_dec_final_dgrad: null pointer");
+    PS_REQUIRE(h, "ps_dec_final_dgrad: null pointer");
+    return dec_final_dgrad_run(g_o, w_packed, h, nullptr, act_out, g_scale, n_img, H, W, precision, stream);
+}
+
+// the same with the saved activation given as the padded split planes the tensor-core layers write (its hi plane carries the sign):
+// the forward of the predictor's training step then never materialises the 64-channel fp32 NCHW activation
+extern "C" int ps_dec_final_dgrad_planes(const float* g_o, const float* w_packed, const void* h_planes, void* act_out,
+                                         const float* g_scale, int n_img, int H, int W, int precision, void* stream) {
+    PS_REQUIRE(h_planes && ps_aligned16(h_planes), "ps_dec_final_dgrad_planes: null / unaligned planes");
+    return dec_final_dgrad_run(g_o, w_packed, nullptr, h_planes, act_out, g_scale, n_img, H, W, precision, stream);
+}
+
+static int dec_final_dgrad_run(const float* g_o, const float* w_packed, const float* h, const void* h_planes, void* act_out,
+                               const float* g_scale, int n_img, int H, int W, int precision, void* stream) {
+    PS_REQUIRE(g_o && w_packed && act_out, "ps_dec_final_dgrad: null pointer");
     PS_REQUIRE(precision == 2 || precision == 3, "ps_dec_final_dgrad: precision must be 2 (fp16) or 3 (fp16x3)");
     if (n_img == 0) return PS_OK;
     const long long P = (long long)n_img * (H + 4) * (W + 4);
@@ -530,7 +562,8 @@ extern "C" int ps_dec_final_dgrad(const float* g_o, const float* w_packed, const
     const long long total = (long long)n_img * H * W;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    dec_final_dgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g_o, w_packed, h, hi, lo, g_scale, n_img, H, W);
+    dec_final_dgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g_o, w_packed, h, reinterpret_cast<const uint16_t*>(h_planes), hi, lo,
+                                                                               g_scale, n_img, H, W);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;

@@ -34,7 +34,9 @@ class _DecodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, slots, savi):
-        recon, recons, masks, saved = savi._decode_impl(slots.detach(), keep=True)
+        # predictor training: the decoder is frozen, so the last block's activation is kept as split planes (its sign is all the
+        # data gradient needs) and the 3x3 convolution + compositing run on the tensor cores like in inference
+        recon, recons, masks, saved = savi._decode_impl(slots.detach(), keep="planes")
         ctx.savi, ctx.saved_acts = savi, saved
         ctx.save_for_backward(recons, masks)
         ctx.set_materialize_grads(False)
@@ -458,7 +460,9 @@ class SAVi(nn.Module):
         return recon, (recons, masks)
 
     def _decode_impl(self, slots, keep):
-        """ forward kernels; with keep=True the per-layer activations needed by the data gradient are returned """
+        """ forward kernels; with keep=True the per-layer activations needed by the backward are returned (the last block's as fp32
+        NCHW: the weight gradient of the final convolution reads it); keep="planes": data gradient only, the last block's activation
+        stays in the split-plane format and the tensor-core compositing kernel is used """
         M, S, D = slots.shape
         H, W = self.decoder_resolution
         dec = self.decoder
@@ -483,8 +487,9 @@ class SAVi(nn.Module):
             G = ops.linear(sl, wsum)                                           # (n_img, ncls^2 * C1)
             n_img = (m1 - m0) * S
             if use_tc:
+                planes_last = keep == "planes" and prec == 3 and S <= 16
                 if keep:
-                    acts = [ops.conv_tc_workspace(n_img, H, W, slots.device) for _ in range(3)]      # h1, h2, h3
+                    acts = [ops.conv_tc_workspace(n_img, H, W, slots.device) for _ in range(4 if planes_last else 3)]      # h1, h2, h3 (, h4)
                 else:
                     a = self._tc_workspace("dec_a", n_img, H, W, slots.device)
                     b = self._tc_workspace("dec_b", n_img, H, W, slots.device)
@@ -492,6 +497,12 @@ class SAVi(nn.Module):
                 ops.dec_expand_split(G, P_hwc, acts[0], n_img, H, W, k, prec)
                 for i, blk in enumerate(blocks[1:-1]):
                     ops.conv5x5_tc(acts[i], self._tc_weight(blk), blk.conv.bias, n_img, H, W, blk._relu, prec, act_out=acts[i + 1])
+                if planes_last:
+                    ops.conv5x5_tc(acts[2], self._tc_weight(blocks[-1]), blocks[-1].conv.bias, n_img, H, W, blocks[-1]._relu, prec, act_out=acts[3])
+                    r, rs, ms = ops.dec_composite_tc(acts[3], self._final_packed_tc(final), final.bias, m1 - m0, S, H, W)
+                    recon_l.append(r); recons_l.append(rs); masks_l.append(ms)
+                    saved.append((m0, m1, acts[:3], ("planes", acts[3])))
+                    continue
                 if not keep and prec == 3 and S <= 16:
                     # inference: the last block stays in the split format and the 3x3 conv + slot softmax + compositing
                     # run on the tensor cores too (no fp32 NCHW round trip of the 64-channel activation)
@@ -551,7 +562,11 @@ class SAVi(nn.Module):
             # far below fp16's normal range; the convolutions are linear, so the scale is undone exactly at the end
             amax = g_o.abs().max().clamp_min(1e-30)
             g_scale = torch.exp2(-torch.floor(torch.log2(amax))).reshape(1)
-            ops.dec_final_dgrad(g_o, wfin, h, ga, prec, g_scale)                                   # through conv3x3 and relu(h4)
+            if isinstance(h, tuple):                                                               # ("planes", h4 as split planes)
+                assert wg is None, "the weight gradient of the final convolution needs the fp32 activation (keep=True)"
+                ops.dec_final_dgrad_planes(g_o, wfin, h[1], ga, n_img, H, W, prec, g_scale)
+            else:
+                ops.dec_final_dgrad(g_o, wfin, h, ga, prec, g_scale)                               # through conv3x3 and relu(h4)
             inv = 1.0 / g_scale
             if wg is not None:
                 dwf, dbf = ops.conv3x3_final_wgrad(g_o, h)

@@ -784,6 +784,16 @@ def dec_composite_bwd(recons, masks, g_recon, g_recons, g_masks):
     return g_o
 
 
+def dec_final_dgrad_planes(g_o, w_packed, h_planes, act_out, n_img, H, W, precision, g_scale=None):
+    """ dec_final_dgrad with the saved last-block activation as padded split planes (predictor training: no fp32 NCHW copy) """
+    lib = _lib.load()
+    with _timed("dec_final_dgrad"):
+        st = lib.ps_dec_final_dgrad_planes(_ptr(g_o), _ptr(w_packed), _ptr(h_planes), _ptr(act_out), _ptr(g_scale), n_img, H, W,
+                                           int(precision), _stream())
+    _lib.check(st, "ps_dec_final_dgrad_planes")
+    return act_out
+
+
 def dec_final_dgrad(g_o, w_packed, h, act_out, precision, g_scale=None):
     lib = _lib.load()
     n_img, _, H, W = h.shape
