@@ -87,12 +87,22 @@ class SoftPositionEmbed(nn.Module):
         self.grid = build_grid(resolution, vmin=vmin, vmax=vmax).permute(0, 3, 1, 2)   # plain attribute, as upstream
         self._cache = DerivedWeights()
 
+    def grid_on(self, device, dtype=torch.float32):
+        """ the (1, 4, H, W) coordinate grid on `device` -- `grid` itself stays a plain CPU attribute as upstream; the device copy is
+        made once (a host-to-device copy per call would also be illegal inside a CUDA-graph capture of a training step) """
+        key = (str(device), dtype)
+        c = getattr(self, "_grid_dev", None)
+        if c is None or c[0] != key:
+            c = (key, self.grid.to(device=device, dtype=dtype))
+            self._grid_dev = c
+        return c[1]
+
     def table(self, channels_last=True):
         """ (H*W, C) if channels_last else (C, H, W): projection(grid), weight-only """
         w, b = self.projection.weight, self.projection.bias
 
         def build():
-            g = self.grid.to(device=w.device, dtype=w.dtype)[0]                       # (4, H, W)
+            g = self.grid_on(w.device, w.dtype)[0]                                    # (4, H, W)
             emb = torch.einsum("ck,khw->chw", w[:, :, 0, 0], g) + b[:, None, None]   # (C, H, W)
             return emb.contiguous(), emb.permute(1, 2, 0).reshape(-1, emb.shape[0]).contiguous()
         chw, hwc = self._cache.get([w, b], build)

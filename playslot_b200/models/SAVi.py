@@ -290,7 +290,7 @@ class SAVi(nn.Module):
         prec = ops.TC_PRECISION[self.conv_mode]
         cache = self._tc_w.setdefault((id(block), prec), DerivedWeights())
         w = block.conv.weight
-        return cache.get([w], lambda: ops.pack_conv_weight_tc(self._pad64(w.detach()), prec))
+        return cache.get([w], lambda: ops.pack_conv_weight_tc(self._pad64(w.detach()), prec, owner=w))
 
     def _tc_first_conv(self, block):
         """ (packed weight, bias) of the first encoder conv with its output channels zero-padded to 64 """
@@ -342,7 +342,7 @@ class SAVi(nn.Module):
             wp[:co, :ci] = w
             wp[co:, ci:] = w
             bp = torch.cat([c.bias.detach(), c.bias.detach()]).contiguous()
-            return (ops.pack_conv_weight(wp) if first else ops.pack_conv_weight_tc(wp, prec)), bp
+            return (ops.pack_conv_weight(wp) if first else ops.pack_conv_weight_tc(wp, prec, owner=c.weight)), bp
         return cache.get([c.weight, c.bias], build)
 
     def _encode_convs_tc_paired(self, x, posemb):
@@ -531,7 +531,7 @@ class SAVi(nn.Module):
         prec = ops.TC_PRECISION[self.conv_mode]
         cache = self._tc_w.setdefault((id(block), prec, "flip"), DerivedWeights())
         w = block.conv.weight
-        return cache.get([w], lambda: ops.pack_conv_weight_tc(self._pad64(w.detach()).flip(2, 3).transpose(0, 1).contiguous(), prec))
+        return cache.get([w], lambda: ops.pack_conv_weight_tc(self._pad64(w.detach()).flip(2, 3).transpose(0, 1).contiguous(), prec, owner=w))
 
     def _decode_backward(self, saved, recons, masks, g_recon, g_recons, g_masks, weight_grads=False, slots=None):
         """ d loss / d slots through compositing, the 3x3 and the three 5x5 convolutions and the collapsed first one; with
@@ -606,7 +606,7 @@ class SAVi(nn.Module):
     def _final_packed_tc(self, conv):
         if not hasattr(self, "_fin_tc_cache"):
             self._fin_tc_cache = DerivedWeights()
-        return self._fin_tc_cache.get([conv.weight], lambda: ops.pack_final_conv_tc(conv.weight))
+        return self._fin_tc_cache.get([conv.weight], lambda: ops.pack_final_conv_tc(conv.weight, owner=conv.weight))
 
     def broadcast(self, slots):
         """ (B, S, D) -> (B*S, D, H, W): slot broadcast + position embedding (SAVi.py:237-248).  The decode

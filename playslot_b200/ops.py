@@ -196,7 +196,7 @@ def linear(x, weight, bias=None, ln=None, act=ACT_NONE, res=None, res_div=1, res
     lmode = mode or _LINEAR_MODE
     if lmode != "fp32" and M >= LINEAR_TC_MIN_ROWS:
         prec = TC_PRECISION[lmode]
-        w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, prec, reuse_scale=reuse_pack_scale)
+        w_tc, w_scale, Kp, Npad = _packed_linear_weight(weight, prec, reuse_scale=reuse_pack_scale or REUSE_CONV_PACK_SCALE)
         with _timed("linear_tc_p%d" % prec, (M, N, K)):
             st = lib.ps_linear_tc(_ptr(x2), K, _ptr(w_tc), float(w_scale), Kp, Npad, _ptr(bias), _ptr(g), _ptr(b), float(eps),
                                   _ptr(res), ldres, int(res_div), int(res_mod or 0), _ptr(y2), N, M, N, K, int(act), prec, _stream())
@@ -527,14 +527,13 @@ def dec_composite(h, w_packed, bias, M, S):
     return recon, recons, masks
 
 
-def pack_final_conv_tc(w):
+def pack_final_conv_tc(w, owner=None):
     """ final decoder conv weight (4, 64, 3, 3) -> (int16 (3 filter rows, 32 rows [hi: kx0 o0-3 | kx1 o0-3 | kx2 o0-3 | 4 zero; lo: same],
     64 cin), w_scale): the three taps of a filter row form one N = 32 operand of ps_dec_composite_tc """
     Cout, Cin, K, _ = w.shape
     assert (Cout, Cin, K) == (4, 64, 3), "the tensor-core compositing kernel covers the 64 -> 4 channel 3x3 convolution"
     wt = w.detach().float().permute(2, 3, 0, 1).reshape(3, 12, 64)          # [ky][kx * 4 + o][cin]
-    amax = float(wt.abs().max())
-    scale = 1.0 if amax == 0.0 else 2.0 ** (-round(math.log2(amax)))
+    scale = _conv_pack_scale(wt, owner, 3)
     wt = wt * scale
     h = wt.to(torch.float16)
     lo = ((wt - h.float()) * TC_LO_SCALE).to(torch.float16)
@@ -613,7 +612,29 @@ def conv_tc_workspace(n_img, H, W, device):
     return torch.zeros(2, elems // 64, 64, device=device, dtype=torch.int16)
 
 
-def pack_conv_weight_tc(w, precision):
+# Training steps captured in a CUDA graph repack the convolution weights inside the graph every replay: the power-of-two scale
+# (which only keeps the fp16 parts in range) must then come without a host synchronisation.  While this flag is set, the packers
+# reuse the scale chosen at a tensor's first packing (stored on the parameter object) instead of measuring max|w| again (the
+# tensor-core Linear layers do the same through _packed_linear_weight(reuse_scale=True)).
+REUSE_CONV_PACK_SCALE = False
+
+
+def _conv_pack_scale(wt, owner, precision):
+    """ power of two that puts max|w| near 1; `owner`: the parameter the scale is remembered on (None: always measured) """
+    if precision == 1:
+        return 1.0
+    if owner is not None and REUSE_CONV_PACK_SCALE:
+        sc = getattr(owner, "_ps_conv_scale", None)
+        if sc is not None:
+            return sc
+    amax = float(wt.abs().max())
+    scale = 1.0 if amax == 0.0 else 2.0 ** (-round(math.log2(amax)))
+    if owner is not None:
+        owner._ps_conv_scale = scale
+    return scale
+
+
+def pack_conv_weight_tc(w, precision, owner=None):
     """
     nn.Conv2d weight (64, 64, 5, 5) fp32 -> (16-bit tensor (25 taps, 2 [hi, lo], 64 cout, 64 cin), w_scale).
     The weights are multiplied by a power of two w_scale that puts max|w| near 1 (exact; undone in the kernel's
@@ -622,8 +643,7 @@ def pack_conv_weight_tc(w, precision):
     Cout, Cin, K, _ = w.shape
     assert (Cout, Cin, K) == (64, 64, 5), "the tensor-core convolution covers 64 -> 64 channels, 5x5"
     wt = w.detach().float().permute(2, 3, 0, 1).reshape(K * K, Cout, Cin)
-    amax = float(wt.abs().max())
-    scale = 1.0 if amax == 0.0 or precision == 1 else 2.0 ** (-round(__import__("math").log2(amax)))
+    scale = _conv_pack_scale(wt, owner, precision)
     wt = wt * scale
     if precision == 1:
         hi = wt.to(torch.bfloat16).view(torch.int16)

@@ -140,7 +140,7 @@ def encoder_tokens_train(savi, frames):
                                   "tensor-core path (conv_mode fp16x3 / fp16)")
     pe = savi.encoder_pos_embedding
     H, W = pe.resolution
-    grid = pe.grid.to(device=pe.projection.weight.device, dtype=torch.float32)[0].reshape(4, H * W)       # (4, HW)
+    grid = pe.grid_on(pe.projection.weight.device)[0].reshape(4, H * W)                                  # (4, HW)
     posemb = grid.t() @ pe.projection.weight[:, :, 0, 0].t() + pe.projection.bias                         # (HW, C), differentiable
     params = []
     for b in blocks:
@@ -169,7 +169,7 @@ def _decoder_constants_diff(savi):
     rows = [w[:, :, taps(cy), taps(cx)].sum(dim=(2, 3)) for cy in range(2 * p + 1) for cx in range(2 * p + 1)]
     wsum = torch.stack(rows, dim=0).reshape(-1, w.shape[1])
     H, W = savi.decoder_resolution
-    grid = pe.grid.to(device=w.device, dtype=torch.float32)[0]                                            # (4, H, W)
+    grid = pe.grid_on(w.device)[0]                                                                        # (4, H, W)
     pos = torch.einsum("ck,khw->chw", pe.projection.weight[:, :, 0, 0], grid) + pe.projection.bias[:, None, None]
     P = F.conv2d(pos[None], w, conv1.bias, padding=p)[0]                                                  # (C1, H, W)
     return wsum, P.permute(1, 2, 0).reshape(H * W, -1)

@@ -300,3 +300,58 @@ def savi_train_step(savi, optimizer, videos, bucket=None, clip_gradient=0.05, **
         torch.nn.utils.clip_grad_norm_(savi.parameters(), clip_gradient)
     optimizer.step()
     return loss.detach(), out
+
+
+class GraphedSaviTrainStep:
+    """
+    `savi_train_step` (src/02_train_savi.py:21-70 as driven by base/baseTrainer.py) for a fixed clip shape captured in ONE CUDA
+    graph: forward with decode, MSE loss, full backward (encoder, SlotAttention, transition, decoder), clip, Adam.  Launched from
+    Python the ~1500 kernels of a step leave a third of the time to the host.  The convolution weights are repacked inside the
+    graph every replay with the power-of-two scale chosen at their first packing (`ops.REUSE_CONV_PACK_SCALE`: no host
+    synchronisation), the gradients accumulate in a flat GradientBucket (all-reduced inside the graph when torch.distributed is
+    initialised).  The optimizer must be built with capturable=True.  A `LearnedRandom` initializer draws its noise from the CUDA
+    generator inside the graph (graph-safe Philox offsets), like the reference draws it on the device.
+    """
+
+    def __init__(self, savi, optimizer, batch, frames, resolution=(64, 64), clip_gradient=0.05, warmup=3, video_dtype=torch.float32):
+        from . import ops
+        self.savi, self.optimizer = savi, optimizer
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.bucket = GradientBucket(savi.parameters())
+        dev = next(savi.parameters()).device
+        H, W = resolution
+        self.video = torch.zeros(batch, frames, 3, H, W, device=dev, dtype=video_dtype)
+
+        def body():
+            return savi_train_step(savi, optimizer, self.video, bucket=self.bucket, clip_gradient=clip_gradient)
+
+        snap = _snapshot_training_state(savi, optimizer)
+        old_flag, ops.REUSE_CONV_PACK_SCALE = ops.REUSE_CONV_PACK_SCALE, True
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    body()                                   # builds caches, workspaces, Adam state and the remembered pack scales
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()
+            self.graph = torch.cuda.CUDAGraph()
+            kw = {"capture_error_mode": "thread_local"} if self.world > 1 else {}
+            n0 = ops.launch_count()
+            with torch.cuda.graph(self.graph, **kw):
+                self.loss, self.out = body()
+            self.launches_per_replay = ops.launch_count() - n0
+        finally:
+            ops.REUSE_CONV_PACK_SCALE = old_flag
+            _restore_training_state(savi, optimizer, snap)
+            self.bucket.flat.zero_()
+
+    def __call__(self, videos):
+        """ one optimisation step on `videos` (B, T, 3, H, W); returns (loss tensor, model output dict) -- static tensors of the graph """
+        self.video.copy_(videos, non_blocking=True)
+        self.graph.replay()
+        from . import ops
+        ops.bump_weight_generation()             # eager forwards after this step must rebuild their derived weights
+        return self.loss, self.out

@@ -43,11 +43,24 @@ def main():
     opt = torch.optim.Adam(savi.parameters(), lr=1e-4)
     video = torch.rand(args.batch, args.frames, 3, 64, 64, device="cuda")
     ms = timed(lambda: train.savi_train_step(savi, opt, video), args.reps)
+    # the same step captured in one CUDA graph (train.GraphedSaviTrainStep)
+    graphed_ms, graphed_err = None, None
+    try:
+        import copy as _copy
+        savi_g = _copy.deepcopy(savi)
+        opt_g = torch.optim.Adam(savi_g.parameters(), lr=1e-4, capturable=True)
+        gstep = train.GraphedSaviTrainStep(savi_g, opt_g, args.batch, args.frames)
+        graphed_ms = timed(lambda: gstep(video), max(args.reps, 10))
+        launches = gstep.launches_per_replay
+        del gstep, savi_g, opt_g
+    except Exception as e:
+        graphed_err = repr(e)[:300]
     ops.profile_start()
     train.savi_train_step(savi, opt, video)
     prof = ops.profile_stop()
     tot = sum(v["ms"] for v in prof.values())
     out = {"workload": f"SAVi training step, {args.experiment}, {args.batch} videos x {args.frames} frames", "ours_ms": ms,
+           "ours_graphed_ms": graphed_ms, "graphed_error": graphed_err,
            "ours_videos_per_s": args.batch / ms * 1e3,
            "kernel_ms": {k: round(v["ms"], 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}, "profiled_kernel_ms": tot}
     try:
