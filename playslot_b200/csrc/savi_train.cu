@@ -408,6 +408,70 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const uint16_t* _
     }
 }
 
+// The same with register reuse (W % 4 == 0): a thread owns whole filter ROWS (ci, ky) -- its part takes rows part, part + 4, ... --
+// and walks the image row four pixels at a time: the 4 + ks - 1 input values of a filter row come in with two LDS.128 and feed
+// 4 * ks FMAs (the first version issued one shared-memory load per FMA: 14.2 ms per SAVi training step, LDS-bound).
+template <int KS>
+__global__ void __launch_bounds__(256) conv_first_wgrad4_kernel(const uint16_t* __restrict__ dh_hi, const uint16_t* __restrict__ dh_lo,
+                                                               const float* __restrict__ x, const uint8_t* __restrict__ x8,
+                                                               float* __restrict__ dW, int Cin, int H, int W, int band, float scale) {
+    extern __shared__ __align__(16) float s_rows4[];  // [Cin * KS][Wq] input rows around y (zero padded), Wq = pitch rounded up to 4 floats (+ 4 slack)
+    constexpr int PAD = KS / 2, RMAX = 5;             // Cin * KS <= 20 rows -> at most 5 per part
+    const int img = blockIdx.y, Wr = W + KS - 1, Wq = ((Wr + 3) & ~3) + 4;
+    const int co = threadIdx.x & 63, part = threadIdx.x >> 6;
+    const int n_rows = Cin * KS;
+    const int Wp = W + 4, Hp = H + 4;
+    float acc[RMAX][KS];
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j)
+#pragma unroll
+        for (int k = 0; k < KS; ++k) acc[j][k] = 0.f;
+    const int y0 = blockIdx.x * band, y1 = min(H, y0 + band);
+    for (int y = y0; y < y1; ++y) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_rows * Wq; i += 256) {
+            const int r = i / Wq, c = i - r * Wq;
+            const int ci = r / KS, ky = r - ci * KS, xx = c - PAD, yy = y + ky - PAD;
+            float v = 0.f;
+            if (c < Wr && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const size_t o = (((size_t)img * Cin + ci) * H + yy) * W + xx;
+                v = x8 ? __fdiv_rn((float)x8[o], 255.0f) : x[o];
+            }
+            s_rows4[i] = v;
+        }
+        __syncthreads();
+        const size_t row_base = (((size_t)img * Hp + y + 2) * Wp + 2) * 64;
+        for (int xx = 0; xx < W; xx += 4) {
+            float g[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g[c] = plane_val(dh_hi, dh_lo, row_base + (size_t)(xx + c) * 64 + co);
+#pragma unroll
+            for (int j = 0; j < RMAX; ++j) {
+                const int r = part + 4 * j;
+                if (r < n_rows) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(s_rows4 + r * Wq + xx);
+                    const float4 w1 = *reinterpret_cast<const float4*>(s_rows4 + r * Wq + xx + 4);
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int k = 0; k < KS; ++k)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[j][k] = fmaf(g[c], w[c + k], acc[j][k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+        const int r = part + 4 * j;
+        if (r < n_rows) {
+            const int ci = r / KS, ky = r - ci * KS;
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+                atomicAdd(dW + (size_t)co * (Cin * KS * KS) + (ci * KS + ky) * KS + k, acc[j][k] * scale);
+        }
+    }
+}
+
 // last decoder convolution (64 -> 4, 3x3): dW[co][ci][ky][kx] += sum g[img][co][y][x] h[img][ci][y+ky-1][x+kx-1]; db[co] += sum g.
 // grid (n_img); thread = (ci 0..63, tap group 0..3 handling taps {g, g+4, g+8}); rows streamed through shared memory.
 __global__ void __launch_bounds__(256) conv3x3_final_wgrad_kernel(const float* __restrict__ g_o, const float* __restrict__ h, float* __restrict__ dW,
@@ -426,24 +490,52 @@ __global__ void __launch_bounds__(256) conv3x3_final_wgrad_kernel(const float* _
     float accb = 0.f;
     for (int y = 0; y < H; ++y) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 64 * 3 * Wr; i += 256) {
-            const int c = i / (3 * Wr), r = (i / Wr) % 3, xx = i % Wr - 1, yy = y + r - 1;
-            s_h[(c * 3 + r) * (Wr + 1) + (i % Wr)] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? h[((size_t)img * 64 + c) * HW + (size_t)yy * W + xx] : 0.f;
+        // rolling three-row window: image row yy lives in slot (yy + 3) % 3; only row y + 1 is new (rows -1, 0, 1 at y = 0)
+        for (int yy = (y == 0 ? -1 : y + 1); yy <= y + 1; ++yy) {
+            const int slot = (yy + 3) % 3;
+            const bool row_ok = yy >= 0 && yy < H;
+            for (int i = threadIdx.x; i < 64 * Wr; i += 256) {
+                const int c = i / Wr, col = i - c * Wr, xx = col - 1;
+                s_h[(c * 3 + slot) * (Wr + 1) + col] = (row_ok && xx >= 0 && xx < W) ? h[((size_t)img * 64 + c) * HW + (size_t)yy * W + xx] : 0.f;
+            }
         }
         for (int i = threadIdx.x; i < 4 * W; i += 256) s_g[i] = g_o[((size_t)img * 4 + i / W) * HW + (size_t)y * W + (i % W)];
         __syncthreads();
+        if ((W & 3) == 0) {
+            // four pixels per step: the 16 gradient values (4 outputs x 4 pixels) come in with four LDS.128 and are shared by the
+            // thread's three taps -- 48 FMAs per 16 shared-memory loads (the scalar loop below issues five loads per four FMAs)
+            const float* hr[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int tap = min(tg + 4 * i, 8), ky = tap / 3, kx = tap - 3 * ky;
+                hr[i] = s_h + (ci * 3 + (y + ky + 2) % 3) * (Wr + 1) + kx;          // filter row ky reads image row y + ky - 1
+            }
+            for (int xx = 0; xx < W; xx += 4) {
+                const float4 g0 = *reinterpret_cast<const float4*>(s_g + xx), g1 = *reinterpret_cast<const float4*>(s_g + W + xx);
+                const float4 g2 = *reinterpret_cast<const float4*>(s_g + 2 * W + xx), g3 = *reinterpret_cast<const float4*>(s_g + 3 * W + xx);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float h0 = hr[i][xx], h1 = hr[i][xx + 1], h2 = hr[i][xx + 2], h3 = hr[i][xx + 3];
+                    acc[i][0] = fmaf(g0.x, h0, fmaf(g0.y, h1, fmaf(g0.z, h2, fmaf(g0.w, h3, acc[i][0]))));
+                    acc[i][1] = fmaf(g1.x, h0, fmaf(g1.y, h1, fmaf(g1.z, h2, fmaf(g1.w, h3, acc[i][1]))));
+                    acc[i][2] = fmaf(g2.x, h0, fmaf(g2.y, h1, fmaf(g2.z, h2, fmaf(g2.w, h3, acc[i][2]))));
+                    acc[i][3] = fmaf(g3.x, h0, fmaf(g3.y, h1, fmaf(g3.z, h2, fmaf(g3.w, h3, acc[i][3]))));
+                }
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int tap = tg + 4 * i;
             if (tap < 9) {
                 const int ky = tap / 3, kx = tap - 3 * ky;
-                const float* hr = s_h + (ci * 3 + ky) * (Wr + 1) + kx;
+                const float* hr = s_h + (ci * 3 + (y + ky + 2) % 3) * (Wr + 1) + kx;
                 for (int xx = 0; xx < W; ++xx) {
                     const float hv = hr[xx];
                     acc[i][0] = fmaf(s_g[xx], hv, acc[i][0]); acc[i][1] = fmaf(s_g[W + xx], hv, acc[i][1]);
                     acc[i][2] = fmaf(s_g[2 * W + xx], hv, acc[i][2]); acc[i][3] = fmaf(s_g[3 * W + xx], hv, acc[i][3]);
                 }
             }
+        }
         }
         if (threadIdx.x < 4) for (int xx = 0; xx < W; ++xx) accb += s_g[threadIdx.x * W + xx];
     }
@@ -612,8 +704,17 @@ extern "C" int ps_conv_first_wgrad(const void* dh_planes, const float* x, const 
     const long long P = (long long)n_img * (H + 4) * (W + 4);
     const uint16_t* hi = reinterpret_cast<const uint16_t*>(dh_planes);
     const uint16_t* lo = precision == 3 ? hi + P * 64 : nullptr;
-    const size_t smem = (size_t)Cin * ksize * (W + ksize - 1) * sizeof(float);
     const int band = 16;
+    if (W % 4 == 0) {
+        const size_t smem4 = (size_t)Cin * ksize * ((((W + ksize - 1) + 3) & ~3) + 4) * sizeof(float);
+        const dim3 grid((H + band - 1) / band, n_img);
+        if (ksize == 5) conv_first_wgrad4_kernel<5><<<grid, 256, smem4, (cudaStream_t)stream>>>(hi, lo, x, x8, dW, Cin, H, W, band, scale);
+        else conv_first_wgrad4_kernel<3><<<grid, 256, smem4, (cudaStream_t)stream>>>(hi, lo, x, x8, dW, Cin, H, W, band, scale);
+        PS_COUNT_LAUNCH();
+        PS_LAUNCH_CHECK();
+        return PS_OK;
+    }
+    const size_t smem = (size_t)Cin * ksize * (W + ksize - 1) * sizeof(float);
     conv_first_wgrad_kernel<<<dim3((H + band - 1) / band, n_img), 256, smem, (cudaStream_t)stream>>>(hi, lo, x, x8, dW, Cin, H, W, ksize, band, scale);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
