@@ -346,6 +346,9 @@ int ps_planes_colsum(const void* planes, float* out, int n_img, int H, int W, in
 int ps_conv_first_wgrad(const void* dh_planes, const float* x, const unsigned char* x8, float* dW, int n_img, int Cin, int H, int W,
                         int ksize, int precision, float scale, void* stream);
 int ps_conv3x3_final_wgrad(const float* g_o, const float* h, float* dW, float* db, int n_img, int H, int W, void* stream);
+/* ... with h as the padded split planes the tensor-core layers write (precision 2: hi plane only, 3: hi + lo) */
+int ps_conv3x3_final_wgrad_planes(const float* g_o, const void* h_planes, int precision, float* dW, float* db, int n_img, int H, int W,
+                                  void* stream);
 int ps_colsum(const float* X, float* out, long long M, long long N, float scale, void* stream);
 int ps_nhwc_to_split_scaled(const float* tokens, int ld, const float* scale, void* planes, int n_img, int H, int W, int precision,
                             void* stream);

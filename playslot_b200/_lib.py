@@ -69,6 +69,7 @@ SIGNATURES = {
     "ps_planes_colsum": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "ps_conv_first_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "ps_conv3x3_final_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "ps_conv3x3_final_wgrad_planes": (c_i, [c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_f]),
     "ps_colsum": (c_i, [c_f, c_f, ctypes.c_longlong, ctypes.c_longlong, c_fl, c_f]),
     "ps_nhwc_to_split_scaled": (c_i, [c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "ps_tblock_stack": (c_i, [c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_fl] + [c_f] * 10 + [c_f, c_f]),

@@ -507,8 +507,9 @@ __global__ void __launch_bounds__(256) conv_first_wgrad4_kernel(const uint16_t* 
 
 // last decoder convolution (64 -> 4, 3x3): dW[co][ci][ky][kx] += sum g[img][co][y][x] h[img][ci][y+ky-1][x+kx-1]; db[co] += sum g.
 // grid (n_img); thread = (ci 0..63, tap group 0..3 handling taps {g, g+4, g+8}); rows streamed through shared memory.
-__global__ void __launch_bounds__(256) conv3x3_final_wgrad_kernel(const float* __restrict__ g_o, const float* __restrict__ h, float* __restrict__ dW,
-                                                                 float* __restrict__ db, int H, int W) {
+__global__ void __launch_bounds__(256) conv3x3_final_wgrad_kernel(const float* __restrict__ g_o, const float* __restrict__ h,
+                                                                 const uint16_t* __restrict__ h_hi, const uint16_t* __restrict__ h_lo,
+                                                                 float* __restrict__ dW, float* __restrict__ db, int H, int W) {
     extern __shared__ float sm[];
     const int img = blockIdx.x, Wr = W + 2;
     float* s_h = sm;                                 // [64][3][Wr + 1]
@@ -527,9 +528,19 @@ __global__ void __launch_bounds__(256) conv3x3_final_wgrad_kernel(const float* _
         for (int yy = (y == 0 ? -1 : y + 1); yy <= y + 1; ++yy) {
             const int slot = (yy + 3) % 3;
             const bool row_ok = yy >= 0 && yy < H;
-            for (int i = threadIdx.x; i < 64 * Wr; i += 256) {
-                const int c = i / Wr, col = i - c * Wr, xx = col - 1;
-                s_h[(c * 3 + slot) * (Wr + 1) + col] = (row_ok && xx >= 0 && xx < W) ? h[((size_t)img * 64 + c) * HW + (size_t)yy * W + xx] : 0.f;
+            if (h) {
+                for (int i = threadIdx.x; i < 64 * Wr; i += 256) {
+                    const int c = i / Wr, col = i - c * Wr, xx = col - 1;
+                    s_h[(c * 3 + slot) * (Wr + 1) + col] = (row_ok && xx >= 0 && xx < W) ? h[((size_t)img * 64 + c) * HW + (size_t)yy * W + xx] : 0.f;
+                }
+            } else {
+                // saved activation as padded split planes [img][(H + 4)(W + 4)][64]: consecutive threads read consecutive channels of a
+                // position (coalesced 2-byte loads of the hi and lo rows); the zero border of the planes supplies the padding columns
+                const size_t prow = (((size_t)img * (H + 4) + yy + 2) * (W + 4) + 1) * 64;      // column -1 of image row yy
+                for (int i = threadIdx.x; i < 64 * Wr; i += 256) {
+                    const int col = i >> 6, c = i & 63;
+                    s_h[(c * 3 + slot) * (Wr + 1) + col] = row_ok ? plane_val(h_hi, h_lo, prow + (size_t)col * 64 + c) : 0.f;
+                }
             }
         }
         for (int i = threadIdx.x; i < 4 * W; i += 256) s_g[i] = g_o[((size_t)img * 4 + i / W) * HW + (size_t)y * W + (i % W)];
@@ -755,14 +766,32 @@ extern "C" int ps_conv_first_wgrad(const void* dh_planes, const float* x, const 
 }
 
 // dW (4, 64, 3, 3) += sum g_o * shifted h, db (4) += sum g_o; g_o (n_img, 4, H, W), h (n_img, 64, H, W) fp32 NCHW; zeroed by the caller
+static int conv3x3_final_wgrad_run(const float* g_o, const float* h, const void* h_planes, int precision, float* dW, float* db, int n_img,
+                                   int H, int W, void* stream);
+
 extern "C" int ps_conv3x3_final_wgrad(const float* g_o, const float* h, float* dW, float* db, int n_img, int H, int W, void* stream) {
-    PS_REQUIRE(g_o && h && dW, "ps_conv3x3_final_wgrad: null pointer");
+    PS_REQUIRE(h, "ps_conv3x3_final_wgrad: null pointer");
+    return conv3x3_final_wgrad_run(g_o, h, nullptr, 0, dW, db, n_img, H, W, stream);
+}
+
+// the same with the saved activation h given as the padded split planes of the tensor-core layers (precision 2: hi plane only)
+extern "C" int ps_conv3x3_final_wgrad_planes(const float* g_o, const void* h_planes, int precision, float* dW, float* db, int n_img, int H,
+                                             int W, void* stream) {
+    PS_REQUIRE(h_planes && (precision == 2 || precision == 3), "ps_conv3x3_final_wgrad_planes: planes with precision 2 | 3 required");
+    return conv3x3_final_wgrad_run(g_o, nullptr, h_planes, precision, dW, db, n_img, H, W, stream);
+}
+
+static int conv3x3_final_wgrad_run(const float* g_o, const float* h, const void* h_planes, int precision, float* dW, float* db, int n_img,
+                                   int H, int W, void* stream) {
+    PS_REQUIRE(g_o && dW, "ps_conv3x3_final_wgrad: null pointer");
     if (n_img == 0) return PS_OK;
     PS_REQUIRE(n_img <= 65535 && W <= 256, "ps_conv3x3_final_wgrad: at most 65535 images, W <= 256");
     const size_t smem = (size_t)(64 * 3 * (W + 3) + 4 * W) * sizeof(float);
     static PsSmemConfig smem_cfg = {};
     if (smem > 48 * 1024) PS_CUDA(ps_ensure_smem(conv3x3_final_wgrad_kernel, smem, smem_cfg));
-    conv3x3_final_wgrad_kernel<<<n_img, 256, smem, (cudaStream_t)stream>>>(g_o, h, dW, db, H, W);
+    const uint16_t* hi = reinterpret_cast<const uint16_t*>(h_planes);
+    const uint16_t* lo = (hi && precision == 3) ? hi + (long long)n_img * (H + 4) * (W + 4) * 64 : nullptr;
+    conv3x3_final_wgrad_kernel<<<n_img, 256, smem, (cudaStream_t)stream>>>(g_o, h, hi, lo, dW, db, H, W);
     PS_COUNT_LAUNCH();
     PS_LAUNCH_CHECK();
     return PS_OK;

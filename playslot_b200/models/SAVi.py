@@ -487,7 +487,7 @@ class SAVi(nn.Module):
             G = ops.linear(sl, wsum)                                           # (n_img, ncls^2 * C1)
             n_img = (m1 - m0) * S
             if use_tc:
-                planes_last = keep == "planes" and prec == 3 and S <= 16
+                planes_last = bool(keep) and prec == 3 and S <= 16      # both training paths: h4 stays in the split-plane format
                 if keep:
                     acts = [ops.conv_tc_workspace(n_img, H, W, slots.device) for _ in range(4 if planes_last else 3)]      # h1, h2, h3 (, h4)
                 else:
@@ -563,13 +563,13 @@ class SAVi(nn.Module):
             amax = g_o.abs().max().clamp_min(1e-30)
             g_scale = torch.exp2(-torch.floor(torch.log2(amax))).reshape(1)
             if isinstance(h, tuple):                                                               # ("planes", h4 as split planes)
-                assert wg is None, "the weight gradient of the final convolution needs the fp32 activation (keep=True)"
                 ops.dec_final_dgrad_planes(g_o, wfin, h[1], ga, n_img, H, W, prec, g_scale)
             else:
                 ops.dec_final_dgrad(g_o, wfin, h, ga, prec, g_scale)                               # through conv3x3 and relu(h4)
             inv = 1.0 / g_scale
             if wg is not None:
-                dwf, dbf = ops.conv3x3_final_wgrad(g_o, h)
+                dwf, dbf = (ops.conv3x3_final_wgrad_planes(g_o, h[1], n_img, H, W, prec) if isinstance(h, tuple)
+                            else ops.conv3x3_final_wgrad(g_o, h))
                 wg["final"][0] += dwf; wg["final"][1] += dbf
                 wg["conv"][2][0] += ops.conv5x5_planes_wgrad(ga, acts[2], n_img, H, W, prec, prec) * inv     # block 3: h3 -> h4
                 wg["conv"][2][1] += ops.planes_colsum(ga, n_img, H, W, prec) * inv

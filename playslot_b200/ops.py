@@ -1016,6 +1016,18 @@ def conv3x3_final_wgrad(g_o, h):
     return dW, db
 
 
+def conv3x3_final_wgrad_planes(g_o, h_planes, n, H, W, precision):
+    """ conv3x3_final_wgrad with h as padded split planes """
+    lib = _lib.load()
+    _req(g_o, "g_o")
+    dW = torch.zeros(4, 64, 3, 3, device=g_o.device, dtype=torch.float32)
+    db = torch.zeros(4, device=g_o.device, dtype=torch.float32)
+    with _timed("conv3x3_final_wgrad"):
+        st = lib.ps_conv3x3_final_wgrad_planes(_ptr(g_o), _ptr(h_planes), int(precision), _ptr(dW), _ptr(db), n, H, W, _stream())
+    _lib.check(st, "ps_conv3x3_final_wgrad_planes")
+    return dW, db
+
+
 def colsum(x2d, scale=1.0):
     """ (M, N) -> (N,) column sums times scale """
     lib = _lib.load()
