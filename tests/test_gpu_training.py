@@ -167,6 +167,8 @@ def test_decode_data_gradient(case, gscale):
     with torch.no_grad():
         _, _, _, saved = savi._decode_impl(slots.to(DEV), keep=True)
     _, _, acts, h4 = saved[0]
+    if isinstance(h4, tuple):                   # ("planes", ...): the last block's activation is kept in the split-plane format too
+        h4 = _unpack_split(h4[1], M * S, H, W)
     mk = [(_unpack_split(a, M * S, H, W) > 0).double() for a in acts] + [(h4 > 0).double()]
     sd64 = {k: v.double().to(DEV) for k, v in ssd.items()}
     sr = slots.clone().double().to(DEV).requires_grad_(True)
