@@ -460,9 +460,11 @@ class SAVi(nn.Module):
         return recon, (recons, masks)
 
     def _decode_impl(self, slots, keep):
-        """ forward kernels; with keep=True the per-layer activations needed by the backward are returned (the last block's as fp32
-        NCHW: the weight gradient of the final convolution reads it); keep="planes": data gradient only, the last block's activation
-        stays in the split-plane format and the tensor-core compositing kernel is used """
+        """ forward kernels; with keep (True: SAVi training, "planes": predictor training) the per-layer activations the backward
+        needs are returned.  In the fp16x3 mode the last block's activation stays in the split-plane format as well -- saved as
+        ("planes", tensor) -- and the 3x3 convolution + compositing run on the tensor cores as in inference; the final data gradient
+        takes its ReLU mask, and SAVi training its final weight gradient, from those planes.  Single-product modes keep an fp32 NCHW
+        copy and the FFMA compositing kernel. """
         M, S, D = slots.shape
         H, W = self.decoder_resolution
         dec = self.decoder
