@@ -573,23 +573,41 @@ static int dec_final_dgrad_run(const float* g_o, const float* w_packed, const fl
 // class of g[img][y][x][c] (g: fp32 NHWC tokens, already masked by relu').  One CTA per image.
 __global__ void __launch_bounds__(256) dec_expand_bwd_kernel(const float* __restrict__ g, float* __restrict__ dG, const float* __restrict__ g_scale,
                                                             int H, int W, int pad) {
+    // thread = (4 consecutive channels, column lane 0..15): float4 loads, the columns x = lane, lane + 16, ... of every row; interior
+    // pixels of interior rows (most of the image) accumulate in registers, the border classes go through shared-memory atomics
+    // (the first version walked the image with one 4-byte load and one dependent add per step: 470 us per 256 images)
     extern __shared__ float s_acc[];                 // [ncls*ncls][64]
     const int ncls = 2 * pad + 1;
     for (int i = threadIdx.x; i < ncls * ncls * 64; i += 256) s_acc[i] = 0.f;
     __syncthreads();
     const int img = blockIdx.x;
-    const int c = threadIdx.x & 63, ysub = threadIdx.x >> 6;
-    const float* gi = g + (size_t)img * H * W * 64;
-    for (int y = ysub; y < H; y += 4) {
+    const int c4 = (threadIdx.x & 15) * 4, xl = threadIdx.x >> 4;
+    const float* gi = g + (size_t)img * H * W * 64 + c4;
+    float4 mid_mid = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < H; ++y) {
         const int cy = y < pad ? y : (y > H - 1 - pad ? 2 * pad - (H - 1 - y) : pad);
-        float mid = 0.f;
-        for (int x = 0; x < W; ++x) {
-            const float v = gi[((size_t)y * W + x) * 64 + c];
-            if (x < pad) atomicAdd(&s_acc[(cy * ncls + x) * 64 + c], v);
-            else if (x > W - 1 - pad) atomicAdd(&s_acc[(cy * ncls + 2 * pad - (W - 1 - x)) * 64 + c], v);
-            else mid += v;
+        float4 mid = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int x = xl; x < W; x += 16) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(gi + ((size_t)y * W + x) * 64));
+            if (x < pad || x > W - 1 - pad) {
+                const int cx = x < pad ? x : 2 * pad - (W - 1 - x);
+                float* d = &s_acc[(cy * ncls + cx) * 64 + c4];
+                atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w);
+            } else {
+                mid.x += v.x; mid.y += v.y; mid.z += v.z; mid.w += v.w;
+            }
         }
-        atomicAdd(&s_acc[(cy * ncls + pad) * 64 + c], mid);
+        if (cy == pad) {
+            mid_mid.x += mid.x; mid_mid.y += mid.y; mid_mid.z += mid.z; mid_mid.w += mid.w;
+        } else {
+            float* d = &s_acc[(cy * ncls + pad) * 64 + c4];
+            atomicAdd(d, mid.x); atomicAdd(d + 1, mid.y); atomicAdd(d + 2, mid.z); atomicAdd(d + 3, mid.w);
+        }
+    }
+    {
+        float* d = &s_acc[(pad * ncls + pad) * 64 + c4];
+        atomicAdd(d, mid_mid.x); atomicAdd(d + 1, mid_mid.y); atomicAdd(d + 2, mid_mid.z); atomicAdd(d + 3, mid_mid.w);
     }
     __syncthreads();
     const float inv = g_scale ? 1.0f / *g_scale : 1.0f;

@@ -491,7 +491,7 @@ class SAVi(nn.Module):
             if use_tc:
                 planes_last = bool(keep) and prec == 3 and S <= 16      # both training paths: h4 stays in the split-plane format
                 if keep:
-                    acts = [ops.conv_tc_workspace(n_img, H, W, slots.device) for _ in range(4 if planes_last else 3)]      # h1, h2, h3 (, h4)
+                    acts = [self._acquire_train_ws(n_img, H, W, slots.device) for _ in range(4 if planes_last else 3)]     # h1, h2, h3 (, h4)
                 else:
                     a = self._tc_workspace("dec_a", n_img, H, W, slots.device)
                     b = self._tc_workspace("dec_b", n_img, H, W, slots.device)
@@ -527,6 +527,18 @@ class SAVi(nn.Module):
         if len(recon_l) == 1:
             return recon_l[0], recons_l[0], masks_l[0], saved
         return torch.cat(recon_l), torch.cat(recons_l), torch.cat(masks_l), saved
+
+    def _acquire_train_ws(self, n_img, H, W, device):
+        """ activation planes kept for a backward pass: taken from a pool that `_decode_backward` refills, so a training step does
+        not zero-fill ~10 GB of fresh workspaces (the producers keep the borders zero, like in the cached inference workspaces) """
+        pool = self.__dict__.setdefault("_train_ws_pool", {}).setdefault((n_img, H, W, str(device)), [])
+        return pool.pop() if pool else ops.conv_tc_workspace(n_img, H, W, device)
+
+    def _release_train_ws(self, tensors, n_img, H, W, device):
+        pool = self.__dict__.setdefault("_train_ws_pool", {}).setdefault((n_img, H, W, str(device)), [])
+        for t in tensors:
+            if all(t is not q for q in pool):
+                pool.append(t)
 
     def _tc_weight_flipped(self, block):
         """ packed weights of the data gradient: W'[ci][co][ky][kx] = W[co][ci][K-1-ky][K-1-kx] """
@@ -592,6 +604,9 @@ class SAVi(nn.Module):
                 dws, _ = ops.linear_wgrad(dG, f32c(slots[m0:m1].reshape(n_img, self.slot_dim)), want_bias=False)
                 wg["wsum"] += dws
                 wg["P_hwc"] += ops.colsum(tokens.view(n_img, H * W * 64)).view(H * W, 64) * inv
+        for m0, m1, acts, h in saved:                      # the activations are consumed: hand their buffers back to the pool
+            extra = [h[1]] if isinstance(h, tuple) else []
+            self._release_train_ws(list(acts) + extra, (m1 - m0) * S, H, W, recons.device)
         if wg is None:
             return out
         params = []
